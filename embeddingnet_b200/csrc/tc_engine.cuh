@@ -1,0 +1,328 @@
+// Tensor-core distance engine for sm_100a: C = A . B^T as a tcgen05/TMEM GEMM fed by TMA, with the FP32
+// inputs split into two TF32 planes (hi, lo) so that hi*hi + hi*lo + lo*hi reproduces the FP32 product to
+// ~2^-21 ("3xTF32").  The 128x128 accumulator tile never leaves the SM: a pluggable epilogue functor consumes it
+// straight out of TMEM (label masks, per-anchor reductions, top-k, ...).
+//
+// Replaces, for the large shapes, the arithmetic the reference delegates to
+//   sklearn.metrics.pairwise_distances      (embedding_net/datagenerators.py:219)
+//   sklearn.neighbors.KNeighborsClassifier  (embedding_net/models.py:136-138)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// (each owns one 32-lane TMEM quarter).  Three mbarrier pipelines: smem full/empty, TMEM full/empty.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace en {
+namespace tc {
+
+constexpr int BM = 128;            // rows of A per tile (UMMA M)
+constexpr int BN = 128;            // rows of B per tile (UMMA N)
+constexpr int BK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;          // tf32: 32 bytes per MMA
+constexpr int STAGES = 3;
+constexpr int NUM_ACC = 2;         // TMEM accumulator double buffer
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KiB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // Ahi, Alo, Bhi, Blo
+// Each accumulator buffer holds TWO 128-column tiles: the dominant hi*hi sum and, separately, the small cross
+// terms hi*lo + lo*hi.  The tensor core truncates (does not round) when it adds into the FP32 accumulator, so
+// the bias grows with the number of MMAs chained into one cell; keeping the cross terms apart cuts that chain
+// from 3*d/8 to d/8 links for the large term (measured on B200: 6e-6 -> ~2e-6 relative on all-positive sums).
+constexpr int ACC_COLS = 2 * BN;                   // main | cross
+constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 512 = all of TMEM (1 CTA/SM anyway, by smem)
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(BN == BM, "A and B tiles share TILE_BYTES");
+
+struct Shape {
+  int64_t M;        // rows of A (anchors / queries)
+  int64_t N;        // rows of B (candidates / bank rows)
+  int kblocks;      // ceil(d / BK); planes are zero padded to kblocks*BK columns
+  int tiles_m;
+  int tiles_n;
+  int n_splits;     // column-tile ranges per row tile (work item = (row tile, range))
+  int tiles_per_split;
+  int passes;       // 3 = hi*hi+hi*lo+lo*hi (fp32 faithful), 1 = hi*hi only (plain TF32; diagnostics)
+};
+
+struct Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[NUM_ACC];
+  uint64_t tmem_empty[NUM_ACC];
+  uint32_t tmem_base;
+};
+
+// Epilogue concept:
+//   struct Ep { struct Params; struct Row;
+//     static __device__ void item_begin(const Params&, Row&, int64_t row, bool row_valid, int tile_m, int split);
+//     static __device__ void chunk(const Params&, Row&, int64_t row, bool row_valid, int64_t col0, const float (&dot)[32]);
+//     static __device__ void tile_end(const Params&, Row&, int64_t row, bool row_valid, int tile_n);
+//     static __device__ void item_end(const Params&, Row&, int64_t row, bool row_valid, int tile_m, int split); };
+// `chunk` receives dot[j] = <A[row], B[col0 + j]> for 32 consecutive candidate rows (columns past N hold 0).
+
+template <class Ep>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const Shape shape, const typename Ep::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tile bases.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = shape.tiles_m * shape.n_splits;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_a_lo);
+    ptx::prefetch_tmap(&tm_b_hi);
+    ptx::prefetch_tmap(&tm_b_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      ptx::mbar_init(&bars->tmem_full[a], 1);
+      ptx::mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile_m = item / shape.n_splits;
+        const int split = item % shape.n_splits;
+        const int nt0 = split * shape.tiles_per_split;
+        const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
+        for (int nt = nt0; nt < nt1; ++nt) {
+          for (int kb = 0; kb < shape.kblocks; ++kb) {
+            ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * STAGE_BYTES;
+            const bool lo = shape.passes > 1;
+            ptx::mbar_arrive_expect_tx(&bars->full[stage], lo ? STAGE_BYTES : 2 * TILE_BYTES);
+            ptx::tma_load_2d(&tm_a_hi, &bars->full[stage], st + 0 * TILE_BYTES, kb * BK, tile_m * BM);
+            ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st + 2 * TILE_BYTES, kb * BK, nt * BN);
+            if (lo) {
+              ptx::tma_load_2d(&tm_a_lo, &bars->full[stage], st + 1 * TILE_BYTES, kb * BK, tile_m * BM);
+              ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + 3 * TILE_BYTES, kb * BK, nt * BN);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item % shape.n_splits;
+        const int nt0 = split * shape.tiles_per_split;
+        const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
+        for (int nt = nt0; nt < nt1; ++nt, ++acc_it) {
+          const uint32_t acc = acc_it % NUM_ACC;
+          const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
+          ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * ACC_COLS;   // hi*hi
+          const uint32_t tmem_x = tmem_d + BN;                   // hi*lo + lo*hi
+          for (int kb = 0; kb < shape.kblocks; ++kb) {
+            ptx::mbar_wait(&bars->full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
+            const uint64_t a_lo = ptx::make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
+            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
+            const uint64_t b_lo = ptx::make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 bytes along K inside the 128B swizzle row: +2 in the (addr>>4) field
+              const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
+              if (shape.passes > 1) {
+                ptx::mma_tf32_ss(tmem_x, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                ptx::mma_tf32_ss(tmem_x, a_hi + koff, b_lo + koff, idesc, 1);
+                ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+              } else {
+                ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+              }
+            }
+            ptx::mma_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          ptx::mma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM -> registers)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are reachable from this warp
+    uint32_t acc_it = 0;
+    typename Ep::Row rs;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile_m = item / shape.n_splits;
+      const int split = item % shape.n_splits;
+      const int nt0 = split * shape.tiles_per_split;
+      const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
+      const int64_t row = static_cast<int64_t>(tile_m) * BM + quarter * 32 + lane;
+      const bool row_valid = row < shape.M;
+      Ep::item_begin(ep, rs, row, row_valid, tile_m, split);
+      for (int nt = nt0; nt < nt1; ++nt, ++acc_it) {
+        const uint32_t acc = acc_it % NUM_ACC;
+        const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
+        ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float dot[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, dot);
+          if (shape.passes > 1) {
+            float cross[32];
+            ptx::tmem_ld_32x32(taddr + BN + c * 32, cross);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot[j] += cross[j];
+          } else {
+            ptx::tmem_ld_wait();
+          }
+          Ep::chunk(ep, rs, row, row_valid, static_cast<int64_t>(nt) * BN + c * 32, dot);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
+        Ep::tile_end(ep, rs, row, row_valid, nt);
+      }
+      Ep::item_end(ep, rs, row, row_valid, tile_m, split);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a split plane: `rows` x `cols_padded` fp32, row-major, box = (BK cols, 128 rows), 128B swizzle.
+// Rows past `rows` are zero-filled by TMA, so ragged M/N need no host padding.
+inline int make_plane_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols_padded) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols_padded), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols_padded) * 4};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes) {
+  Shape s;
+  s.M = M;
+  s.N = N;
+  s.kblocks = (d + BK - 1) / BK;
+  s.tiles_m = static_cast<int>((M + BM - 1) / BM);
+  s.tiles_n = static_cast<int>((N + BN - 1) / BN);
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > s.tiles_n) n_splits = s.tiles_n;
+  s.tiles_per_split = (s.tiles_n + n_splits - 1) / n_splits;
+  s.n_splits = (s.tiles_n + s.tiles_per_split - 1) / s.tiles_per_split;
+  s.passes = passes;
+  return s;
+}
+
+template <class Ep>
+inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                          const CUtensorMap& b_lo, const Shape& shape, const typename Ep::Params& ep, int num_sms,
+                          cudaStream_t stream) {
+  static bool attr_set = false;  // per (Ep) instantiation
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(dist_gemm_kernel<Ep>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int items = shape.tiles_m * shape.n_splits;
+  const int grid = items < num_sms ? items : num_sms;
+  dist_gemm_kernel<Ep><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, shape, ep);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- operand prep
+// x (rows x d, leading dimension ldx) -> hi/lo TF32 planes (rows x dpad, zero padded) + squared row norms.
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in TF32, so the tensor core sees them
+// unmodified.  One warp per row; float4 loads when the row is 16B aligned.
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
+                                    float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norms) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float* hr = hi + row * dpad;
+  float* lr = lo + row * dpad;
+  double acc = 0.0;
+  for (int c = lane; c < dpad; c += 32) {
+    float v = c < d ? xr[c] : 0.0f;
+    float h = to_tf32(v);
+    float l = to_tf32(v - h);
+    hr[c] = h;
+    lr[c] = l;
+    acc += static_cast<double>(v) * static_cast<double>(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && norms) norms[row] = static_cast<float>(acc);
+}
+
+inline cudaError_t launch_split(const float* x, int64_t rows, int d, int64_t ldx, int dpad, float* hi, float* lo,
+                                float* norms, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  const int threads = 256;
+  const int64_t blocks = (rows * 32 + threads - 1) / threads;
+  split_planes_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, rows, d, ldx, dpad, hi, lo, norms);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace en
