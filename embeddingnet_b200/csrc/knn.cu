@@ -1,0 +1,514 @@
+// Encoding-bank nearest neighbours: the scan the reference leaves to scikit-learn's brute-force
+// KNeighborsClassifier (embedding_net/models.py:15,58,136-138) and to the undefined `calculate_distances` + np.argmin
+// of EmbeddingNet.predict (embedding_net/models.py:123-124).
+//
+//   stage 1a  en_knn_shard_topk : tcgen05 3xTF32 distance GEMM (queries x bank shard) with a per-query running
+//                                 top-(k+slack) kept in registers by the epilogue thread that owns the query row;
+//   stage 1b  en_knn_stream_topk: for a handful of queries (the reference's one-image-per-call pattern) a CUDA-core
+//                                 fp32 streaming scan bounded by HBM bandwidth;
+//   stage 2   exact re-rank     : the surviving candidates are re-evaluated as float64 sum (q-b)^2 and ordered by
+//                                 (distance, global id) -- lowest id wins ties, shard-invariant by construction;
+//   merge / vote / accuracy     : k-way merge of per-shard lists (after the NCCL all-gather), majority vote
+//                                 (KNeighborsClassifier.predict), top-1 / top-5 tallies (models.py:144-161).
+#include "common.cuh"
+#include "tc_engine.cuh"
+
+namespace en {
+namespace {
+
+constexpr float kInf = 3.0e38f;
+
+struct Cand {
+  float t;      // ranking proxy, ascending = nearer
+  int32_t idx;  // row inside the shard, -1 = empty
+};
+
+// sorted insert into a register-resident list (ascending by t; arrival order breaks ties, and rows arrive in
+// ascending id order, so equal proxies keep the lower id first)
+template <int KC>
+__device__ __forceinline__ void list_insert(float (&v)[KC], int32_t (&id)[KC], float t, int32_t i) {
+  v[KC - 1] = t;
+  id[KC - 1] = i;
+#pragma unroll
+  for (int q = KC - 1; q > 0; --q) {
+    if (v[q] < v[q - 1]) {
+      const float tv = v[q]; v[q] = v[q - 1]; v[q - 1] = tv;
+      const int32_t ti = id[q]; id[q] = id[q - 1]; id[q - 1] = ti;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- stage 1a: tensor-core scan epilogue
+template <int KC>
+struct EpTopK {
+  struct Params {
+    const float* bank_norms;
+    const int32_t* bank_labels;   // may be null
+    const int32_t* query_labels;  // may be null (then no exclusion)
+    Cand* lists;                  // [Q][n_lists][KC]
+    int64_t n_bank;
+    int n_lists;
+  };
+  struct Row {
+    float v[KC];
+    int32_t id[KC];
+    int32_t qlabel;
+    bool exclude;
+  };
+  static constexpr int kSmemBytes = 0;
+  static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int) {
+#pragma unroll
+    for (int q = 0; q < KC; ++q) {
+      r.v[q] = kInf;
+      r.id[q] = -1;
+    }
+    r.exclude = p.query_labels != nullptr && p.bank_labels != nullptr;
+    r.qlabel = (r.exclude && valid) ? p.query_labels[row] : 0;
+  }
+  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int64_t col0,
+                               const float (&dot)[32]) {
+    if (col0 >= p.n_bank) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t c = col0 + j;
+      if (c < p.n_bank) {
+        const float t = fmaf(-2.f, dot[j], __ldg(&p.bank_norms[c]));
+        if (t < r.v[KC - 1]) {
+          if (!r.exclude || __ldg(&p.bank_labels[c]) != r.qlabel) list_insert<KC>(r.v, r.id, t, static_cast<int32_t>(c));
+        }
+      }
+    }
+  }
+  static __device__ void tile_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int) {}
+  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
+    if (!valid) return;
+    Cand* out = p.lists + (row * p.n_lists + split) * KC;
+#pragma unroll
+    for (int q = 0; q < KC; ++q) out[q] = Cand{r.v[q], r.id[q]};
+  }
+};
+
+// ---------------------------------------------------------------- stage 1b: HBM-bound streaming scan
+// One warp per bank row at a time; the (<= 8) queries live in shared memory; lane q keeps query q's running list.
+template <int KC>
+__global__ void __launch_bounds__(256)
+knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank, int64_t n_bank,
+                  int64_t rows_per_warp, Cand* __restrict__ lists, int n_lists) {
+  extern __shared__ float qs[];  // [Q][d]
+  for (int i = threadIdx.x; i < Q * d; i += blockDim.x) qs[i] = queries[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t r0 = gwarp * rows_per_warp;
+  const int64_t r1 = min(r0 + rows_per_warp, n_bank);
+  float v[KC];
+  int32_t id[KC];
+#pragma unroll
+  for (int q = 0; q < KC; ++q) {
+    v[q] = kInf;
+    id[q] = -1;
+  }
+  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(bank) & 15) == 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* b = bank + r * d;
+    float s[EN_KNN_STREAM_MAX_Q];
+#pragma unroll
+    for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) s[q] = 0.f;
+    if (vec) {
+      for (int c = lane * 4; c < d; c += 128) {
+        const float4 bv = __ldcs(reinterpret_cast<const float4*>(b + c));  // streamed once: evict-first
+#pragma unroll
+        for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
+          if (q < Q) {
+            const float4 qv = *reinterpret_cast<const float4*>(qs + q * d + c);
+            float t;
+            t = qv.x - bv.x; s[q] = fmaf(t, t, s[q]);
+            t = qv.y - bv.y; s[q] = fmaf(t, t, s[q]);
+            t = qv.z - bv.z; s[q] = fmaf(t, t, s[q]);
+            t = qv.w - bv.w; s[q] = fmaf(t, t, s[q]);
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) {
+        const float bv = b[c];
+#pragma unroll
+        for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
+          if (q < Q) {
+            const float t = qs[q * d + c] - bv;
+            s[q] = fmaf(t, t, s[q]);
+          }
+        }
+      }
+    }
+    float mine = kInf;
+#pragma unroll
+    for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
+      if (q < Q) {
+        const float tot = warp_sum(s[q]);
+        if (lane == q) mine = tot;
+      }
+    }
+    if (lane < Q && mine < v[KC - 1]) list_insert<KC>(v, id, mine, static_cast<int32_t>(r));
+  }
+  if (lane < Q && gwarp < n_lists) {
+    Cand* out = lists + (static_cast<int64_t>(lane) * n_lists + gwarp) * KC;
+#pragma unroll
+    for (int q = 0; q < KC; ++q) out[q] = Cand{v[q], id[q]};
+  }
+}
+
+// ---------------------------------------------------------------- stage 2: exact re-rank
+// One warp per query.  Extract the KC best proxies over all lists in (t, idx) order, re-evaluate them exactly,
+// order by (d2, global id), emit the first k.
+template <int KC>
+__global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, int d,
+                                  const float* __restrict__ bank, int64_t id_offset, const Cand* __restrict__ lists,
+                                  int n_lists, int k, double* __restrict__ d2_out, int64_t* __restrict__ ids_out) {
+  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  const Cand* mine = lists + q * n_lists * KC;
+  const int total = n_lists * KC;
+  float last_t = -kInf;
+  int32_t last_i = -1;
+  double my_d2 = 1e300;   // lane r holds the r-th extracted candidate
+  int32_t my_idx = -1;
+  for (int r = 0; r < KC; ++r) {
+    float bt = kInf;
+    int32_t bi = 0x7fffffff;
+    for (int c = lane; c < total; c += 32) {
+      const Cand x = mine[c];
+      if (x.idx < 0) continue;
+      const bool after = x.t > last_t || (x.t == last_t && x.idx > last_i);
+      if (after && (x.t < bt || (x.t == bt && x.idx < bi))) {
+        bt = x.t;
+        bi = x.idx;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ot < bt || (ot == bt && oi < bi)) {
+        bt = ot;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) break;  // lists exhausted (warp-uniform)
+    last_t = bt;
+    last_i = bi;
+    const float* a = queries + q * d;
+    const float* b = bank + static_cast<int64_t>(bi) * d;
+    double acc = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
+      acc += t * t;
+    }
+    acc = warp_sum(acc);
+    if (lane == r) {
+      my_d2 = acc;
+      my_idx = bi;
+    }
+  }
+  // rank by (d2, idx) among the KC (<= 32) extracted; lanes >= KC hold sentinels
+  int rank = 0;
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const double od = __shfl_sync(0xffffffffu, my_d2, o);
+    const int32_t oi = __shfl_sync(0xffffffffu, my_idx, o);
+    if (oi >= 0 && (od < my_d2 || (od == my_d2 && oi < my_idx))) ++rank;
+  }
+  if (my_idx >= 0 && rank < k) {
+    d2_out[q * k + rank] = my_d2;
+    ids_out[q * k + rank] = id_offset + my_idx;
+  }
+  // fewer than k candidates: pad
+  const int found = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
+  if (lane >= found && lane < k) {
+    d2_out[q * k + lane] = INFINITY;
+    ids_out[q * k + lane] = -1;
+  }
+}
+
+// ---------------------------------------------------------------- merge of per-shard lists
+__global__ void knn_merge_kernel(const double* __restrict__ d2p, const int64_t* __restrict__ idp, int P, int64_t Q,
+                                 int k, double* __restrict__ d2, int64_t* __restrict__ ids) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  double last_d = -1.0;
+  int64_t last_i = -1;
+  for (int r = 0; r < k; ++r) {
+    double bd = INFINITY;
+    int64_t bi = -1;
+    for (int p = 0; p < P; ++p) {
+      const double* dd = d2p + (static_cast<int64_t>(p) * Q + q) * k;
+      const int64_t* ii = idp + (static_cast<int64_t>(p) * Q + q) * k;
+      for (int c = 0; c < k; ++c) {
+        const int64_t i = ii[c];
+        if (i < 0) continue;
+        const double x = dd[c];
+        const bool after = x > last_d || (x == last_d && i > last_i);
+        if (after && (bi < 0 || x < bd || (x == bd && i < bi))) {
+          bd = x;
+          bi = i;
+        }
+      }
+    }
+    d2[q * k + r] = bi >= 0 ? bd : INFINITY;
+    ids[q * k + r] = bi;
+    if (bi >= 0) {
+      last_d = bd;
+      last_i = bi;
+    } else {
+      last_d = INFINITY;
+    }
+  }
+}
+
+__global__ void sqrt_kernel(const double* __restrict__ d2, int64_t n, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(sqrt(d2[i]));
+}
+
+// majority vote, ties -> smallest label id (sklearn: classes_[argmax(counts)], classes_ sorted)
+__global__ void knn_vote_kernel(const int64_t* __restrict__ ids, int64_t Q, int k, const int32_t* __restrict__ labels,
+                                int64_t n_total, int32_t* __restrict__ pred) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  int best_cnt = 0;
+  int32_t best_lab = 0x7fffffff;
+  for (int a = 0; a < k; ++a) {
+    const int64_t ia = ids[q * k + a];
+    if (ia < 0 || ia >= n_total) continue;
+    const int32_t la = labels[ia];
+    int cnt = 0;
+    for (int b = 0; b < k; ++b) {
+      const int64_t ib = ids[q * k + b];
+      if (ib >= 0 && ib < n_total && labels[ib] == la) ++cnt;
+    }
+    if (cnt > best_cnt || (cnt == best_cnt && la < best_lab)) {
+      best_cnt = cnt;
+      best_lab = la;
+    }
+  }
+  pred[q] = best_cnt > 0 ? best_lab : -1;
+}
+
+__global__ void knn_accuracy_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ pred,
+                                    const int32_t* __restrict__ qlabels, int64_t Q, int k_ids,
+                                    const int32_t* __restrict__ labels, int64_t n_total,
+                                    unsigned long long* __restrict__ counts) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int top1 = 0, top5 = 0;
+  if (q < Q) {
+    const int32_t want = qlabels[q];
+    top1 = pred[q] == want;
+    const int kk = k_ids < 5 ? k_ids : 5;
+    for (int a = 0; a < kk; ++a) {
+      const int64_t ia = ids[q * k_ids + a];
+      if (ia >= 0 && ia < n_total && labels[ia] == want) top5 = 1;
+    }
+  }
+  const unsigned m1 = __ballot_sync(0xffffffffu, top1), m5 = __ballot_sync(0xffffffffu, top5);
+  if ((threadIdx.x & 31) == 0) {
+    if (m1) atomicAdd(&counts[0], static_cast<unsigned long long>(__popc(m1)));
+    if (m5) atomicAdd(&counts[1], static_cast<unsigned long long>(__popc(m5)));
+  }
+}
+
+inline int kc_for(int k) {
+  const int need = k + EN_KNN_SLACK;
+  return need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+}
+
+inline int knn_splits(int64_t Q, int64_t n_bank, int sms) {
+  const int tiles_m = static_cast<int>((Q + tc::BM - 1) / tc::BM);
+  const int tiles_n = static_cast<int>((n_bank + tc::BN - 1) / tc::BN);
+  int s = (16 * sms + tiles_m - 1) / tiles_m;
+  if (s > tiles_n) s = tiles_n;
+  if (s < 1) s = 1;
+  return s;
+}
+
+template <int KC>
+int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh, const CUtensorMap& bl,
+             const tc::Shape& sh, const float* bank_norms, const int32_t* bank_labels, const int32_t* query_labels,
+             Cand* lists, int64_t n_bank, int sms, cudaStream_t st) {
+  typename EpTopK<KC>::Params ep{bank_norms, bank_labels, query_labels, lists, n_bank, sh.n_splits};
+  EN_CUDA(tc::launch<EpTopK<KC>>(qh, ql, bh, bl, sh, ep, sms, st));
+  ++launch_counter();
+  return EN_OK;
+}
+
+template <int KC>
+int run_rerank(const float* queries, int64_t Q, int d, const float* bank, int64_t id_offset, const Cand* lists,
+               int n_lists, int k, double* d2, int64_t* ids, cudaStream_t st) {
+  knn_rerank_kernel<KC><<<static_cast<unsigned>((Q * 32 + 255) / 256), 256, 0, st>>>(queries, Q, d, bank, id_offset,
+                                                                                    lists, n_lists, k, d2, ids);
+  EN_LAUNCHED("knn_rerank_kernel");
+  return EN_OK;
+}
+
+constexpr int STREAM_WARPS = 8;
+
+inline void stream_geometry(int64_t n_bank, int sms, int64_t* rows_per_warp, int* n_lists, int* blocks) {
+  int64_t warps = static_cast<int64_t>(sms) * 4 * STREAM_WARPS;  // 4 resident CTAs per SM
+  if (warps > n_bank) warps = n_bank > 0 ? n_bank : 1;
+  *rows_per_warp = (n_bank + warps - 1) / warps;
+  const int64_t used = (n_bank + *rows_per_warp - 1) / *rows_per_warp;
+  *blocks = static_cast<int>((used + STREAM_WARPS - 1) / STREAM_WARPS);
+  *n_lists = *blocks * STREAM_WARPS;
+}
+
+}  // namespace
+}  // namespace en
+
+using namespace en;
+
+extern "C" {
+
+int en_bank_dpad(int d) { return d > 0 ? (d + tc::BK - 1) / tc::BK * tc::BK : 0; }
+
+int en_bank_prepare(const float* bank, int64_t n, int d, float* hi, float* lo, float* norms, void* stream) {
+  EN_REQUIRE(bank && hi && lo && norms && n >= 0 && d > 0, "en_bank_prepare: bad arguments");
+  if (n == 0) return EN_OK;
+  EN_CUDA(tc::launch_split(bank, n, d, d, en_bank_dpad(d), hi, lo, norms, as_stream(stream)));
+  ++launch_counter();
+  return EN_OK;
+}
+
+size_t en_ws_bytes_knn(int64_t Q, int64_t n_bank, int d, int k) {
+  if (Q <= 0 || n_bank <= 0 || d <= 0 || k <= 0 || k > EN_KNN_MAX_K) return 0;
+  const size_t dpad = static_cast<size_t>(en_bank_dpad(d));
+  // splits depend on the SM count; size for the worst case of 148 SMs x 16 items
+  const int tiles_m = static_cast<int>((Q + tc::BM - 1) / tc::BM);
+  const int tiles_n = static_cast<int>((n_bank + tc::BN - 1) / tc::BN);
+  int s = (16 * 160 + tiles_m - 1) / tiles_m;
+  if (s > tiles_n) s = tiles_n;
+  if (s < 1) s = 1;
+  return 2 * align_up(static_cast<size_t>(Q) * dpad * 4) + align_up(static_cast<size_t>(Q) * 4) +
+         align_up(static_cast<size_t>(Q) * s * kc_for(k) * sizeof(Cand));
+}
+
+int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_hi,
+                      const float* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                      const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids, void* ws,
+                      size_t ws_bytes, void* stream) {
+  EN_REQUIRE(queries && bank && bank_hi && bank_lo && bank_norms && d2 && ids && Q > 0 && n_bank > 0 && d > 0,
+             "en_knn_shard_topk: bad arguments");
+  EN_REQUIRE(k > 0 && k <= EN_KNN_MAX_K, "en_knn_shard_topk: k must be in [1, %d] (got %d)", EN_KNN_MAX_K, k);
+  EN_REQUIRE((query_labels == nullptr) == (bank_labels == nullptr) || query_labels == nullptr,
+             "en_knn_shard_topk: query_labels requires bank_labels");
+  EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_shard_topk: shard too large (%lld rows)", (long long)n_bank);
+  if (int rc = check_sm100()) return rc;
+  if (!ws || ws_bytes < en_ws_bytes_knn(Q, n_bank, d, k))
+    return fail(EN_ERR_WORKSPACE, "en_knn_shard_topk: workspace too small (%zu < %zu)", ws_bytes,
+                en_ws_bytes_knn(Q, n_bank, d, k));
+  cudaStream_t st = as_stream(stream);
+  const int sms = device_sm_count();
+  const int dpad = en_bank_dpad(d);
+  const int KC = kc_for(k);
+  Workspace w(ws, ws_bytes);
+  float* qhi = w.take<float>(static_cast<size_t>(Q) * dpad);
+  float* qlo = w.take<float>(static_cast<size_t>(Q) * dpad);
+  float* qn = w.take<float>(Q);
+  tc::Shape sh = tc::make_shape(Q, n_bank, d, knn_splits(Q, n_bank, sms), 3);
+  Cand* lists = w.take<Cand>(static_cast<size_t>(Q) * sh.n_splits * KC);
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_knn_shard_topk: workspace too small or misaligned");
+  EN_CUDA(tc::launch_split(queries, Q, d, d, dpad, qhi, qlo, qn, st));
+  ++launch_counter();
+  CUtensorMap tqh, tql, tbh, tbl;
+  if (tc::make_plane_tmap(&tqh, qhi, Q, dpad) || tc::make_plane_tmap(&tql, qlo, Q, dpad) ||
+      tc::make_plane_tmap(&tbh, bank_hi, n_bank, dpad) || tc::make_plane_tmap(&tbl, bank_lo, n_bank, dpad))
+    return fail(EN_ERR_DRIVER, "en_knn_shard_topk: cuTensorMapEncodeTiled failed");
+  const int32_t* ql = bank_labels ? query_labels : nullptr;
+  int rc;
+  if (KC == 8) rc = run_scan<8>(tqh, tql, tbh, tbl, sh, bank_norms, bank_labels, ql, lists, n_bank, sms, st);
+  else if (KC == 16) rc = run_scan<16>(tqh, tql, tbh, tbl, sh, bank_norms, bank_labels, ql, lists, n_bank, sms, st);
+  else rc = run_scan<32>(tqh, tql, tbh, tbl, sh, bank_norms, bank_labels, ql, lists, n_bank, sms, st);
+  if (rc) return rc;
+  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
+  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
+  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
+}
+
+size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k) {
+  if (Q <= 0 || Q > EN_KNN_STREAM_MAX_Q || n_bank <= 0 || d <= 0 || k <= 0 || k > EN_KNN_MAX_K) return 0;
+  int64_t rpw;
+  int n_lists, blocks;
+  stream_geometry(n_bank, 160, &rpw, &n_lists, &blocks);
+  return align_up(static_cast<size_t>(Q) * n_lists * kc_for(k) * sizeof(Cand));
+}
+
+int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                       int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(queries && bank && d2 && ids && Q > 0 && n_bank > 0 && d > 0, "en_knn_stream_topk: bad arguments");
+  EN_REQUIRE(Q <= EN_KNN_STREAM_MAX_Q, "en_knn_stream_topk: at most %d queries per call (got %lld)",
+             EN_KNN_STREAM_MAX_Q, (long long)Q);
+  EN_REQUIRE(k > 0 && k <= EN_KNN_MAX_K, "en_knn_stream_topk: k must be in [1, %d]", EN_KNN_MAX_K);
+  EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_stream_topk: shard too large");
+  EN_REQUIRE(static_cast<size_t>(Q) * d * 4 <= 160 * 1024, "en_knn_stream_topk: Q*d too large for shared memory");
+  if (!ws || ws_bytes < en_ws_bytes_knn_stream(Q, n_bank, d, k))
+    return fail(EN_ERR_WORKSPACE, "en_knn_stream_topk: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int sms = device_sm_count();
+  int64_t rpw;
+  int n_lists, blocks;
+  stream_geometry(n_bank, sms, &rpw, &n_lists, &blocks);
+  const int KC = kc_for(k);
+  Cand* lists = static_cast<Cand*>(ws);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(EN_ERR_WORKSPACE, "workspace misaligned");
+  const size_t smem = static_cast<size_t>(Q) * d * 4;
+#define EN_STREAM(KCV)                                                                                          \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                   static_cast<int>(smem)));                                                    \
+    knn_stream_kernel<KCV><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank, \
+                                                                     rpw, lists, n_lists);                      \
+    EN_LAUNCHED("knn_stream_kernel");                                                                           \
+    return run_rerank<KCV>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, st);                     \
+  } while (0)
+  if (KC == 8) EN_STREAM(8);
+  if (KC == 16) EN_STREAM(16);
+  EN_STREAM(32);
+#undef EN_STREAM
+}
+
+int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
+                 int64_t* ids, void* stream) {
+  EN_REQUIRE(d2_parts && id_parts && d2 && ids && n_parts > 0 && Q > 0 && k > 0, "en_knn_merge: bad arguments");
+  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(d2_parts, id_parts, n_parts,
+                                                                                          Q, k, d2, ids);
+  EN_LAUNCHED("knn_merge_kernel");
+  return EN_OK;
+}
+
+int en_knn_finalize_dist(const double* d2, int64_t n, float* dist, void* stream) {
+  EN_REQUIRE(d2 && dist && n >= 0, "en_knn_finalize_dist: bad arguments");
+  if (n == 0) return EN_OK;
+  sqrt_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(d2, n, dist);
+  EN_LAUNCHED("sqrt_kernel");
+  return EN_OK;
+}
+
+int en_knn_vote(const int64_t* ids, int64_t Q, int k, const int32_t* labels, int64_t n_total, int32_t* pred,
+                void* stream) {
+  EN_REQUIRE(ids && labels && pred && Q > 0 && k > 0 && n_total > 0, "en_knn_vote: bad arguments");
+  knn_vote_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(ids, Q, k, labels, n_total,
+                                                                                         pred);
+  EN_LAUNCHED("knn_vote_kernel");
+  return EN_OK;
+}
+
+int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* query_labels, int64_t Q, int k_ids,
+                    const int32_t* labels, int64_t n_total, int64_t* counts, void* stream) {
+  EN_REQUIRE(ids && pred && query_labels && labels && counts && Q > 0 && k_ids > 0, "en_knn_accuracy: bad arguments");
+  knn_accuracy_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(
+      ids, pred, query_labels, Q, k_ids, labels, n_total, reinterpret_cast<unsigned long long*>(counts));
+  EN_LAUNCHED("knn_accuracy_kernel");
+  return EN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// Memory-bound row-wise kernels: L2 normalisation, the pre-mined [a|p|n] triplet hinge, element-wise contrastive
+// loss / accuracy, and the Siamese distance heads -- forward and backward.  One warp per row, 128-bit loads when the
+// row is 16-byte aligned, FP32 math with IEEE sqrt/div (no fast-math), reductions by warp shuffle.
+//
+// Reference call sites (under /root/reference): embedding_net/backbones.py:38,77,118 (l2_normalize),
+// embedding_net/losses_and_accuracies.py:4-11,26-42,47-50, embedding_net/models.py:217-228.
+#include "common.cuh"
+
+namespace en {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int THREADS = WARPS_PER_BLOCK * 32;
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------- l2 normalise
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int d) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * d;
+  float* yr = y + row * d;
+  const bool vec = (d & 3) == 0 && aligned16(xr) && aligned16(yr);
+  float ss = 0.f;
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    for (int c = lane; c < d / 4; c += 32) {
+      float4 v = x4[c];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) ss += xr[c] * xr[c];
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    float4* y4 = reinterpret_cast<float4*>(yr);
+    for (int c = lane; c < d / 4; c += 32) {
+      float4 v = x4[c];
+      y4[c] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) yr[c] = xr[c] * inv;
+  }
+}
+
+// y = x*inv, inv = max(ss,eps)^-1/2  =>  gx = g*inv - [ss >= eps] * x * (g.x) * inv^3
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                  int64_t rows, int d) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * d;
+  const float* gr = gy + row * d;
+  float* or_ = gx + row * d;
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float v = xr[c];
+    ss += v * v;
+    dot += v * gr[c];
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+  const float k = ss >= 1e-12f ? dot * inv * inv * inv : 0.f;
+  for (int c = lane; c < d; c += 32) or_[c] = gr[c] * inv - xr[c] * k;
+}
+
+// ---------------------------------------------------------------- triplet [a|p|n]
+__global__ void triplet_apn_fwd_kernel(const float* __restrict__ y, int64_t B, int third, float margin,
+                                       float* __restrict__ loss) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* a = y + row * 3 * third;
+  const float* p = a + third;
+  const float* n = p + third;
+  float pos = 0.f, neg = 0.f;
+  if ((third & 3) == 0 && aligned16(a)) {
+    const float4 *a4 = reinterpret_cast<const float4*>(a), *p4 = reinterpret_cast<const float4*>(p),
+                 *n4 = reinterpret_cast<const float4*>(n);
+    for (int c = lane; c < third / 4; c += 32) {
+      float4 va = a4[c], vp = p4[c], vn = n4[c];
+      float t;
+      t = va.x - vp.x; pos += t * t; t = va.y - vp.y; pos += t * t;
+      t = va.z - vp.z; pos += t * t; t = va.w - vp.w; pos += t * t;
+      t = va.x - vn.x; neg += t * t; t = va.y - vn.y; neg += t * t;
+      t = va.z - vn.z; neg += t * t; t = va.w - vn.w; neg += t * t;
+    }
+  } else {
+    for (int c = lane; c < third; c += 32) {
+      float t = a[c] - p[c];
+      pos += t * t;
+      t = a[c] - n[c];
+      neg += t * t;
+    }
+  }
+  pos = warp_sum(pos);
+  neg = warp_sum(neg);
+  if (lane == 0) loss[row] = fmaxf(__fadd_rn(__fsub_rn(pos, neg), margin), 0.f);
+}
+
+__global__ void triplet_apn_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gloss, int64_t B,
+                                       int third, float margin, float* __restrict__ gy) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* a = y + row * 3 * third;
+  const float* p = a + third;
+  const float* n = p + third;
+  float pos = 0.f, neg = 0.f;
+  for (int c = lane; c < third; c += 32) {
+    float t = a[c] - p[c];
+    pos += t * t;
+    t = a[c] - n[c];
+    neg += t * t;
+  }
+  pos = warp_sum(pos);
+  neg = warp_sum(neg);
+  // TF routes maximum(x, 0)'s gradient to x when x >= 0.
+  const float g = (__fadd_rn(__fsub_rn(pos, neg), margin) >= 0.f) ? gloss[row] : 0.f;
+  float* ga = gy + row * 3 * third;
+  float* gp = ga + third;
+  float* gn = gp + third;
+  for (int c = lane; c < third; c += 32) {
+    const float ap = a[c] - p[c], an = a[c] - n[c];
+    ga[c] = g * 2.f * (ap - an);
+    gp[c] = -g * 2.f * ap;
+    gn[c] = g * 2.f * an;
+  }
+}
+
+// ---------------------------------------------------------------- element-wise contrastive / accuracy
+// (B,1)-shaped inputs: a single block with a deterministic tree reduction in double.
+__device__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+__global__ void contrastive_fwd_kernel(const float* __restrict__ yt, const float* __restrict__ yp, int64_t n,
+                                       float* __restrict__ loss) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = yp[i], t = yt[i];
+    const float m = fmaxf(1.0f - d, 0.f);
+    acc += static_cast<double>(t * (d * d) + (1.0f - t) * (m * m));
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss[0] = static_cast<float>(acc / static_cast<double>(n));
+}
+
+__global__ void contrastive_bwd_kernel(const float* __restrict__ yt, const float* __restrict__ yp,
+                                       const float* __restrict__ gloss, int64_t n, float* __restrict__ g) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = yp[i], t = yt[i];
+  const float scale = gloss[0] / static_cast<float>(n);
+  g[i] = scale * (t * 2.f * d - (1.f - t) * 2.f * fmaxf(1.f - d, 0.f));
+}
+
+__global__ void pair_accuracy_kernel(const float* __restrict__ yt, const float* __restrict__ yp, int64_t n,
+                                     float* __restrict__ acc_out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (yt[i] == (yp[i] < 0.5f ? 1.0f : 0.0f)) ? 1.0 : 0.0;
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) acc_out[0] = static_cast<float>(acc / static_cast<double>(n));
+}
+
+// ---------------------------------------------------------------- Siamese heads
+__global__ void siamese_l2_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int64_t B, int d,
+                                      float* __restrict__ dist) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* a = e1 + row * d;
+  const float* b = e2 + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float t = a[c] - b[c];
+    s += t * t;
+  }
+  s = warp_sum(s);
+  if (lane == 0) dist[row] = sqrtf(fmaxf(s, 1e-7f));
+}
+
+__global__ void siamese_l2_bwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
+                                      const float* __restrict__ gdist, int64_t B, int d, float* __restrict__ g1,
+                                      float* __restrict__ g2) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* a = e1 + row * d;
+  const float* b = e2 + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float t = a[c] - b[c];
+    s += t * t;
+  }
+  s = warp_sum(s);
+  // d/ds sqrt(max(s, eps)) = [s >= eps] / (2 sqrt(s));  ds/de1 = 2 (e1 - e2)
+  const float k = s >= 1e-7f ? gdist[row] / sqrtf(s) : 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = k * (a[c] - b[c]);
+    g1[row * d + c] = v;
+    g2[row * d + c] = -v;
+  }
+}
+
+__global__ void siamese_l1_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int64_t n,
+                                      float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fabsf(e1[i] - e2[i]);
+}
+__global__ void siamese_l1_bwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
+                                      const float* __restrict__ go, int64_t n, float* __restrict__ g1,
+                                      float* __restrict__ g2) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = e1[i] - e2[i];
+  const float s = t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f);
+  g1[i] = s * go[i];
+  g2[i] = -s * go[i];
+}
+
+inline unsigned row_blocks(int64_t rows) { return static_cast<unsigned>((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
+inline unsigned elem_blocks(int64_t n) { return static_cast<unsigned>((n + THREADS - 1) / THREADS); }
+
+}  // namespace
+}  // namespace en
+
+using namespace en;
+
+extern "C" {
+
+int en_l2_normalize_fwd(const float* x, float* y, int64_t rows, int d, void* stream) {
+  EN_REQUIRE(x && y && rows >= 0 && d > 0, "en_l2_normalize_fwd: bad arguments (rows=%lld d=%d)", (long long)rows, d);
+  if (rows == 0) return EN_OK;
+  l2norm_fwd_kernel<<<row_blocks(rows), THREADS, 0, as_stream(stream)>>>(x, y, rows, d);
+  EN_LAUNCHED("l2norm_fwd_kernel");
+  return EN_OK;
+}
+
+int en_l2_normalize_bwd(const float* x, const float* gy, float* gx, int64_t rows, int d, void* stream) {
+  EN_REQUIRE(x && gy && gx && rows >= 0 && d > 0, "en_l2_normalize_bwd: bad arguments");
+  if (rows == 0) return EN_OK;
+  l2norm_bwd_kernel<<<row_blocks(rows), THREADS, 0, as_stream(stream)>>>(x, gy, gx, rows, d);
+  EN_LAUNCHED("l2norm_bwd_kernel");
+  return EN_OK;
+}
+
+int en_triplet_apn_fwd(const float* y_pred, int64_t B, int total_len, float margin, float* loss, void* stream) {
+  EN_REQUIRE(y_pred && loss && B >= 0 && total_len > 0, "en_triplet_apn_fwd: bad arguments");
+  EN_REQUIRE(total_len % 3 == 0,
+             "en_triplet_apn_fwd: y_pred last dimension (%d) must be a multiple of 3 ([a|p|n] thirds, lac:29-31)",
+             total_len);
+  if (B == 0) return EN_OK;
+  triplet_apn_fwd_kernel<<<row_blocks(B), THREADS, 0, as_stream(stream)>>>(y_pred, B, total_len / 3, margin, loss);
+  EN_LAUNCHED("triplet_apn_fwd_kernel");
+  return EN_OK;
+}
+
+int en_triplet_apn_bwd(const float* y_pred, const float* gloss, int64_t B, int total_len, float margin,
+                       float* gy_pred, void* stream) {
+  EN_REQUIRE(y_pred && gloss && gy_pred && B >= 0 && total_len > 0 && total_len % 3 == 0,
+             "en_triplet_apn_bwd: bad arguments");
+  if (B == 0) return EN_OK;
+  triplet_apn_bwd_kernel<<<row_blocks(B), THREADS, 0, as_stream(stream)>>>(y_pred, gloss, B, total_len / 3, margin,
+                                                                           gy_pred);
+  EN_LAUNCHED("triplet_apn_bwd_kernel");
+  return EN_OK;
+}
+
+int en_contrastive_fwd(const float* y_true, const float* y_pred, int64_t n, float* loss, void* stream) {
+  EN_REQUIRE(y_true && y_pred && loss && n > 0, "en_contrastive_fwd: bad arguments");
+  contrastive_fwd_kernel<<<1, 1024, 0, as_stream(stream)>>>(y_true, y_pred, n, loss);
+  EN_LAUNCHED("contrastive_fwd_kernel");
+  return EN_OK;
+}
+
+int en_contrastive_bwd(const float* y_true, const float* y_pred, const float* gloss, int64_t n, float* gy_pred,
+                       void* stream) {
+  EN_REQUIRE(y_true && y_pred && gloss && gy_pred && n > 0, "en_contrastive_bwd: bad arguments");
+  contrastive_bwd_kernel<<<elem_blocks(n), THREADS, 0, as_stream(stream)>>>(y_true, y_pred, gloss, n, gy_pred);
+  EN_LAUNCHED("contrastive_bwd_kernel");
+  return EN_OK;
+}
+
+int en_pair_accuracy(const float* y_true, const float* y_pred, int64_t n, float* acc, void* stream) {
+  EN_REQUIRE(y_true && y_pred && acc && n > 0, "en_pair_accuracy: bad arguments");
+  pair_accuracy_kernel<<<1, 1024, 0, as_stream(stream)>>>(y_true, y_pred, n, acc);
+  EN_LAUNCHED("pair_accuracy_kernel");
+  return EN_OK;
+}
+
+int en_siamese_l2_fwd(const float* e1, const float* e2, int64_t B, int d, float* dist, void* stream) {
+  EN_REQUIRE(e1 && e2 && dist && B >= 0 && d > 0, "en_siamese_l2_fwd: bad arguments");
+  if (B == 0) return EN_OK;
+  siamese_l2_fwd_kernel<<<row_blocks(B), THREADS, 0, as_stream(stream)>>>(e1, e2, B, d, dist);
+  EN_LAUNCHED("siamese_l2_fwd_kernel");
+  return EN_OK;
+}
+
+int en_siamese_l2_bwd(const float* e1, const float* e2, const float* gdist, int64_t B, int d, float* g1, float* g2,
+                      void* stream) {
+  EN_REQUIRE(e1 && e2 && gdist && g1 && g2 && B >= 0 && d > 0, "en_siamese_l2_bwd: bad arguments");
+  if (B == 0) return EN_OK;
+  siamese_l2_bwd_kernel<<<row_blocks(B), THREADS, 0, as_stream(stream)>>>(e1, e2, gdist, B, d, g1, g2);
+  EN_LAUNCHED("siamese_l2_bwd_kernel");
+  return EN_OK;
+}
+
+int en_siamese_l1_fwd(const float* e1, const float* e2, int64_t n, float* out, void* stream) {
+  EN_REQUIRE(e1 && e2 && out && n >= 0, "en_siamese_l1_fwd: bad arguments");
+  if (n == 0) return EN_OK;
+  siamese_l1_fwd_kernel<<<elem_blocks(n), THREADS, 0, as_stream(stream)>>>(e1, e2, n, out);
+  EN_LAUNCHED("siamese_l1_fwd_kernel");
+  return EN_OK;
+}
+
+int en_siamese_l1_bwd(const float* e1, const float* e2, const float* gout, int64_t n, float* g1, float* g2,
+                      void* stream) {
+  EN_REQUIRE(e1 && e2 && gout && g1 && g2 && n >= 0, "en_siamese_l1_bwd: bad arguments");
+  if (n == 0) return EN_OK;
+  siamese_l1_bwd_kernel<<<elem_blocks(n), THREADS, 0, as_stream(stream)>>>(e1, e2, gout, n, g1, g2);
+  EN_LAUNCHED("siamese_l1_bwd_kernel");
+  return EN_OK;
+}
+
+}  // extern "C"

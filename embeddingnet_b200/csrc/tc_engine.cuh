@@ -30,7 +30,8 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // Ahi, Alo, Bhi, Blo
 constexpr int ACC_COLS = 2 * BN;                   // main | cross
 constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 512 = all of TMEM (1 CTA/SM anyway, by smem)
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BASE_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_EP_MAX = 232448 - SMEM_BASE_BYTES;  // what is left of the 227 KB for an epilogue's scratch
 static_assert(BN == BM, "A and B tiles share TILE_BYTES");
 
 struct Shape {
@@ -52,13 +53,17 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-// Epilogue concept:
-//   struct Ep { struct Params; struct Row;
-//     static __device__ void item_begin(const Params&, Row&, int64_t row, bool row_valid, int tile_m, int split);
-//     static __device__ void chunk(const Params&, Row&, int64_t row, bool row_valid, int64_t col0, const float (&dot)[32]);
-//     static __device__ void tile_end(const Params&, Row&, int64_t row, bool row_valid, int tile_n);
-//     static __device__ void item_end(const Params&, Row&, int64_t row, bool row_valid, int tile_m, int split); };
+// Epilogue concept (one thread owns one row of the 128-row tile for the whole work item):
+//   struct Ep { struct Params; struct Row; static constexpr int kSmemBytes;   // scratch, <= SMEM_EP_MAX
+//     static __device__ void item_begin(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int tile_m, int split);
+//     static __device__ void chunk(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int64_t col0, const float (&dot)[32]);
+//     static __device__ void tile_end(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int tile_n);
+//     static __device__ void item_end(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int tile_m, int split); };
 // `chunk` receives dot[j] = <A[row], B[col0 + j]> for 32 consecutive candidate rows (columns past N hold 0).
+struct Ctx {
+  uint8_t* smem;  // Ep::kSmemBytes of shared scratch (16-byte aligned), shared by the 128 epilogue threads
+  int erow;       // this thread's row inside the tile, 0..127
+};
 
 template <class Ep>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -69,6 +74,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   // 128B swizzle atoms need 1024-byte aligned tile bases.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* ep_smem = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,6 +179,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are reachable from this warp
     uint32_t acc_it = 0;
     typename Ep::Row rs;
+    const Ctx ctx{ep_smem, quarter * 32 + lane};
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile_m = item / shape.n_splits;
       const int split = item % shape.n_splits;
@@ -180,7 +187,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
       const int64_t row = static_cast<int64_t>(tile_m) * BM + quarter * 32 + lane;
       const bool row_valid = row < shape.M;
-      Ep::item_begin(ep, rs, row, row_valid, tile_m, split);
+      Ep::item_begin(ep, rs, ctx, row, row_valid, tile_m, split);
       for (int nt = nt0; nt < nt1; ++nt, ++acc_it) {
         const uint32_t acc = acc_it % NUM_ACC;
         const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
@@ -200,14 +207,14 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           } else {
             ptx::tmem_ld_wait();
           }
-          Ep::chunk(ep, rs, row, row_valid, static_cast<int64_t>(nt) * BN + c * 32, dot);
+          Ep::chunk(ep, rs, ctx, row, row_valid, static_cast<int64_t>(nt) * BN + c * 32, dot);
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
-        Ep::tile_end(ep, rs, row, row_valid, nt);
+        Ep::tile_end(ep, rs, ctx, row, row_valid, nt);
       }
-      Ep::item_end(ep, rs, row, row_valid, tile_m, split);
+      Ep::item_end(ep, rs, ctx, row, row_valid, tile_m, split);
     }
   }
 
@@ -270,13 +277,12 @@ template <class Ep>
 inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                           const CUtensorMap& b_lo, const Shape& shape, const typename Ep::Params& ep, int num_sms,
                           cudaStream_t stream) {
-  static bool attr_set = false;  // per (Ep) instantiation
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(dist_gemm_kernel<Ep>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static_assert(Ep::kSmemBytes <= SMEM_EP_MAX, "epilogue scratch does not fit beside the operand pipeline");
+  constexpr int SMEM_BYTES = SMEM_BASE_BYTES + Ep::kSmemBytes;
+  // idempotent, cheap; set on every launch so it also holds after a device switch (one attribute per device)
+  cudaError_t e =
+      cudaFuncSetAttribute(dist_gemm_kernel<Ep>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   const int items = shape.tiles_m * shape.n_splits;
   const int grid = items < num_sms ? items : num_sms;
   dist_gemm_kernel<Ep><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, shape, ep);
@@ -293,7 +299,7 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-__global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
+static __global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
                                     float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norms) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;

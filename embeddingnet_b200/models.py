@@ -1,0 +1,355 @@
+"""Drop-in for the encoding-bank half of ``embedding_net/models.py`` (RocketFlash/EmbeddingNet).
+
+Kept verbatim from the reference (/root/reference/embedding_net/models.py): ``EmbeddingNet.generate_encodings``
+(61-84), ``save_encodings`` (86-90), ``predict`` (115-126), ``predict_knn`` (128-142),
+``calculate_prediction_accuracy`` (144-161), ``train_embeddings_classifier`` (52-59) -- names, arguments, return
+shapes.  What the snapshot leaves undefined or unwritten is defined here from its call sites:
+``calculate_distances`` (models.py:123) and a ``KNeighborsClassifier``-shaped object (``fit`` / ``predict`` /
+``kneighbors``, models.py:58,136,138) stored under ``encoded_training_data['knn_classifier']``.
+
+The bank scan is a streaming tcgen05 distance GEMM with an in-register per-query top-k, followed by an exact
+float64 re-rank (``csrc/knn.cu``).  With a ``torch.distributed`` process group the bank is sharded row-wise, one
+shard per GPU, and the per-shard top-k lists are merged after one NCCL all-gather; results do not depend on the
+number of shards.  Keras model construction, h5 / ONNX export and image IO are out of scope: ``base_model`` is any
+object with ``predict(images) -> (n, d) float32``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import pickle
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import as_cuda_f32, ptr, require_cuda, stream_ptr, workspace
+
+
+class BankKNNClassifier:
+    """``sklearn.neighbors.KNeighborsClassifier``-shaped brute-force classifier over an encoding bank on B200.
+
+    fit(X, y) uploads (this rank's shard of) the bank and prepares the TF32 planes; ``kneighbors`` returns
+    ``(dist (Q, k) float32, idx (Q, k) int64)`` ascending by (distance, index) -- lowest index wins ties;
+    ``predict`` is the uniform majority vote with ties resolved to the smallest class (sklearn's rule).
+
+    process_group: optional torch.distributed group; rank r keeps rows [r*ceil(N/P), (r+1)*ceil(N/P)).
+    """
+
+    def __init__(self, n_neighbors=5, process_group=None, device=None):
+        self.n_neighbors = int(n_neighbors)
+        self.process_group = process_group
+        self.device = device
+        self._fitted = False
+
+    # -- sharding helpers
+    def _world(self):
+        if self.process_group is None:
+            return 1, 0
+        import torch.distributed as dist
+
+        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+
+    @staticmethod
+    def shard_bounds(n_total, world, rank):
+        per = (n_total + world - 1) // world
+        lo = min(rank * per, n_total)
+        return lo, min(lo + per, n_total)
+
+    def fit(self, X, y):
+        """X: (N, d) float32 bank (numpy or torch; every rank passes the full bank or see ``fit_shard``), y: N labels
+        (any hashable, as in the reference where they are class-name strings, models.py:77)."""
+        X = np.asarray(X) if not isinstance(X, torch.Tensor) else X
+        n_total = X.shape[0]
+        world, rank = self._world()
+        lo, hi = self.shard_bounds(n_total, world, rank)
+        self.classes_, y_ids = np.unique(np.asarray(y), return_inverse=True)
+        return self.fit_shard(X[lo:hi], y_ids.astype(np.int32), lo, n_total, classes=self.classes_)
+
+    def fit_shard(self, X_shard, label_ids_all, id_offset, n_total, classes=None):
+        """Fit from this rank's rows only.  label_ids_all: int32 class ids of ALL N rows (4 bytes per row)."""
+        dev = self.device or require_cuda()
+        self.device = dev
+        lib = _lib.load()
+        self._bank = as_cuda_f32(X_shard, dev)
+        if self._bank.dim() != 2:
+            raise ValueError("BankKNNClassifier.fit: X must be (N, d)")
+        n, d = self._bank.shape
+        self._n_total, self._offset, self._d = int(n_total), int(id_offset), d
+        dpad = lib.en_bank_dpad(d)
+        self._hi = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+        self._lo = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+        self._norms = torch.empty(n, dtype=torch.float32, device=dev)
+        if n > 0:
+            _lib.call("en_bank_prepare", ptr(self._bank), n, d, ptr(self._hi), ptr(self._lo), ptr(self._norms),
+                      stream_ptr())
+        ids = label_ids_all if isinstance(label_ids_all, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(label_ids_all, dtype=np.int32)))
+        self._labels = ids.to(dev, torch.int32).contiguous()
+        if self._labels.numel() != n_total:
+            raise ValueError("BankKNNClassifier: need one label id per bank row (%d != %d)" %
+                             (self._labels.numel(), n_total))
+        if classes is not None:
+            self.classes_ = np.asarray(classes)
+        elif not hasattr(self, "classes_"):
+            self.classes_ = np.arange(int(self._labels.max().item()) + 1)
+        self._fitted = True
+        return self
+
+    # -- core search on device tensors
+    def _search(self, q, k, exclude_labels=None):
+        """q: (Q, d) CUDA float32.  Returns (d2 (Q, k) float64, ids (Q, k) int64) global, merged over shards."""
+        if not self._fitted:
+            raise RuntimeError("BankKNNClassifier: call fit() first")
+        lib = _lib.load()
+        dev = self.device
+        Q, d = q.shape
+        if d != self._d:
+            raise ValueError("query dimension %d != bank dimension %d" % (d, self._d))
+        if not (1 <= k <= _lib.EN_KNN_MAX_K):
+            raise ValueError("n_neighbors must be in [1, %d]" % _lib.EN_KNN_MAX_K)
+        n = self._bank.shape[0]
+        d2 = torch.full((Q, k), float("inf"), dtype=torch.float64, device=dev)
+        ids = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
+        if n > 0 and Q > 0:
+            ql = bl = None
+            if exclude_labels is not None:
+                ql = exclude_labels.to(dev, torch.int32).contiguous()
+                bl = self._labels[self._offset:self._offset + n]
+            if Q <= _lib.EN_KNN_STREAM_MAX_Q and ql is None:
+                # the reference's own call pattern: one image per predict() -> HBM-bound streaming scan
+                ws = workspace(lib.en_ws_bytes_knn_stream(Q, n, d, k), dev, "knn")
+                _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), n, self._offset, k, ptr(d2), ptr(ids),
+                          ptr(ws), ws.numel(), stream_ptr())
+            else:
+                ws = workspace(lib.en_ws_bytes_knn(Q, n, d, k), dev, "knn")
+                _lib.call("en_knn_shard_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._hi), ptr(self._lo),
+                          ptr(self._norms), n, self._offset, k, ptr(ql), ptr(bl), ptr(d2), ptr(ids), ptr(ws),
+                          ws.numel(), stream_ptr())
+        world, _ = self._world()
+        if world > 1:
+            import torch.distributed as dist
+
+            d2_all = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
+            id_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(d2_all, d2, group=self.process_group)   # NCCL over NVLink
+            dist.all_gather_into_tensor(id_all, ids, group=self.process_group)
+            d2m = torch.empty_like(d2)
+            idm = torch.empty_like(ids)
+            _lib.call("en_knn_merge", ptr(d2_all), ptr(id_all), world, Q, k, ptr(d2m), ptr(idm), stream_ptr())
+            d2, ids = d2m, idm
+        return d2, ids
+
+    def kneighbors_device(self, X, n_neighbors=None, exclude_labels=None):
+        """Device-resident variant: returns (dist float32, idx int64) CUDA tensors, no host copy."""
+        k = self.n_neighbors if n_neighbors is None else int(n_neighbors)
+        q = as_cuda_f32(X, self.device)
+        if q.dim() == 1:
+            q = q.reshape(1, -1)
+        d2, ids = self._search(q, k, exclude_labels)
+        dist_f = torch.empty(d2.shape, dtype=torch.float32, device=d2.device)
+        _lib.call("en_knn_finalize_dist", ptr(d2), d2.numel(), ptr(dist_f), stream_ptr())
+        return dist_f, ids
+
+    def kneighbors(self, X, n_neighbors=None, return_distance=True):
+        dist_f, ids = self.kneighbors_device(X, n_neighbors)
+        if return_distance:
+            return dist_f.cpu().numpy(), ids.cpu().numpy()
+        return ids.cpu().numpy()
+
+    def predict_device(self, X):
+        """(Q,) int32 class ids on the device."""
+        k = self.n_neighbors
+        q = as_cuda_f32(X, self.device)
+        if q.dim() == 1:
+            q = q.reshape(1, -1)
+        _, ids = self._search(q, k)
+        pred = torch.empty(q.shape[0], dtype=torch.int32, device=self.device)
+        _lib.call("en_knn_vote", ptr(ids), q.shape[0], k, ptr(self._labels), self._n_total, ptr(pred), stream_ptr())
+        return pred, ids
+
+    def predict(self, X):
+        pred, _ = self.predict_device(X)
+        return self.classes_[pred.cpu().numpy()]
+
+    def score_topk(self, X, y):
+        """Batched ``calculate_prediction_accuracy`` (models.py:144-161): one scan, on-device top-1 / top-5 tally."""
+        k = max(self.n_neighbors, 5)
+        q = as_cuda_f32(X, self.device)
+        Q = q.shape[0]
+        _, ids = self._search(q, k)
+        ids_vote = ids[:, :self.n_neighbors].contiguous()
+        pred = torch.empty(Q, dtype=torch.int32, device=self.device)
+        _lib.call("en_knn_vote", ptr(ids_vote), Q, self.n_neighbors, ptr(self._labels), self._n_total, ptr(pred),
+                  stream_ptr())
+        lut = {c: i for i, c in enumerate(self.classes_.tolist())}
+        want = torch.tensor([lut.get(v, -1) for v in np.asarray(y).tolist()], dtype=torch.int32, device=self.device)
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        _lib.call("en_knn_accuracy", ptr(ids), ptr(pred), ptr(want), Q, k, ptr(self._labels), self._n_total,
+                  ptr(counts), stream_ptr())
+        c = counts.cpu().numpy()
+        return {"top1": float(c[0]) / Q, "top5": float(c[1]) / Q}
+
+
+class EmbeddingNet:
+    """Bank / nearest-neighbour part of the reference class (models.py:22-161)."""
+
+    def __init__(self, params, base_model=None):
+        self.params_model = params.get("model", {})
+        self.params_dataloader = params.get("dataloader", {})
+        self.params_generator = params.get("generator", {})
+        self.params_general = params.get("general", {})
+        self.params_train = params.get("train", {})
+        self.params_encodings = params.get("encodings", {})
+        if "softmax" in params:
+            self.params_softmax = params["softmax"]
+        self.base_model = base_model
+        self.backbone_model = None
+        self.model = None
+        self.input_shape = self.params_model.get("input_shape")
+        if "work_dir" in self.params_general and "project_name" in self.params_general:
+            self.workdir_path = os.path.join(self.params_general["work_dir"], self.params_general["project_name"])
+        self.encoded_training_data = {}
+
+    # -- image hooks (out of scope; overridable)
+    def _load_images(self, paths):
+        import cv2
+
+        shape = self.params_model.get("input_shape")
+        imgs = []
+        for p in paths:
+            img = cv2.imread(p)
+            if img is not None and shape:
+                img = cv2.resize(img, (shape[0], shape[1]))
+            imgs.append(img)
+        return np.array(imgs)
+
+    def _load_image(self, image):
+        import cv2
+
+        img = cv2.imread(image) if isinstance(image, str) else image
+        shape = self.input_shape or self.params_model.get("input_shape")
+        return cv2.resize(img, (shape[0], shape[1]))
+
+    def _generate_encodings(self, imgs):
+        return self.base_model.predict(imgs)                                             # models.py:47-49
+
+    def generate_encodings(self, data_loader, max_n_samples=10, shuffle=True):
+        """models.py:61-84: at most ``max_n_samples`` per class, rows appended class by class."""
+        data_paths, data_labels, data_encodings = [], [], []
+        encoded_training_data = {}
+        for class_name in data_loader.class_names:
+            data_list = data_loader.train_data[class_name]
+            if len(data_list) > max_n_samples:
+                if shuffle:
+                    random.shuffle(data_list)
+                data_list = data_list[:max_n_samples]
+            data_paths += data_list
+            imgs = self._load_images(data_list)
+            encods = self._generate_encodings(imgs)
+            for encod in encods:
+                data_encodings.append(encod)
+                data_labels.append(class_name)
+        encoded_training_data["paths"] = data_paths
+        encoded_training_data["labels"] = data_labels
+        encoded_training_data["encodings"] = np.squeeze(np.array(data_encodings))
+        self.encoded_training_data = encoded_training_data
+        return encoded_training_data
+
+    def save_encodings(self, encoded_training_data, save_folder="./", save_file_name="encodings.pkl"):
+        """models.py:86-90 (the fitted GPU classifier is not picklable and is dropped)."""
+        data = {k: v for k, v in encoded_training_data.items() if k != "knn_classifier"}
+        with open(os.path.join(save_folder, save_file_name), "wb") as f:
+            pickle.dump(data, f)
+
+    def load_encodings(self, path_to_encodings, fit_knn=True):
+        """What tools/test.py:22 calls (absent in the snapshot): ``utils.load_encodings`` + classifier fit."""
+        from .utils import load_encodings
+
+        self.encoded_training_data = load_encodings(path_to_encodings)
+        if fit_knn:
+            self.fit_knn()
+        return self.encoded_training_data
+
+    def fit_knn(self, n_neighbors=None, process_group=None):
+        k = n_neighbors or self.params_encodings.get("knn_k", 5) or 5
+        clf = BankKNNClassifier(n_neighbors=k, process_group=process_group)
+        clf.fit(self._bank_matrix(), self.encoded_training_data["labels"])
+        self.encoded_training_data["knn_classifier"] = clf
+        return clf
+
+    def train_embeddings_classifier(self, data_loader, classification_model, max_n_samples=10, shuffle=True):
+        """models.py:52-59."""
+        encodings = self.generate_encodings(data_loader, max_n_samples=max_n_samples, shuffle=shuffle)
+        classification_model.fit(encodings["encodings"], encodings["labels"])
+        if isinstance(classification_model, BankKNNClassifier):
+            self.encoded_training_data["knn_classifier"] = classification_model
+
+    def _bank_matrix(self):
+        enc = np.asarray(self.encoded_training_data["encodings"], dtype=np.float32)
+        return enc.reshape(1, -1) if enc.ndim == 1 else enc   # np.squeeze quirk for a one-row bank (models.py:82)
+
+    def _nn1(self):
+        clf = self.encoded_training_data.get("_nn1")
+        if clf is None:
+            clf = BankKNNClassifier(n_neighbors=1)
+            clf.fit(self._bank_matrix(), self.encoded_training_data["labels"])
+            self.encoded_training_data["_nn1"] = clf
+        return clf
+
+    def calculate_distances(self, encoding):
+        """The method ``predict`` calls but the snapshot never defines (models.py:123): Euclidean distance from one
+        encoding to every bank row, shape (N,)."""
+        dev = require_cuda()
+        bank = as_cuda_f32(self._bank_matrix(), dev)
+        q = as_cuda_f32(np.asarray(encoding, np.float32).reshape(1, -1), dev).expand(bank.shape[0], -1).contiguous()
+        n, d = bank.shape  # row-wise sqrt(max(sum (a-b)^2, 1e-7)) kernel of the Siamese head
+        dist = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        _lib.call("en_siamese_l2_fwd", ptr(q), ptr(bank), n, d, ptr(dist), stream_ptr())
+        return dist.reshape(-1).cpu().numpy()
+
+    def predict(self, image):
+        """models.py:115-126: nearest bank row (np.argmin -> lowest index on ties) -> its label."""
+        img = self._load_image(image)
+        encoding = self.base_model.predict(np.expand_dims(img, axis=0))
+        return self.predict_encoding(encoding)
+
+    def predict_encoding(self, encoding):
+        _, idx = self._nn1().kneighbors(np.asarray(encoding, np.float32).reshape(1, -1), n_neighbors=1)
+        return self.encoded_training_data["labels"][int(idx[0, 0])]
+
+    def predict_knn(self, image, with_top5=False):
+        """models.py:128-142."""
+        img = self._load_image(image)
+        encoding = self.base_model.predict(np.expand_dims(img, axis=0))
+        return self.predict_knn_encoding(encoding, with_top5=with_top5)
+
+    def predict_knn_encoding(self, encoding, with_top5=False):
+        clf = self.encoded_training_data["knn_classifier"]
+        encoding = np.asarray(encoding, np.float32).reshape(1, -1)
+        predicted_label = clf.predict(encoding)                                          # models.py:136, shape (1,)
+        if with_top5:
+            prediction_top5_idx = clf.kneighbors(encoding, n_neighbors=5)                # models.py:138
+            prediction_top5 = [self.encoded_training_data["labels"][prediction_top5_idx[1][0][i]] for i in range(5)]
+            return predicted_label, prediction_top5
+        return predicted_label
+
+    def calculate_prediction_accuracy(self, data_loader, batched=True):
+        """models.py:144-161.  ``batched`` embeds all validation images, then ONE bank scan + on-device tally
+        (SURVEY F3); ``batched=False`` keeps the reference's one-image-per-call loop."""
+        paths = data_loader.images_paths["val"]
+        labels = data_loader.images_labels["val"]
+        if batched:
+            imgs = self._load_images(paths)
+            enc = np.asarray(self.base_model.predict(imgs), np.float32)
+            return self.encoded_training_data["knn_classifier"].score_topk(enc, labels)
+        correct_top1 = correct_top5 = 0
+        for img_path, img_label in zip(paths, labels):
+            prediction, prediction_top5 = self.predict_knn(img_path, with_top5=True)
+            if prediction[0] == img_label:
+                correct_top1 += 1
+            if img_label in prediction_top5:
+                correct_top5 += 1
+        n = len(paths)
+        return {"top1": correct_top1 / n, "top5": correct_top5 / n}

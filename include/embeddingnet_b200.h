@@ -1,0 +1,189 @@
+/* embeddingnet_b200 -- C ABI of the B200-native distance / mining / loss / bank-kNN hot path.
+ *
+ * This is the drop-in boundary: plain C, device pointers and sizes only, no torch types.
+ * The reference (RocketFlash/EmbeddingNet) has no FFI of its own -- its "API" for this path is a handful of
+ * Python callables -- so every entry point below cites the reference call site (file:line under /root/reference)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous with respect
+ *     to the host unless stated; outputs are valid once the stream has been synchronised;
+ *   - return value: 0 = OK, negative = argument error detected on the host before any launch (EN_ERR_*),
+ *     positive = cudaError_t.  en_last_error() returns a thread-local message for the last failure;
+ *   - functions are re-entrant and keep no global mutable state (tensor-map encoder lookup is idempotent);
+ *   - workspace: functions taking (ws, ws_bytes) need scratch of at least the matching en_ws_bytes_*() size,
+ *     256-byte aligned; the library never allocates device memory;
+ *   - all matrices are row-major fp32, labels are int32, ids are int64 unless stated.
+ */
+#ifndef EMBEDDINGNET_B200_H
+#define EMBEDDINGNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EN_OK 0
+#define EN_ERR_ARG (-1)        /* bad shape / null pointer / unsupported value */
+#define EN_ERR_WORKSPACE (-2)  /* workspace too small or misaligned */
+#define EN_ERR_DRIVER (-3)     /* cuTensorMapEncodeTiled unavailable / failed */
+#define EN_ERR_ARCH (-4)       /* device is not sm_100 */
+
+#define EN_MODE_SEMIHARD 0     /* datagenerators.py:196-199 */
+#define EN_MODE_HARDEST 1      /* datagenerators.py:188-190 */
+#define EN_MODE_RANDOM_HARD 2  /* datagenerators.py:192-194 */
+
+const char* en_version(void);
+const char* en_last_error(void);
+/* Number of kernel launches issued by this thread through the library since the last reset (bench accounting). */
+int64_t en_launch_count(void);
+void en_launch_count_reset(void);
+
+/* ---------------------------------------------------------------- row-wise kernels (memory bound) */
+/* K.l2_normalize(x, axis=1): y = x * rsqrt(max(sum x^2, 1e-12)).  backbones.py:38,77,118 */
+int en_l2_normalize_fwd(const float* x, float* y, int64_t rows, int d, void* stream);
+int en_l2_normalize_bwd(const float* x, const float* gy, float* gx, int64_t rows, int d, void* stream);
+
+/* triplet_loss(margin)(y_true, y_pred): y_pred is (B, total_len) = [anchor | positive | negative];
+ * loss[b] = max(|a-p|^2 - |a-n|^2 + margin, 0).  losses_and_accuracies.py:26-42.  total_len % 3 must be 0. */
+int en_triplet_apn_fwd(const float* y_pred, int64_t B, int total_len, float margin, float* loss, void* stream);
+/* gy_pred[b, :] = gloss[b] * d loss[b] / d y_pred[b, :] */
+int en_triplet_apn_bwd(const float* y_pred, const float* gloss, int64_t B, int total_len, float margin,
+                       float* gy_pred, void* stream);
+
+/* contrastive_loss(y_true, y_pred) = mean(y*d^2 + (1-y)*max(1-d,0)^2), margin literal 1.
+ * losses_and_accuracies.py:4-11.  n = number of elements; loss is ONE float. */
+int en_contrastive_fwd(const float* y_true, const float* y_pred, int64_t n, float* loss, void* stream);
+int en_contrastive_bwd(const float* y_true, const float* y_pred, const float* gloss, int64_t n, float* gy_pred,
+                       void* stream);
+/* accuracy(y_true, y_pred) = mean(y_true == (y_pred < 0.5)).  losses_and_accuracies.py:47-50 */
+int en_pair_accuracy(const float* y_true, const float* y_pred, int64_t n, float* acc, void* stream);
+
+/* Siamese heads, models.py:217-228.  l2: dist[b] = sqrt(max(sum((e1-e2)^2), 1e-7));  l1: out = |e1 - e2| */
+int en_siamese_l2_fwd(const float* e1, const float* e2, int64_t B, int d, float* dist, void* stream);
+int en_siamese_l2_bwd(const float* e1, const float* e2, const float* gdist, int64_t B, int d, float* g1, float* g2,
+                      void* stream);
+int en_siamese_l1_fwd(const float* e1, const float* e2, int64_t n, float* out, void* stream);
+int en_siamese_l1_bwd(const float* e1, const float* e2, const float* gout, int64_t n, float* g1, float* g2,
+                      void* stream);
+
+/* ---------------------------------------------------------------- pairwise distances + in-batch mining */
+/* sklearn.metrics.pairwise_distances(x) as called at datagenerators.py:219, with sklearn's float32 semantics
+ * (float64 -2xy+|x|^2+|y|^2, cast f32, clamp >= 0, zero diagonal, sqrt unless `squared`).  out is (n, n).
+ * exact != 0: float64 CUDA-core path (bit-compatible with sklearn up to float64 summation order);
+ * exact == 0: tcgen05 3xTF32 path (diagnostics / large n). */
+size_t en_ws_bytes_pairwise(int64_t n, int d, int exact);
+int en_pairwise_dist(const float* x, int64_t n, int d, int squared, int exact, float* out, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* Per (anchor, positive) pair scan of the selection predicates of datagenerators.py:188-199 over ALL rows whose
+ * label differs from the anchor's, ascending row order, on loss = (D[a,p] - D[a,n]) + margin in float32:
+ *   hardest[p]   = row id of the first maximum of loss if that maximum is > 0, else -1
+ *   n_hard[p]    = #{n : loss > 0}
+ *   n_semi[p]    = #{n : 0 < loss < margin}
+ * D is the (n, n) matrix from en_pairwise_dist; pairs is (n_pairs, 2) int32 (anchor, positive). */
+int en_mine_batch_scan(const float* D, const int32_t* labels, int64_t n, const int32_t* pairs, int64_t n_pairs,
+                       float margin, int32_t* hardest, int32_t* n_hard, int32_t* n_semi, void* stream);
+/* The rank[p]-th candidate (0-based, ascending row id) of pair p under `mode` (EN_MODE_SEMIHARD or
+ * EN_MODE_RANDOM_HARD); -1 when rank[p] < 0 or out of range.  The host draws rank[p] from the legacy NumPy RNG
+ * in the reference's pair order, which reproduces np.random.choice(candidates) at datagenerators.py:194,199. */
+int en_mine_batch_select(const float* D, const int32_t* labels, int64_t n, const int32_t* pairs, int64_t n_pairs,
+                         float margin, int mode, const int32_t* rank, int32_t* selected, void* stream);
+
+/* The three selection callables of datagenerators.py:188-199 applied to ONE float32 loss vector (n values):
+ * out3 = { index of the first maximum if that maximum is > 0 else -1, #{loss > 0}, #{0 < loss < margin} };
+ * en_loss_select returns the rank-th (0-based, ascending index) candidate of `mode` in out1[0] (-1 if none). */
+int en_loss_scan(const float* loss_values, int64_t n, float margin, int32_t* out3, void* stream);
+int en_loss_select(const float* loss_values, int64_t n, float margin, int mode, int rank, int32_t* out1,
+                   void* stream);
+
+/* ---------------------------------------------------------------- fused in-batch losses (tcgen05 distance GEMM) */
+/* Batch-hard triplet loss (BASELINE.json north_star; Hermans et al. / Moindrot, cited at README.md:112,116 --
+ * not implemented by the reference).  emb (B, d), labels (B,).
+ *   loss (1 float) = mean_i hinge_i, hinge_i = max(hp_i - hn_i + margin, 0)   (soft: softplus(hp_i - hn_i))
+ * Saved for backward: hp_idx/hn_idx (B,) int32 (-1 = none), coef (B,) = d mean / d(hp_i - hn_i),
+ * hp/hn (B,) distances (squared or not).  The B x B matrix is never written to memory. */
+size_t en_ws_bytes_batch_hard(int64_t B, int d);
+int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared, int soft,
+                      float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef, void* ws,
+                      size_t ws_bytes, void* stream);
+/* gemb (B, d) = gloss[0] * d loss / d emb; gemb is fully overwritten. */
+int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int32_t* hp_idx, const int32_t* hn_idx,
+                      const float* hp, const float* hn, const float* coef, const float* gloss, float* gemb,
+                      void* stream);
+
+/* Batch-all triplet loss: sum over valid (i,j,k) of max(D_ij - D_ik + margin, 0) / #{terms > 1e-16}.
+ * out[0] = loss, out[1] = fraction of positive triplets.  max_positives >= largest class size - 1 (<= 64).
+ * stats (3 doubles, device): hinge sum, #positive terms, #valid triplets -- kept for the backward. */
+size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives);
+int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                     int max_positives, float* out, double* stats, void* ws, size_t ws_bytes, void* stream);
+int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                     int max_positives, const double* stats, const float* gloss, float* gemb, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* All-pairs contrastive loss: losses_and_accuracies.py:4-11 over every ordered pair i != j with
+ * y_ij = [label_i == label_j] and d_ij = sqrt(max(|e_i - e_j|^2, 1e-7)) (models.py:225).  loss is 1 float. */
+size_t en_ws_bytes_contrastive_allpairs(int64_t B, int d);
+int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float* loss, void* ws,
+                                size_t ws_bytes, void* stream);
+int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t B, int d, const float* gloss,
+                                float* gemb, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- encoding bank: nearest neighbours */
+/* Bank preparation (the `fit` of the KNeighborsClassifier-shaped object models.py:58 expects): splits the fp32
+ * bank shard into the two TF32 planes the tensor-core scan streams and computes squared row norms.
+ * dpad = en_bank_dpad(d); hi/lo are (n, dpad), norms (n,). */
+int en_bank_dpad(int d);
+int en_bank_prepare(const float* bank, int64_t n, int d, float* hi, float* lo, float* norms, void* stream);
+
+/* k nearest bank rows of every query, ordered by (exact distance, global id) -- kneighbors() at models.py:138,
+ * np.argmin at models.py:124 for k = 1.  Two stages inside one call: a tcgen05 3xTF32 scan keeps the best
+ * k + EN_KNN_SLACK candidates per query in registers, then those few are re-evaluated exactly in float64
+ * (sum (q-b)^2) and re-ranked, which makes ids independent of tensor-core rounding and of how the bank is sharded.
+ * bank / bank_hi / bank_lo / bank_norms describe THIS shard's n_bank rows whose global ids start at id_offset.
+ * exclude_label (may be NULL): candidates whose bank label equals query_labels[q] are skipped -- offline
+ * hard-negative mining over a bank (BASELINE config 4).  Outputs: d2 (Q, k) float64 squared distances,
+ * ids (Q, k) int64 (-1 = fewer than k candidates), ascending. */
+#define EN_KNN_SLACK 3
+#define EN_KNN_MAX_K 29
+size_t en_ws_bytes_knn(int64_t Q, int64_t n_bank, int d, int k);
+int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_hi,
+                      const float* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                      const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids, void* ws,
+                      size_t ws_bytes, void* stream);
+/* Small-batch variant for the reference's actual call pattern (one query per predict(), models.py:122,135):
+ * a CUDA-core fp32 streaming scan bounded by HBM bandwidth; Q <= EN_KNN_STREAM_MAX_Q.  Same outputs. */
+#define EN_KNN_STREAM_MAX_Q 8
+size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k);
+int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                       int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes, void* stream);
+/* Merge P per-shard lists (P, Q, k) (as gathered by an NCCL all-gather) into the global top-k by (d2, id). */
+int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
+                 int64_t* ids, void* stream);
+/* distances (Q, k) float32 = sqrt(d2). */
+int en_knn_finalize_dist(const double* d2, int64_t n, float* dist, void* stream);
+/* Majority vote of KNeighborsClassifier.predict (models.py:136): labels of the k neighbours are looked up by
+ * global id in `labels` (n_total,), ties resolve to the smallest label id.  pred is (Q,) int32. */
+int en_knn_vote(const int64_t* ids, int64_t Q, int k, const int32_t* labels, int64_t n_total, int32_t* pred,
+                void* stream);
+/* calculate_prediction_accuracy, models.py:144-161: counts[0] += #(pred == label), counts[1] += #(label among the
+ * labels of the first 5 neighbours).  counts is 2 x int64 and must be zeroed by the caller. */
+int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* query_labels, int64_t Q, int k_ids,
+                    const int32_t* labels, int64_t n_total, int64_t* counts, void* stream);
+
+/* ---------------------------------------------------------------- synthetic data (bench / tests) */
+/* x[r, c] = u(r, c) in [-1, 1) from a splitmix64 counter hash; optional class structure:
+ * x = relu?(centre[label(r)] + noise * u) with label(r) = (r + row_offset) / rows_per_class (class-major) when
+ * rows_per_class > 0, else (r + row_offset) % n_classes.  Bit-identical to embeddingnet_b200.synth (NumPy). */
+int en_synth_fill(float* x, int64_t rows, int d, int64_t row_offset, uint64_t seed_centre, uint64_t seed_noise,
+                  int64_t n_classes, int64_t rows_per_class, float noise, int relu, int32_t* labels_out,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMBEDDINGNET_B200_H */

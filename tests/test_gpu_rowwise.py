@@ -1,0 +1,97 @@
+"""GPU parity: memory-bound row-wise kernels vs the oracle and the golden outputs of the reference's own code."""
+import numpy as np
+import pytest
+import torch
+
+from embeddingnet_b200 import synth
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    return lib_built
+
+
+def cuda(x, grad=False):
+    t = torch.tensor(x, device="cuda")
+    t.requires_grad_(grad)
+    return t
+
+
+@pytest.mark.parametrize("name,B,d", [("lac_small", 16, 32), ("lac_refcfg", 60, 256)])
+def test_lac_against_reference_outputs(golden, name, B, d):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    y, _ = synth.make_numpy(B, 3 * d, seed_noise=4242 + B)
+    yp = cuda(y, True)
+    loss = lac.triplet_loss(0.5)(None, yp)
+    assert loss.shape == (B,)
+    scale = float(np.max(np.sum((y[:, :d] - y[:, d:2 * d]) ** 2, axis=1)))
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), golden[name + "_triplet_loss"], rtol=1e-5,
+                               atol=1e-6 * scale)
+    (loss * cuda(golden[name + "_upstream"])).sum().backward()
+    np.testing.assert_allclose(yp.grad.cpu().numpy(), golden[name + "_triplet_grad"], rtol=1e-4, atol=1e-5)
+    dcol, _ = synth.make_numpy(B, 1, seed_noise=555 + B)
+    dcol = np.abs(dcol) * 1.6
+    yt = (np.arange(B) % 2).astype(np.float32).reshape(B, 1)
+    dp = cuda(dcol, True)
+    cl = lac.contrastive_loss(cuda(yt), dp)
+    np.testing.assert_allclose(cl.item(), golden[name + "_contrastive_loss"], rtol=1e-5)
+    cl.backward()
+    np.testing.assert_allclose(dp.grad.cpu().numpy(), golden[name + "_contrastive_grad"], rtol=1e-4, atol=1e-7)
+    assert lac.accuracy(cuda(yt), cuda(dcol)).item() == golden[name + "_accuracy"]
+
+
+def test_triplet_loss_rejects_bad_width():
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    with pytest.raises(ValueError):
+        lac.triplet_loss(0.5)(None, torch.zeros(4, 10, device="cuda"))
+
+
+@pytest.mark.parametrize("B,d", [(1, 1), (7, 5), (128, 256), (4096, 512), (33, 1000)])
+def test_l2_normalize_fwd_bwd(B, d):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, _ = synth.make_numpy(B, d, seed_noise=11, relu=True)
+    if B > 2:
+        x[1] = 0  # post-ReLU rows can be all zero (bb:116-119) -> output 0
+    up, _ = synth.make_numpy(B, d, seed_noise=12)
+    xt = cuda(x, True)
+    y = lac.l2_normalize(xt)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), O.l2_normalize(x), rtol=1e-5, atol=1e-7)
+    (y * cuda(up)).sum().backward()
+    ref = O.l2_normalize_grad(x, up)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max() + 1e-7)
+
+
+@pytest.mark.parametrize("B,d", [(1, 3), (60, 256), (513, 129)])
+def test_siamese_heads(B, d):
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    e1, _ = synth.make_numpy(B, d, seed_noise=21)
+    e2, _ = synth.make_numpy(B, d, seed_noise=22)
+    if B > 1:
+        e2[0] = e1[0]  # clamp branch: sqrt(max(0, 1e-7))
+    up, _ = synth.make_numpy(B, 1, seed_noise=23)
+    a, b = cuda(e1, True), cuda(e2, True)
+    dist = lac.siamese_l2_distance(a, b)
+    assert dist.shape == (B, 1)
+    np.testing.assert_allclose(dist.detach().cpu().numpy(), O.siamese_l2(e1, e2), rtol=1e-5)
+    (dist * cuda(up)).sum().backward()
+    g1, g2 = O.siamese_l2_grad(e1, e2, up)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g1, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), g2, rtol=1e-4, atol=1e-6)
+    l1 = lac.siamese_l1_distance(cuda(e1), cuda(e2))
+    np.testing.assert_array_equal(l1.cpu().numpy(), O.siamese_l1(e1, e2))
+
+
+def test_synth_device_matches_numpy():
+    for kw in (dict(), dict(n_classes=10, rows_per_class=4, noise=0.5, relu=True), dict(n_classes=7, noise=0.25)):
+        x, l = synth.make_numpy(100, 33, row_offset=5, **kw)
+        xd, ld = synth.make_device(100, 33, row_offset=5, **kw)
+        np.testing.assert_array_equal(xd.cpu().numpy(), x)
+        if kw:
+            np.testing.assert_array_equal(ld.cpu().numpy(), l)

@@ -29,15 +29,16 @@ struct EpStore {
     int64_t N;
   };
   struct Row {};
-  static __device__ void item_begin(const Params&, Row&, int64_t, bool, int, int) {}
-  static __device__ void chunk(const Params& p, Row&, int64_t row, bool valid, int64_t col0, const float (&dot)[32]) {
+  static constexpr int kSmemBytes = 0;
+  static __device__ void item_begin(const Params&, Row&, const tc::Ctx&, int64_t, bool, int, int) {}
+  static __device__ void chunk(const Params& p, Row&, const tc::Ctx&, int64_t row, bool valid, int64_t col0, const float (&dot)[32]) {
     if (!valid) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (col0 + j < p.N) p.out[row * p.ld + col0 + j] = dot[j];
   }
-  static __device__ void tile_end(const Params&, Row&, int64_t, bool, int) {}
-  static __device__ void item_end(const Params&, Row&, int64_t, bool, int, int) {}
+  static __device__ void tile_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int) {}
+  static __device__ void item_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int, int) {}
 };
 
 struct EpRowMax {
@@ -48,13 +49,14 @@ struct EpRowMax {
   struct Row {
     float m;
   };
-  static __device__ void item_begin(const Params&, Row& r, int64_t, bool, int, int) { r.m = -3.4e38f; }
-  static __device__ void chunk(const Params&, Row& r, int64_t, bool, int64_t, const float (&dot)[32]) {
+  static constexpr int kSmemBytes = 0;
+  static __device__ void item_begin(const Params&, Row& r, const tc::Ctx&, int64_t, bool, int, int) { r.m = -3.4e38f; }
+  static __device__ void chunk(const Params&, Row& r, const tc::Ctx&, int64_t, bool, int64_t, const float (&dot)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) r.m = fmaxf(r.m, dot[j]);
   }
-  static __device__ void tile_end(const Params&, Row&, int64_t, bool, int) {}
-  static __device__ void item_end(const Params& p, Row& r, int64_t row, bool valid, int, int split) {
+  static __device__ void tile_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int) {}
+  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
     if (valid) p.out[row * p.n_splits + split] = r.m;
   }
 };
