@@ -735,7 +735,9 @@ int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d,
   EN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
   tc::Shape sh = tc::make_shape(B, B, d, tiles_n, 3);  // one column tile per item: candidates are per tile
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
+  prof_begin(st);
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
+  prof_end(st);
   ++launch_counter();
   batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft,
                                                      hp_idx, hn_idx, hp, hn, coef, partial, counter, loss);
@@ -810,7 +812,9 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
       emb, labels, B, d, squared, max_positives, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
   EN_LAUNCHED("collect_positives_kernel");
   EpBatchAll::Params ep{labels, o.norms, pl.pos_d, pl.pos_n, partial, B, max_positives, sh.n_splits, squared, margin};
+  prof_begin(st);
   EN_CUDA(tc::launch<EpBatchAll>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
+  prof_end(st);
   ++launch_counter();
   pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits, pl.pos_n, B, 0, out, stats);
   EN_LAUNCHED("pair_reduce_kernel");
@@ -881,7 +885,9 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
   PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_fwd: workspace too small or misaligned");
   EpContrastive::Params ep{labels, o.norms, partial, B, sh.n_splits};
+  prof_begin(st);
   EN_CUDA(tc::launch<EpContrastive>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
+  prof_end(st);
   ++launch_counter();
   pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits, nullptr, B, 1, loss, nullptr);
   EN_LAUNCHED("pair_reduce_kernel");

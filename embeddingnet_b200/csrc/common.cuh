@@ -63,6 +63,11 @@ struct Workspace {
   bool ok() const { return off <= size && (reinterpret_cast<uintptr_t>(base) & 255) == 0; }
 };
 
+// Optional timing of the dominant kernel of a call: when enabled (en_prof_enable) the entry points bracket their
+// distance-GEMM / streaming-scan launch with CUDA events recorded on the launching stream.
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
+
 int device_sm_count();  // SM count of the current device (cached per device), <0 on error
 int check_sm100();      // 0 when the current device is compute capability 10.x
 

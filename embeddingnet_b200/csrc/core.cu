@@ -13,6 +13,34 @@ int64_t& launch_counter() {
   return c;
 }
 
+namespace {
+struct ProfState {
+  bool on = false;
+  bool have = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+ProfState& prof() {
+  static thread_local ProfState p;
+  return p;
+}
+}  // namespace
+
+void prof_begin(cudaStream_t st) {
+  ProfState& p = prof();
+  if (!p.on) return;
+  if (!p.e0) {
+    cudaEventCreate(&p.e0);
+    cudaEventCreate(&p.e1);
+  }
+  cudaEventRecord(p.e0, st);
+}
+void prof_end(cudaStream_t st) {
+  ProfState& p = prof();
+  if (!p.on || !p.e0) return;
+  cudaEventRecord(p.e1, st);
+  p.have = true;
+}
+
 int device_sm_count() {
   static int cache[64] = {0};
   int dev = 0;
@@ -85,6 +113,21 @@ const char* en_version(void) { return "embeddingnet_b200 0.1.0 (sm_100a)"; }
 const char* en_last_error(void) { return last_error_buf(); }
 int64_t en_launch_count(void) { return launch_counter(); }
 void en_launch_count_reset(void) { launch_counter() = 0; }
+
+int en_prof_enable(int on) {
+  prof().on = on != 0;
+  prof().have = false;
+  return EN_OK;
+}
+
+int en_prof_last_ms(float* ms_host) {
+  EN_REQUIRE(ms_host != nullptr, "en_prof_last_ms: null output");
+  ProfState& p = prof();
+  if (!p.have) return fail(EN_ERR_ARG, "en_prof_last_ms: no timed launch recorded (call en_prof_enable(1) first)");
+  EN_CUDA(cudaEventSynchronize(p.e1));
+  EN_CUDA(cudaEventElapsedTime(ms_host, p.e0, p.e1));
+  return EN_OK;
+}
 
 int en_synth_fill(float* x, int64_t rows, int d, int64_t row_offset, uint64_t seed_centre, uint64_t seed_noise,
                   int64_t n_classes, int64_t rows_per_class, float noise, int relu, int32_t* labels_out,

@@ -336,7 +336,9 @@ int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh
              const tc::Shape& sh, const float* bank_norms, const int32_t* bank_labels, const int32_t* query_labels,
              Cand* lists, int64_t n_bank, int sms, cudaStream_t st) {
   typename EpTopK<KC>::Params ep{bank_norms, bank_labels, query_labels, lists, n_bank, sh.n_splits};
+  prof_begin(st);
   EN_CUDA(tc::launch<EpTopK<KC>>(qh, ql, bh, bl, sh, ep, sms, st));
+  prof_end(st);
   ++launch_counter();
   return EN_OK;
 }
@@ -465,8 +467,10 @@ int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank
     if (smem > 48 * 1024)                                                                                       \
       EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                    static_cast<int>(smem)));                                                    \
+    prof_begin(st);                                                                                             \
     knn_stream_kernel<KCV><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank, \
                                                                      rpw, lists, n_lists);                      \
+    prof_end(st);                                                                                               \
     EN_LAUNCHED("knn_stream_kernel");                                                                           \
     return run_rerank<KCV>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, st);                     \
   } while (0)

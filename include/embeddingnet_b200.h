@@ -42,6 +42,12 @@ const char* en_last_error(void);
 int64_t en_launch_count(void);
 void en_launch_count_reset(void);
 
+/* Measurement hook for bench.py: while enabled (per thread), entry points that contain a distance GEMM or a bank
+ * scan record CUDA events immediately around THAT launch on the caller's stream; en_prof_last_ms synchronises on
+ * the second event and returns the kernel's duration in milliseconds (host pointer). */
+int en_prof_enable(int on);
+int en_prof_last_ms(float* ms_host);
+
 /* ---------------------------------------------------------------- row-wise kernels (memory bound) */
 /* K.l2_normalize(x, axis=1): y = x * rsqrt(max(sum x^2, 1e-12)).  backbones.py:38,77,118 */
 int en_l2_normalize_fwd(const float* x, float* y, int64_t rows, int d, void* stream);

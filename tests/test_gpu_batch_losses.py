@@ -132,7 +132,6 @@ def test_batch_hard_full_size_properties():
     loss2.backward()
     assert abs(loss2.item() - loss.item()) <= 2e-6 * abs(loss.item())
     assert rel_err(e2.grad.cpu().numpy(), e.grad.cpu().numpy()[perm]) < 1e-5
-    _, g = O.batch_hard_grad(lab[:0], x[:0]) if False else (None, None)
 
 
 BA_SHAPES = [(32, 8, 128, True, False), (16, 8, 256, True, True), (7, 5, 33, False, True), (37, 9, 100, True, True),
@@ -183,8 +182,7 @@ def test_contrastive_all_pairs_fwd_bwd(ncls, per, d, norm, shuf):
 
 
 def test_batch_all_and_contrastive_full_size():
-    """BASELINE config 3 (B = 4096, d = 512, 512 classes x 8): forward vs the float64 oracle, backward finite and
-    consistent with a finite-difference directional derivative."""
+    """BASELINE config 3 (B = 4096, d = 512, 512 classes x 8): forward and backward vs the float64 oracle."""
     from embeddingnet_b200 import losses_and_accuracies as lac
 
     x, lab = make_batch(512, 8, 512, True, True)
@@ -195,17 +193,12 @@ def test_batch_all_and_contrastive_full_size():
     loss.backward()
     g = e.grad.cpu().numpy().astype(np.float64)
     assert np.isfinite(g).all() and np.abs(g).max() > 0
-    # directional derivative in float64 from the oracle
-    v = np.random.RandomState(2).randn(*x.shape)
-    v /= np.linalg.norm(v)
-    h = 1e-3
-    lp = O.batch_all(lab, (x.astype(np.float64) + h * v), 0.5, False)
-    lm = O.batch_all(lab, (x.astype(np.float64) - h * v), 0.5, False)
-    # use unrounded float64 losses: recompute without the float32 cast
-    fd = (float(lp["loss"]) - float(lm["loss"])) / (2 * h)
-    an = float((g * v).sum())
-    assert abs(fd - an) <= 5e-2 * max(abs(fd), abs(an)) + 1e-6
+    ga = O.batch_all_grad_analytic(lab, x, 0.5, False)
+    assert rel_err(g, ga) < 1e-4
     x7 = (x * 0.7).astype(np.float32)
     refc = O.contrastive_allpairs(lab, x7)
-    lc = lac.contrastive_loss_all_pairs()(lab, x7)
+    e7 = torch.tensor(x7, device="cuda", requires_grad=True)
+    lc = lac.contrastive_loss_all_pairs()(lab, e7)
     assert abs(lc.item() - float(refc)) <= 1e-5 * float(refc)
+    lc.backward()
+    assert rel_err(e7.grad.cpu().numpy(), O.contrastive_allpairs_grad_analytic(lab, x7)) < 1e-4

@@ -124,6 +124,20 @@ def test_batch_hard_and_all_small_known_answer():
     np.testing.assert_allclose(g.reshape(-1), np.array([0, 1, -2, 1]) / 4.0)
 
 
+def test_analytic_gradients_match_autograd():
+    from conftest import unit_rows
+
+    x, lab = synth.make_numpy(60, 24, n_classes=10, rows_per_class=6, noise=0.5, relu=True)
+    x = unit_rows(x)
+    for squared in (False, True):
+        _, g = O.batch_all_grad(lab, x, 0.5, squared)
+        ga = O.batch_all_grad_analytic(lab, x, 0.5, squared)
+        np.testing.assert_allclose(ga, g, rtol=1e-5, atol=1e-9)
+    x7 = (x * 0.7).astype(np.float32)
+    _, g = O.contrastive_allpairs_grad(lab, x7)
+    np.testing.assert_allclose(O.contrastive_allpairs_grad_analytic(lab, x7), g, rtol=1e-5, atol=1e-10)
+
+
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present (GPU box)")
 def test_oracle_matches_reference_live():
     import torch
