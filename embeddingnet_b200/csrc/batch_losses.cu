@@ -34,18 +34,34 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ e, int d, i
 // =====================================================================================================
 // Batch-hard
 // =====================================================================================================
-// Candidate record per (anchor row, column tile): the two largest same-label and the two smallest other-label
-// proxies t = |b|^2 - 2 a.b (monotone in the distance for a fixed anchor), plus the row maximum.
+// Candidate record per (anchor row, column tile, column half): the two largest same-label and the two smallest
+// other-label proxies t = |b|^2 - 2 a.b (monotone in the distance for a fixed anchor).
 struct BhCand {
-  float p1, p2, n1, n2, rmax;
-  int p1i, p2i, n1i, n2i, rmaxi;
+  float p1, p2, n1, n2;
+  int p1i, p2i, n1i, n2i;
 };
+
+// branch-free running top-2 (value, index); masked elements carry -kBig / +kBig and never win
+__device__ __forceinline__ void top2_max(float& v1, int& i1, float& v2, int& i2, float t, int c) {
+  const bool g1 = t > v1, g2 = t > v2;
+  v2 = g1 ? v1 : (g2 ? t : v2);
+  i2 = g1 ? i1 : (g2 ? c : i2);
+  v1 = g1 ? t : v1;
+  i1 = g1 ? c : i1;
+}
+__device__ __forceinline__ void top2_min(float& v1, int& i1, float& v2, int& i2, float t, int c) {
+  const bool g1 = t < v1, g2 = t < v2;
+  v2 = g1 ? v1 : (g2 ? t : v2);
+  i2 = g1 ? i1 : (g2 ? c : i2);
+  v1 = g1 ? t : v1;
+  i1 = g1 ? c : i1;
+}
 
 struct EpBatchHard {
   struct Params {
     const int32_t* labels;
     const float* norms;
-    BhCand* cand;  // [B][tiles_n]
+    BhCand* cand;  // [B][tiles_n][EPI_H]
     int64_t B;
     int tiles_n;
   };
@@ -57,90 +73,99 @@ struct EpBatchHard {
   static __device__ void reset(Row& r) {
     r.c.p1 = r.c.p2 = -kBig;
     r.c.n1 = r.c.n2 = kBig;
-    r.c.rmax = -kBig;
-    r.c.p1i = r.c.p2i = r.c.n1i = r.c.n2i = r.c.rmaxi = -1;
+    r.c.p1i = r.c.p2i = r.c.n1i = r.c.n2i = -1;
   }
   static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int) {
     r.la = valid ? p.labels[row] : 0;
     reset(r);
   }
-  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int64_t col0,
+  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int64_t col0,
                                const float (&dot)[32]) {
-    if (col0 >= p.B) return;
+    if (col0 >= p.B) return;  // warp-uniform
+    tc::stage_columns(ctx, p.norms, p.labels, col0, p.B);
+    const float4* n4 = reinterpret_cast<const float4*>(ctx.wf);
+    const int4* l4 = reinterpret_cast<const int4*>(ctx.wi);
+    const int c0 = static_cast<int>(col0);
+    // rows and columns are both tiled in aligned groups of 32, so the diagonal can only fall into the chunk whose
+    // first column equals this warp's first row
+    const bool edge = (col0 + 32 > p.B) || (col0 == row - ctx.lane);
+    if (!edge) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t c = col0 + j;
-      if (c < p.B && c != row) {
-        const float t = fmaf(-2.f, dot[j], __ldg(&p.norms[c]));
-        const int ci = static_cast<int>(c);
-        if (t > r.c.rmax) { r.c.rmax = t; r.c.rmaxi = ci; }
-        if (__ldg(&p.labels[c]) == r.la) {
-          if (t > r.c.p1) { r.c.p2 = r.c.p1; r.c.p2i = r.c.p1i; r.c.p1 = t; r.c.p1i = ci; }
-          else if (t > r.c.p2) { r.c.p2 = t; r.c.p2i = ci; }
-        } else {
-          if (t < r.c.n1) { r.c.n2 = r.c.n1; r.c.n2i = r.c.n1i; r.c.n1 = t; r.c.n1i = ci; }
-          else if (t < r.c.n2) { r.c.n2 = t; r.c.n2i = ci; }
+      for (int g = 0; g < 8; ++g) {
+        const float4 nb = n4[g];
+        const int4 lb = l4[g];
+        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        const int lbv[4] = {lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = g * 4 + u;
+          const float t = fmaf(-2.f, dot[j], nbv[u]);
+          const bool same = lbv[u] == r.la;
+          top2_max(r.c.p1, r.c.p1i, r.c.p2, r.c.p2i, same ? t : -kBig, c0 + j);
+          top2_min(r.c.n1, r.c.n1i, r.c.n2, r.c.n2i, same ? kBig : t, c0 + j);
         }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t c = col0 + j;
+        const bool ok = c < p.B && c != row;
+        const float t = fmaf(-2.f, dot[j], ctx.wf[j]);
+        const bool same = ctx.wi[j] == r.la;
+        top2_max(r.c.p1, r.c.p1i, r.c.p2, r.c.p2i, (ok && same) ? t : -kBig, c0 + j);
+        top2_min(r.c.n1, r.c.n1i, r.c.n2, r.c.n2i, (ok && !same) ? t : kBig, c0 + j);
       }
     }
   }
-  static __device__ void tile_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int tile_n) {
-    if (valid) p.cand[row * p.tiles_n + tile_n] = r.c;
+  static __device__ void tile_end(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid,
+                                  int tile_n) {
+    if (valid) {
+      // two 16-byte stores
+      BhCand* out = p.cand + (row * p.tiles_n + tile_n) * tc::EPI_H + ctx.half;
+      reinterpret_cast<float4*>(out)[0] = make_float4(r.c.p1, r.c.p2, r.c.n1, r.c.n2);
+      reinterpret_cast<int4*>(out)[1] = make_int4(r.c.p1i, r.c.p2i, r.c.n1i, r.c.n2i);
+    }
     reset(r);
   }
   static __device__ void item_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int, int) {}
 };
 
 // One warp per anchor: pick the winners among the per-tile candidates.  Every candidate whose proxy lies within the
-// tensor-core error band of the best one is re-evaluated exactly; ties resolve to the lowest index.
+// tensor-core error band of the best one is re-evaluated exactly (float64); ties resolve to the lowest index.
 struct BhPick {
   double d2;
   int idx;
 };
 
-template <bool kMax, int N>
-__device__ __forceinline__ BhPick bh_pick(const float* __restrict__ emb, int d, const float* __restrict__ norms,
-                                          int64_t row, const float (&vals)[N], const int (&idxs)[N], int lane) {
-  // vals/idxs: this lane's candidates (register arrays, statically indexed)
-  const float na = norms[row];
-  float best = kMax ? -kBig : kBig;
-#pragma unroll
-  for (int q = 0; q < N; ++q)
-    if (idxs[q] >= 0) best = kMax ? fmaxf(best, vals[q]) : fminf(best, vals[q]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    best = kMax ? fmaxf(best, ob) : fminf(best, ob);
+template <bool kMax>
+__device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict__ emb, int d,
+                                            const float* __restrict__ norms, float na, int64_t row, float best,
+                                            float val, int idx, int lane) {
+  // error band of the 3xTF32 dot product: a few 1e-6 |a||b| <= 1e-5 (|a|^2 + |b|^2) / 2; the proxy error is twice
+  // that, and both the best and the contender carry it
+  bool contender = false;
+  if (idx >= 0) {
+    const float band = 2.0e-5f * (na + norms[idx]) + 1e-30f;
+    contender = kMax ? (val >= best - band) : (val <= best + band);
   }
-  BhPick win{kMax ? -1.0 : 1e300, -1};
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    // error band of the 3xTF32 dot product: ~4e-6 |a||b| <= 2e-6 (|a|^2 + |b|^2); proxy error is twice that
-    bool contender = false;
-    if (idxs[q] >= 0) {
-      const float band = 1.0e-5f * (na + norms[idxs[q]]) + 1e-30f;
-      contender = kMax ? (vals[q] >= best - 2.f * band) : (vals[q] <= best + 2.f * band);
-    }
-    unsigned m = __ballot_sync(0xffffffffu, contender);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int ci = __shfl_sync(0xffffffffu, idxs[q], src);
-      const double d2 = exact_d2(emb, d, row, ci, lane);
-      const bool better = kMax ? (d2 > win.d2 || (d2 == win.d2 && ci < win.idx))
-                               : (d2 < win.d2 || (d2 == win.d2 && ci < win.idx));
-      if (win.idx < 0 || better) {
-        win.d2 = d2;
-        win.idx = ci;
-      }
+  unsigned m = __ballot_sync(0xffffffffu, contender);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int ci = __shfl_sync(0xffffffffu, idx, src);
+    const double d2 = exact_d2(emb, d, row, ci, lane);
+    const bool better = kMax ? (d2 > win.d2 || (d2 == win.d2 && ci < win.idx))
+                             : (d2 < win.d2 || (d2 == win.d2 && ci < win.idx));
+    if (win.idx < 0 || better) {
+      win.d2 = d2;
+      win.idx = ci;
     }
   }
-  return win;
 }
 
 __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                            const float* __restrict__ norms, const BhCand* __restrict__ cand,
-                                           int64_t B, int d, int tiles_n, float margin, int squared, int soft,
+                                           int64_t B, int d, int n_cand, float margin, int squared, int soft,
                                            int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
                                            float* __restrict__ hp_out, float* __restrict__ hn_out,
                                            float* __restrict__ coef, double* __restrict__ partial,
@@ -150,35 +175,46 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   double hinge = 0.0;
   if (row < B) {
-    // gather: lane handles tiles lane, lane+32, ... ; 2 candidates per tile and class
-    constexpr int MAXQ = 8;  // up to 4 tiles per lane => B <= 128*32*4 = 16384 per pass; loop for more
-    BhPick pos{-1.0, -1}, neg{1e300, -1}, rmx{-1.0, -1};
-    for (int t0 = 0; t0 < tiles_n; t0 += 32 * (MAXQ / 2)) {
-      float pv[MAXQ], nv[MAXQ], rv[MAXQ / 2];
-      int pi[MAXQ], ni[MAXQ], ri[MAXQ / 2];
-#pragma unroll
-      for (int q = 0; q < MAXQ / 2; ++q) {
-        const int t = t0 + q * 32 + lane;
-        if (t < tiles_n) {
-          const BhCand c = cand[row * tiles_n + t];
-          pv[2 * q] = c.p1; pi[2 * q] = c.p1i; pv[2 * q + 1] = c.p2; pi[2 * q + 1] = c.p2i;
-          nv[2 * q] = c.n1; ni[2 * q] = c.n1i; nv[2 * q + 1] = c.n2; ni[2 * q + 1] = c.n2i;
-          rv[q] = c.rmax; ri[q] = c.rmaxi;
-        } else {
-          pi[2 * q] = pi[2 * q + 1] = ni[2 * q] = ni[2 * q + 1] = ri[q] = -1;
-          pv[2 * q] = pv[2 * q + 1] = nv[2 * q] = nv[2 * q + 1] = rv[q] = 0.f;
-        }
-      }
-      const BhPick a = bh_pick<true, MAXQ>(emb, d, norms, row, pv, pi, lane);
-      if (a.idx >= 0 && (pos.idx < 0 || a.d2 > pos.d2 || (a.d2 == pos.d2 && a.idx < pos.idx))) pos = a;
-      const BhPick b = bh_pick<false, MAXQ>(emb, d, norms, row, nv, ni, lane);
-      if (b.idx >= 0 && (neg.idx < 0 || b.d2 < neg.d2 || (b.d2 == neg.d2 && b.idx < neg.idx))) neg = b;
-      const BhPick c = bh_pick<true, MAXQ / 2>(emb, d, norms, row, rv, ri, lane);
-      if (c.idx >= 0 && (rmx.idx < 0 || c.d2 > rmx.d2 || (c.d2 == rmx.d2 && c.idx < rmx.idx))) rmx = c;
+    const BhCand* mine = cand + row * n_cand;
+    const float na = norms[row];
+    // pass 1: best proxies over all records
+    float bp = -kBig, bn = kBig;
+    for (int t = lane; t < n_cand; t += 32) {
+      const float4 v = reinterpret_cast<const float4*>(mine + t)[0];
+      bp = fmaxf(bp, v.x);  // p1 >= p2
+      bn = fminf(bn, v.z);  // n1 <= n2
     }
-    // Moindrot: hardest positive = max(mask * D) (0 without positives); hardest negative =
-    // min(D + rowmax * (1 - mask_neg)) which degenerates to the row maximum when the anchor has no negatives.
-    if (neg.idx < 0) neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+      bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+    }
+    // pass 2: exact re-evaluation of everything inside the band
+    BhPick pos{-1.0, -1}, neg{1e300, -1};
+    for (int t0 = 0; t0 < n_cand; t0 += 32) {
+      const int t = t0 + lane;
+      float4 v = make_float4(-kBig, -kBig, kBig, kBig);
+      int4 ix = make_int4(-1, -1, -1, -1);
+      if (t < n_cand) {
+        v = reinterpret_cast<const float4*>(mine + t)[0];
+        ix = reinterpret_cast<const int4*>(mine + t)[1];
+      }
+      bh_consider<true>(pos, emb, d, norms, na, row, bp, v.x, ix.x, lane);
+      bh_consider<true>(pos, emb, d, norms, na, row, bp, v.y, ix.y, lane);
+      bh_consider<false>(neg, emb, d, norms, na, row, bn, v.z, ix.z, lane);
+      bh_consider<false>(neg, emb, d, norms, na, row, bn, v.w, ix.w, lane);
+    }
+    if (neg.idx < 0) {
+      // No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row
+      // maximum; a degenerate batch, handled exactly by a brute-force scan (never on a training path).
+      BhPick rmx{-1.0, -1};
+      for (int64_t j = 0; j < B; ++j) {
+        if (j == row) continue;
+        const double d2 = exact_d2(emb, d, row, j, lane);
+        if (rmx.idx < 0 || d2 > rmx.d2) { rmx.d2 = d2; rmx.idx = static_cast<int>(j); }
+      }
+      neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
+    }
     const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
     const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
     const double z = hp - hn;
@@ -295,7 +331,7 @@ __global__ void batch_hard_bwd_scatter_kernel(const float* __restrict__ emb, int
 // =====================================================================================================
 // Batch-all / all-pairs contrastive: shared pieces
 // =====================================================================================================
-constexpr int kMaxPos = 64;  // largest supported (class size - 1)
+constexpr int kMaxPos = 63;  // largest supported (class size - 1); bounded by the epilogue's shared-memory budget
 
 // One warp per anchor: list its positives (same label, j != i, ascending j) with exact distances.
 __global__ void collect_positives_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
@@ -343,7 +379,7 @@ struct EpBatchAll {
     const float* norms;
     const float* pos_d;    // [B][cap]
     const int32_t* pos_n;  // [B]
-    PairPartial* partial;  // [B][n_splits]
+    PairPartial* partial;  // [B][n_splits][EPI_H]
     int64_t B;
     int cap, n_splits, squared;
     float margin;
@@ -357,11 +393,13 @@ struct EpBatchAll {
     double sum;
     unsigned long long cnt;
   };
-  static constexpr int kSmemBytes = kMaxPos * tc::BM * 4;  // positives, transposed: [slot][row in tile]
+  static constexpr int kSmemBytes = kMaxPos * tc::BM * 4;  // positives + margin, transposed: [slot][row in tile]
   static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int, int) {
     r.la = valid ? p.labels[row] : 0;
     r.na = valid ? p.norms[row] : 0.f;
     r.npos = valid ? p.pos_n[row] : 0;
+    // both column-half threads of a row write the same values to the same slots (idempotent); each thread only
+    // ever reads its own row's column, after its own writes
     float* sm = reinterpret_cast<float*>(ctx.smem);
     for (int s = 0; s < r.npos; ++s) sm[s * tc::BM + ctx.erow] = p.pos_d[row * p.cap + s] + p.margin;
     r.sum = 0.0;
@@ -371,13 +409,14 @@ struct EpBatchAll {
   }
   static __device__ void chunk(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int64_t col0,
                                const float (&dot)[32]) {
-    if (col0 >= p.B || r.npos == 0) return;
+    if (col0 >= p.B) return;
+    tc::stage_columns(ctx, p.norms, p.labels, col0, p.B);
     const float* sm = reinterpret_cast<const float*>(ctx.smem) + ctx.erow;
+    const int ncols = static_cast<int>(p.B - col0 < 32 ? p.B - col0 : 32);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int64_t c = col0 + j;
-      if (c < p.B && __ldg(&p.labels[c]) != r.la) {
-        const float d2 = fmaxf(r.na + __ldg(&p.norms[c]) - 2.f * dot[j], 0.f);
+      if (j < ncols && ctx.wi[j] != r.la) {
+        const float d2 = fmaxf(r.na + ctx.wf[j] - 2.f * dot[j], 0.f);
         const float dn = p.squared ? d2 : sqrtf(d2);
         for (int s = 0; s < r.npos; ++s) {
           const float t = sm[s * tc::BM] - dn;  // D_ap + margin - D_an
@@ -395,8 +434,9 @@ struct EpBatchAll {
     r.tile_sum = 0.f;
     r.tile_cnt = 0;
   }
-  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
-    if (valid) p.partial[row * p.n_splits + split] = PairPartial{r.sum, r.cnt};
+  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int,
+                                  int split) {
+    if (valid) p.partial[(row * p.n_splits + split) * tc::EPI_H + ctx.half] = PairPartial{r.sum, r.cnt};
   }
 };
 
@@ -405,7 +445,7 @@ struct EpContrastive {
   struct Params {
     const int32_t* labels;
     const float* norms;
-    PairPartial* partial;
+    PairPartial* partial;  // [B][n_splits][EPI_H]
     int64_t B;
     int n_splits;
   };
@@ -422,29 +462,26 @@ struct EpContrastive {
     r.sum = 0.0;
     r.tile_sum = 0.f;
   }
-  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int64_t col0,
+  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int64_t col0,
                                const float (&dot)[32]) {
     if (col0 >= p.B) return;
+    tc::stage_columns(ctx, p.norms, p.labels, col0, p.B);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int64_t c = col0 + j;
-      if (c < p.B && c != row) {
-        const float d2 = fmaxf(r.na + __ldg(&p.norms[c]) - 2.f * dot[j], 1e-7f);  // models.py:225 clamp
-        if (__ldg(&p.labels[c]) == r.la) {
-          r.tile_sum += d2;
-        } else {
-          const float m = fmaxf(1.f - sqrtf(d2), 0.f);
-          r.tile_sum += m * m;
-        }
-      }
+      const float d2 = fmaxf(r.na + ctx.wf[j] - 2.f * dot[j], 1e-7f);  // models.py:225 clamp
+      const float m = fmaxf(1.f - sqrtf(d2), 0.f);
+      const float term = (ctx.wi[j] == r.la) ? d2 : m * m;
+      r.tile_sum += (c < p.B && c != row) ? term : 0.f;
     }
   }
   static __device__ void tile_end(const Params&, Row& r, const tc::Ctx&, int64_t, bool, int) {
     r.sum += static_cast<double>(r.tile_sum);
     r.tile_sum = 0.f;
   }
-  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
-    if (valid) p.partial[row * p.n_splits + split] = PairPartial{r.sum, 0ull};
+  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int,
+                                  int split) {
+    if (valid) p.partial[(row * p.n_splits + split) * tc::EPI_H + ctx.half] = PairPartial{r.sum, 0ull};
   }
 };
 
@@ -709,7 +746,7 @@ extern "C" {
 size_t en_ws_bytes_batch_hard(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles_n = static_cast<size_t>((B + tc::BN - 1) / tc::BN);
-  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * sizeof(BhCand)) +
+  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * tc::EPI_H * sizeof(BhCand)) +
          align_up(static_cast<size_t>((B + 7) / 8) * sizeof(double)) + align_up(sizeof(unsigned));
 }
 
@@ -727,7 +764,7 @@ int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d,
   TcOperands o;
   if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
   const int tiles_n = static_cast<int>((B + tc::BN - 1) / tc::BN);
-  BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n);
+  BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * tc::EPI_H);
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
   double* partial = w.take<double>(blocks);
   unsigned* counter = w.take<unsigned>(1);
@@ -739,7 +776,7 @@ int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d,
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
   prof_end(st);
   ++launch_counter();
-  batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft,
+  batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n * tc::EPI_H, margin, squared, soft,
                                                      hp_idx, hn_idx, hp, hn, coef, partial, counter, loss);
   EN_LAUNCHED("batch_hard_finalize_kernel");
   return EN_OK;
@@ -768,7 +805,7 @@ static size_t pos_bytes(int64_t B, int cap) {
 size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
   if (B <= 0 || d <= 0 || max_positives <= 0 || max_positives > kMaxPos) return 0;
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
-  return operand_bytes(B, d) + pos_bytes(B, max_positives) + align_up(static_cast<size_t>(B) * tiles * sizeof(PairPartial));
+  return operand_bytes(B, d) + pos_bytes(B, max_positives) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
 }
 
 struct PosLists {
@@ -805,7 +842,7 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   PosLists pl = take_pos(w, B, max_positives);
   const int sms = device_sm_count();
   tc::Shape sh = tc::make_shape(B, B, d, splits_for(B, sms), 3);
-  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits);
+  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits * tc::EPI_H);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
   collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
@@ -816,7 +853,7 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   EN_CUDA(tc::launch<EpBatchAll>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
   ++launch_counter();
-  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits, pl.pos_n, B, 0, out, stats);
+  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits * tc::EPI_H, pl.pos_n, B, 0, out, stats);
   EN_LAUNCHED("pair_reduce_kernel");
   // a class larger than max_positives + 1 would silently drop triplets: surface it (one 4-byte read-back)
   int32_t status_h = 0;
@@ -867,7 +904,7 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
 size_t en_ws_bytes_contrastive_allpairs(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
-  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles * sizeof(PairPartial));
+  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
 }
 
 int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float* loss, void* ws,
@@ -882,14 +919,14 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
   if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
   const int sms = device_sm_count();
   tc::Shape sh = tc::make_shape(B, B, d, splits_for(B, sms), 3);
-  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits);
+  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits * tc::EPI_H);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_fwd: workspace too small or misaligned");
   EpContrastive::Params ep{labels, o.norms, partial, B, sh.n_splits};
   prof_begin(st);
   EN_CUDA(tc::launch<EpContrastive>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
   ++launch_counter();
-  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits, nullptr, B, 1, loss, nullptr);
+  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits * tc::EPI_H, nullptr, B, 1, loss, nullptr);
   EN_LAUNCHED("pair_reduce_kernel");
   return EN_OK;
 }

@@ -65,40 +65,63 @@ struct EpTopK {
     r.exclude = p.query_labels != nullptr && p.bank_labels != nullptr;
     r.qlabel = (r.exclude && valid) ? p.query_labels[row] : 0;
   }
-  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int64_t col0,
+  static __device__ void chunk(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int64_t col0,
                                const float (&dot)[32]) {
     if (col0 >= p.n_bank) return;
+    tc::stage_columns(ctx, p.bank_norms, nullptr, col0, p.n_bank);
+    const int ncols = static_cast<int>(p.n_bank - col0 < 32 ? p.n_bank - col0 : 32);
+    const float4* n4 = reinterpret_cast<const float4*>(ctx.wf);
+    // fast reject: most chunks contain nothing below the current k-th best once the list has warmed up
+    float tmin = kInf;
+    float t[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 nb = n4[g];
+      t[4 * g + 0] = fmaf(-2.f, dot[4 * g + 0], nb.x);
+      t[4 * g + 1] = fmaf(-2.f, dot[4 * g + 1], nb.y);
+      t[4 * g + 2] = fmaf(-2.f, dot[4 * g + 2], nb.z);
+      t[4 * g + 3] = fmaf(-2.f, dot[4 * g + 3], nb.w);
+    }
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tmin = fminf(tmin, t[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tmin = fminf(tmin, j < ncols ? t[j] : kInf);
+    }
+    if (!__any_sync(0xffffffffu, tmin < r.v[KC - 1])) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int64_t c = col0 + j;
-      if (c < p.n_bank) {
-        const float t = fmaf(-2.f, dot[j], __ldg(&p.bank_norms[c]));
-        if (t < r.v[KC - 1]) {
-          if (!r.exclude || __ldg(&p.bank_labels[c]) != r.qlabel) list_insert<KC>(r.v, r.id, t, static_cast<int32_t>(c));
-        }
+      if (j < ncols && t[j] < r.v[KC - 1]) {
+        const int64_t c = col0 + j;
+        if (!r.exclude || __ldg(&p.bank_labels[c]) != r.qlabel) list_insert<KC>(r.v, r.id, t[j], static_cast<int32_t>(c));
       }
     }
   }
   static __device__ void tile_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int) {}
-  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
+  static __device__ void item_end(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int,
+                                  int split) {
     if (!valid) return;
-    Cand* out = p.lists + (row * p.n_lists + split) * KC;
+    Cand* out = p.lists + (row * p.n_lists + split * tc::EPI_H + ctx.half) * KC;
 #pragma unroll
     for (int q = 0; q < KC; ++q) out[q] = Cand{r.v[q], r.id[q]};
   }
 };
 
 // ---------------------------------------------------------------- stage 1b: HBM-bound streaming scan
-// One warp per bank row at a time; the (<= 8) queries live in shared memory; lane q keeps query q's running list.
-template <int KC>
+// The reference's call pattern is one query per predict() (models.py:122,135): the scan is then bounded by HBM
+// bandwidth, not by math.  One warp streams two bank rows at a time (all 128-bit loads of both rows are issued
+// before any arithmetic, evict-first), the (<= 8, zero padded to QT) queries sit in shared memory, lane q keeps
+// query q's running list, and the eight warps of a block merge their lists in shared memory before writing out.
+template <int KC, int DV, int QT>  // DV = float4 per lane per row (d == 128 * DV), 0 = any d; QT = padded queries
 __global__ void __launch_bounds__(256)
 knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank, int64_t n_bank,
-                  int64_t rows_per_warp, Cand* __restrict__ lists, int n_lists) {
-  extern __shared__ float qs[];  // [Q][d]
-  for (int i = threadIdx.x; i < Q * d; i += blockDim.x) qs[i] = queries[i];
+                  int64_t rows_per_warp, Cand* __restrict__ lists) {
+  extern __shared__ float qs[];  // [QT][d], then the block's merge area
+  for (int i = threadIdx.x; i < QT * d; i += blockDim.x) qs[i] = i < Q * d ? queries[i] : 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
   const int64_t r0 = gwarp * rows_per_warp;
   const int64_t r1 = min(r0 + rows_per_warp, n_bank);
   float v[KC];
@@ -108,76 +131,113 @@ knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* 
     v[q] = kInf;
     id[q] = -1;
   }
-  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(bank) & 15) == 0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const float* b = bank + r * d;
-    float s[EN_KNN_STREAM_MAX_Q];
+  for (int64_t r = r0; r < r1; r += 2) {
+    const bool two = r + 1 < r1;
+    float s0[QT], s1[QT];
 #pragma unroll
-    for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) s[q] = 0.f;
-    if (vec) {
-      for (int c = lane * 4; c < d; c += 128) {
-        const float4 bv = __ldcs(reinterpret_cast<const float4*>(b + c));  // streamed once: evict-first
+    for (int q = 0; q < QT; ++q) s0[q] = s1[q] = 0.f;
+    if (DV > 0) {
+      const float4* b0 = reinterpret_cast<const float4*>(bank + r * d) + lane;
+      const float4* b1 = reinterpret_cast<const float4*>(bank + (two ? r + 1 : r) * d) + lane;
+      float4 x0[DV > 0 ? DV : 1], x1[DV > 0 ? DV : 1];
 #pragma unroll
-        for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
-          if (q < Q) {
-            const float4 qv = *reinterpret_cast<const float4*>(qs + q * d + c);
-            float t;
-            t = qv.x - bv.x; s[q] = fmaf(t, t, s[q]);
-            t = qv.y - bv.y; s[q] = fmaf(t, t, s[q]);
-            t = qv.z - bv.z; s[q] = fmaf(t, t, s[q]);
-            t = qv.w - bv.w; s[q] = fmaf(t, t, s[q]);
-          }
+      for (int i = 0; i < DV; ++i) x0[i] = __ldcs(b0 + 32 * i);  // streamed once: evict-first
+#pragma unroll
+      for (int i = 0; i < DV; ++i) x1[i] = __ldcs(b1 + 32 * i);
+#pragma unroll
+      for (int i = 0; i < DV; ++i) {
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+          const float4 qv = *reinterpret_cast<const float4*>(qs + q * d + 4 * (lane + 32 * i));
+          float t;
+          t = qv.x - x0[i].x; s0[q] = fmaf(t, t, s0[q]);
+          t = qv.y - x0[i].y; s0[q] = fmaf(t, t, s0[q]);
+          t = qv.z - x0[i].z; s0[q] = fmaf(t, t, s0[q]);
+          t = qv.w - x0[i].w; s0[q] = fmaf(t, t, s0[q]);
+          t = qv.x - x1[i].x; s1[q] = fmaf(t, t, s1[q]);
+          t = qv.y - x1[i].y; s1[q] = fmaf(t, t, s1[q]);
+          t = qv.z - x1[i].z; s1[q] = fmaf(t, t, s1[q]);
+          t = qv.w - x1[i].w; s1[q] = fmaf(t, t, s1[q]);
         }
       }
     } else {
+      const float* b0 = bank + r * d;
+      const float* b1 = bank + (two ? r + 1 : r) * d;
       for (int c = lane; c < d; c += 32) {
-        const float bv = b[c];
+        const float y0 = b0[c], y1 = b1[c];
 #pragma unroll
-        for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
-          if (q < Q) {
-            const float t = qs[q * d + c] - bv;
-            s[q] = fmaf(t, t, s[q]);
-          }
+        for (int q = 0; q < QT; ++q) {
+          const float qv = qs[q * d + c];
+          float t = qv - y0;
+          s0[q] = fmaf(t, t, s0[q]);
+          t = qv - y1;
+          s1[q] = fmaf(t, t, s1[q]);
         }
       }
     }
-    float mine = kInf;
+    float m0 = kInf, m1 = kInf;
 #pragma unroll
-    for (int q = 0; q < EN_KNN_STREAM_MAX_Q; ++q) {
-      if (q < Q) {
-        const float tot = warp_sum(s[q]);
-        if (lane == q) mine = tot;
+    for (int q = 0; q < QT; ++q) {
+      const float t0 = warp_sum(s0[q]), t1 = warp_sum(s1[q]);
+      if (lane == q) {
+        m0 = t0;
+        m1 = t1;
       }
     }
-    if (lane < Q && mine < v[KC - 1]) list_insert<KC>(v, id, mine, static_cast<int32_t>(r));
+    if (lane < Q) {
+      if (m0 < v[KC - 1]) list_insert<KC>(v, id, m0, static_cast<int32_t>(r));
+      if (two && m1 < v[KC - 1]) list_insert<KC>(v, id, m1, static_cast<int32_t>(r + 1));
+    }
   }
-  if (lane < Q && gwarp < n_lists) {
-    Cand* out = lists + (static_cast<int64_t>(lane) * n_lists + gwarp) * KC;
+  // block-level merge: warps cover ascending row ranges, so appending warp after warp keeps ties in id order
+  __syncthreads();
+  Cand* merge = reinterpret_cast<Cand*>(qs);  // [8 warps][QT][KC]
+  if (lane < QT) {
+#pragma unroll
+    for (int q = 0; q < KC; ++q) merge[(warp * QT + lane) * KC + q] = Cand{v[q], id[q]};
+  }
+  __syncthreads();
+  if (threadIdx.x < Q) {
+    const int qq = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < KC; ++q) {
+      v[q] = kInf;
+      id[q] = -1;
+    }
+    for (int w = 0; w < 8; ++w) {
+      for (int q = 0; q < KC; ++q) {
+        const Cand c = merge[(w * QT + qq) * KC + q];
+        if (c.idx >= 0 && c.t < v[KC - 1]) list_insert<KC>(v, id, c.t, c.idx);
+      }
+    }
+    Cand* out = lists + (static_cast<int64_t>(qq) * gridDim.x + blockIdx.x) * KC;
 #pragma unroll
     for (int q = 0; q < KC; ++q) out[q] = Cand{v[q], id[q]};
   }
 }
 
 // ---------------------------------------------------------------- stage 2: exact re-rank
-// One warp per query.  Extract the KC best proxies over all lists in (t, idx) order, re-evaluate them exactly,
-// order by (d2, global id), emit the first k.
+// One block per query (32 threads when the candidate lists are short, 256 when the streaming scan left thousands).
+// Extract the KC best proxies over all lists in (t, idx) order, re-evaluate them exactly in float64, order by
+// (d2, global id), emit the first k.
 template <int KC>
 __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, int d,
                                   const float* __restrict__ bank, int64_t id_offset, const Cand* __restrict__ lists,
                                   int n_lists, int k, double* __restrict__ d2_out, int64_t* __restrict__ ids_out) {
-  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (q >= Q) return;
+  __shared__ float s_t[8];
+  __shared__ int32_t s_i[8];
+  const int64_t q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const Cand* mine = lists + q * n_lists * KC;
   const int total = n_lists * KC;
   float last_t = -kInf;
   int32_t last_i = -1;
-  double my_d2 = 1e300;   // lane r holds the r-th extracted candidate
+  double my_d2 = 1e300;   // warp 0: lane r holds the r-th extracted candidate
   int32_t my_idx = -1;
   for (int r = 0; r < KC; ++r) {
     float bt = kInf;
     int32_t bi = 0x7fffffff;
-    for (int c = lane; c < total; c += 32) {
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
       const Cand x = mine[c];
       if (x.idx < 0) continue;
       const bool after = x.t > last_t || (x.t == last_t && x.idx > last_i);
@@ -195,22 +255,41 @@ __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, 
         bi = oi;
       }
     }
-    if (bi == 0x7fffffff) break;  // lists exhausted (warp-uniform)
+    if (nwarps > 1) {
+      __syncthreads();
+      if (lane == 0) {
+        s_t[warp] = bt;
+        s_i[warp] = bi;
+      }
+      __syncthreads();
+      bt = s_t[0];
+      bi = s_i[0];
+      for (int w = 1; w < nwarps; ++w) {
+        if (s_t[w] < bt || (s_t[w] == bt && s_i[w] < bi)) {
+          bt = s_t[w];
+          bi = s_i[w];
+        }
+      }
+    }
+    if (bi == 0x7fffffff) break;  // lists exhausted (block-uniform)
     last_t = bt;
     last_i = bi;
-    const float* a = queries + q * d;
-    const float* b = bank + static_cast<int64_t>(bi) * d;
-    double acc = 0.0;
-    for (int c = lane; c < d; c += 32) {
-      const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
-      acc += t * t;
-    }
-    acc = warp_sum(acc);
-    if (lane == r) {
-      my_d2 = acc;
-      my_idx = bi;
+    if (warp == 0) {
+      const float* a = queries + q * d;
+      const float* b = bank + static_cast<int64_t>(bi) * d;
+      double acc = 0.0;
+      for (int c = lane; c < d; c += 32) {
+        const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
+        acc += t * t;
+      }
+      acc = warp_sum(acc);
+      if (lane == r) {
+        my_d2 = acc;
+        my_idx = bi;
+      }
     }
   }
+  if (warp != 0) return;
   // rank by (d2, idx) among the KC (<= 32) extracted; lanes >= KC hold sentinels
   int rank = 0;
 #pragma unroll
@@ -335,7 +414,7 @@ template <int KC>
 int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh, const CUtensorMap& bl,
              const tc::Shape& sh, const float* bank_norms, const int32_t* bank_labels, const int32_t* query_labels,
              Cand* lists, int64_t n_bank, int sms, cudaStream_t st) {
-  typename EpTopK<KC>::Params ep{bank_norms, bank_labels, query_labels, lists, n_bank, sh.n_splits};
+  typename EpTopK<KC>::Params ep{bank_norms, bank_labels, query_labels, lists, n_bank, sh.n_splits * tc::EPI_H};
   prof_begin(st);
   EN_CUDA(tc::launch<EpTopK<KC>>(qh, ql, bh, bl, sh, ep, sms, st));
   prof_end(st);
@@ -346,21 +425,59 @@ int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh
 template <int KC>
 int run_rerank(const float* queries, int64_t Q, int d, const float* bank, int64_t id_offset, const Cand* lists,
                int n_lists, int k, double* d2, int64_t* ids, cudaStream_t st) {
-  knn_rerank_kernel<KC><<<static_cast<unsigned>((Q * 32 + 255) / 256), 256, 0, st>>>(queries, Q, d, bank, id_offset,
-                                                                                    lists, n_lists, k, d2, ids);
+  const int threads = n_lists * KC > 1024 ? 256 : 32;
+  knn_rerank_kernel<KC><<<static_cast<unsigned>(Q), threads, 0, st>>>(queries, Q, d, bank, id_offset, lists, n_lists,
+                                                                       k, d2, ids);
   EN_LAUNCHED("knn_rerank_kernel");
   return EN_OK;
 }
 
 constexpr int STREAM_WARPS = 8;
 
-inline void stream_geometry(int64_t n_bank, int sms, int64_t* rows_per_warp, int* n_lists, int* blocks) {
+inline void stream_geometry(int64_t n_bank, int sms, int64_t* rows_per_warp, int* blocks) {
   int64_t warps = static_cast<int64_t>(sms) * 4 * STREAM_WARPS;  // 4 resident CTAs per SM
-  if (warps > n_bank) warps = n_bank > 0 ? n_bank : 1;
-  *rows_per_warp = (n_bank + warps - 1) / warps;
-  const int64_t used = (n_bank + *rows_per_warp - 1) / *rows_per_warp;
+  if (warps * 2 > n_bank) warps = n_bank > 1 ? n_bank / 2 : 1;
+  int64_t rpw = (n_bank + warps - 1) / warps;
+  rpw = (rpw + 1) / 2 * 2;  // rows are streamed in pairs
+  *rows_per_warp = rpw;
+  const int64_t used = (n_bank + rpw - 1) / rpw;
   *blocks = static_cast<int>((used + STREAM_WARPS - 1) / STREAM_WARPS);
-  *n_lists = *blocks * STREAM_WARPS;
+}
+
+template <int KC, int DV, int QT>
+int launch_stream(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw, int blocks,
+                  Cand* lists, cudaStream_t st) {
+  size_t smem = static_cast<size_t>(QT) * d * 4;
+  const size_t merge = static_cast<size_t>(STREAM_WARPS) * QT * KC * sizeof(Cand);
+  if (merge > smem) smem = merge;
+  if (smem > 48 * 1024)
+    EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KC, DV, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  prof_begin(st);
+  knn_stream_kernel<KC, DV, QT><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank,
+                                                                          rpw, lists);
+  prof_end(st);
+  EN_LAUNCHED("knn_stream_kernel");
+  return EN_OK;
+}
+
+template <int KC, int DV>
+int launch_stream_q(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw,
+                    int blocks, Cand* lists, cudaStream_t st) {
+  if (Q == 1) return launch_stream<KC, DV, 1>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (Q == 2) return launch_stream<KC, DV, 2>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (Q <= 4) return launch_stream<KC, DV, 4>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  return launch_stream<KC, DV, 8>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+}
+
+template <int KC>
+int launch_stream_d(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw,
+                    int blocks, Cand* lists, cudaStream_t st) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(bank) & 15) == 0;
+  if (aligned && d == 128) return launch_stream_q<KC, 1>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (aligned && d == 256) return launch_stream_q<KC, 2>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (aligned && d == 512) return launch_stream_q<KC, 4>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  return launch_stream_q<KC, 0>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
 }
 
 }  // namespace
@@ -390,7 +507,7 @@ size_t en_ws_bytes_knn(int64_t Q, int64_t n_bank, int d, int k) {
   if (s > tiles_n) s = tiles_n;
   if (s < 1) s = 1;
   return 2 * align_up(static_cast<size_t>(Q) * dpad * 4) + align_up(static_cast<size_t>(Q) * 4) +
-         align_up(static_cast<size_t>(Q) * s * kc_for(k) * sizeof(Cand));
+         align_up(static_cast<size_t>(Q) * s * tc::EPI_H * kc_for(k) * sizeof(Cand));
 }
 
 int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_hi,
@@ -416,7 +533,7 @@ int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank,
   float* qlo = w.take<float>(static_cast<size_t>(Q) * dpad);
   float* qn = w.take<float>(Q);
   tc::Shape sh = tc::make_shape(Q, n_bank, d, knn_splits(Q, n_bank, sms), 3);
-  Cand* lists = w.take<Cand>(static_cast<size_t>(Q) * sh.n_splits * KC);
+  Cand* lists = w.take<Cand>(static_cast<size_t>(Q) * sh.n_splits * tc::EPI_H * KC);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_knn_shard_topk: workspace too small or misaligned");
   EN_CUDA(tc::launch_split(queries, Q, d, d, dpad, qhi, qlo, qn, st));
   ++launch_counter();
@@ -430,17 +547,18 @@ int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank,
   else if (KC == 16) rc = run_scan<16>(tqh, tql, tbh, tbl, sh, bank_norms, bank_labels, ql, lists, n_bank, sms, st);
   else rc = run_scan<32>(tqh, tql, tbh, tbl, sh, bank_norms, bank_labels, ql, lists, n_bank, sms, st);
   if (rc) return rc;
-  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
-  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
-  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, sh.n_splits, k, d2, ids, st);
+  const int nl = sh.n_splits * tc::EPI_H;
+  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
+  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
+  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
 }
 
 size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k) {
   if (Q <= 0 || Q > EN_KNN_STREAM_MAX_Q || n_bank <= 0 || d <= 0 || k <= 0 || k > EN_KNN_MAX_K) return 0;
   int64_t rpw;
-  int n_lists, blocks;
-  stream_geometry(n_bank, 160, &rpw, &n_lists, &blocks);
-  return align_up(static_cast<size_t>(Q) * n_lists * kc_for(k) * sizeof(Cand));
+  int blocks;
+  stream_geometry(n_bank, 160, &rpw, &blocks);  // sized for the largest SM count
+  return align_up(static_cast<size_t>(Q) * (blocks + 8) * kc_for(k) * sizeof(Cand));
 }
 
 int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
@@ -450,34 +568,25 @@ int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank
              EN_KNN_STREAM_MAX_Q, (long long)Q);
   EN_REQUIRE(k > 0 && k <= EN_KNN_MAX_K, "en_knn_stream_topk: k must be in [1, %d]", EN_KNN_MAX_K);
   EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_stream_topk: shard too large");
-  EN_REQUIRE(static_cast<size_t>(Q) * d * 4 <= 160 * 1024, "en_knn_stream_topk: Q*d too large for shared memory");
+  EN_REQUIRE(static_cast<size_t>(8) * d * 4 <= 160 * 1024, "en_knn_stream_topk: d too large for shared memory");
   if (!ws || ws_bytes < en_ws_bytes_knn_stream(Q, n_bank, d, k))
     return fail(EN_ERR_WORKSPACE, "en_knn_stream_topk: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(EN_ERR_WORKSPACE, "workspace misaligned");
   cudaStream_t st = as_stream(stream);
   const int sms = device_sm_count();
   int64_t rpw;
-  int n_lists, blocks;
-  stream_geometry(n_bank, sms, &rpw, &n_lists, &blocks);
+  int blocks;
+  stream_geometry(n_bank, sms, &rpw, &blocks);
   const int KC = kc_for(k);
   Cand* lists = static_cast<Cand*>(ws);
-  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(EN_ERR_WORKSPACE, "workspace misaligned");
-  const size_t smem = static_cast<size_t>(Q) * d * 4;
-#define EN_STREAM(KCV)                                                                                          \
-  do {                                                                                                          \
-    if (smem > 48 * 1024)                                                                                       \
-      EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                   static_cast<int>(smem)));                                                    \
-    prof_begin(st);                                                                                             \
-    knn_stream_kernel<KCV><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank, \
-                                                                     rpw, lists, n_lists);                      \
-    prof_end(st);                                                                                               \
-    EN_LAUNCHED("knn_stream_kernel");                                                                           \
-    return run_rerank<KCV>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, st);                     \
-  } while (0)
-  if (KC == 8) EN_STREAM(8);
-  if (KC == 16) EN_STREAM(16);
-  EN_STREAM(32);
-#undef EN_STREAM
+  int rc;
+  if (KC == 8) rc = launch_stream_d<8>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  else if (KC == 16) rc = launch_stream_d<16>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  else rc = launch_stream_d<32>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (rc) return rc;
+  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
+  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
+  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
 }
 
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,

@@ -109,7 +109,7 @@ struct EpStoreDist {
     for (int j = 0; j < 32; ++j) {
       const int64_t c = col0 + j;
       if (c < p.n) {
-        float f = fmaxf(r.na + __ldg(&p.norms[c]) - 2.f * dot[j], 0.f);
+        float f = fmaxf(r.na + __ldg(&p.norms[c]) - 2.f * dot[j], 0.f);  // diagnostics path: plain loads
         if (c == row) f = 0.f;
         p.out[row * p.n + c] = p.squared ? f : sqrtf(f);
       }

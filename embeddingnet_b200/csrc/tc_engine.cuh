@@ -7,8 +7,12 @@
 //   sklearn.metrics.pairwise_distances      (embedding_net/datagenerators.py:219)
 //   sklearn.neighbors.KNeighborsClassifier  (embedding_net/models.py:136-138)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-// (each owns one 32-lane TMEM quarter).  Three mbarrier pipelines: smem full/empty, TMEM full/empty.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
+// A warp can only read the TMEM lane quarter (warp_id % 4), so each quarter (32 tile rows) is served by EPI_H = 2
+// warps that split the 128 accumulator columns between them: two epilogue warps per SM sub-partition, which is what
+// hides the ALU / shared-memory latency of the per-element epilogue math (ncu, round 1: with one warp per
+// sub-partition the epilogue ran at IPC 0.2 and took twice as long as the MMAs it was supposed to hide behind).
+// Three mbarrier pipelines: smem full/empty, TMEM full/empty.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -29,8 +33,13 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // Ahi, Alo, Bhi, Blo
 // from 3*d/8 to d/8 links for the large term (measured on B200: 6e-6 -> ~2e-6 relative on all-positive sums).
 constexpr int ACC_COLS = 2 * BN;                   // main | cross
 constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 512 = all of TMEM (1 CTA/SM anyway, by smem)
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BASE_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_H = 2;                           // epilogue warps per TMEM lane quarter (column halves)
+constexpr int EPI_WARPS = 4 * EPI_H;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // 320
+constexpr int COLS_PER_EPI_WARP = BN / EPI_H;      // 64
+constexpr int WARP_SCRATCH_BYTES = 256;            // per-epilogue-warp column cache: 32 floats + 32 ints
+constexpr int SMEM_BASE_BYTES =
+    STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * WARP_SCRATCH_BYTES;
 constexpr int SMEM_EP_MAX = 232448 - SMEM_BASE_BYTES;  // what is left of the 227 KB for an epilogue's scratch
 static_assert(BN == BM, "A and B tiles share TILE_BYTES");
 
@@ -53,7 +62,8 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-// Epilogue concept (one thread owns one row of the 128-row tile for the whole work item):
+// Epilogue concept (EPI_H threads share one row of the 128-row tile, each owning BN / EPI_H of its columns, for
+// the whole work item; results are published per (row, ..., ctx.half)):
 //   struct Ep { struct Params; struct Row; static constexpr int kSmemBytes;   // scratch, <= SMEM_EP_MAX
 //     static __device__ void item_begin(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int tile_m, int split);
 //     static __device__ void chunk(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int64_t col0, const float (&dot)[32]);
@@ -61,9 +71,24 @@ struct Barriers {
 //     static __device__ void item_end(const Params&, Row&, const Ctx&, int64_t row, bool row_valid, int tile_m, int split); };
 // `chunk` receives dot[j] = <A[row], B[col0 + j]> for 32 consecutive candidate rows (columns past N hold 0).
 struct Ctx {
-  uint8_t* smem;  // Ep::kSmemBytes of shared scratch (16-byte aligned), shared by the 128 epilogue threads
-  int erow;       // this thread's row inside the tile, 0..127
+  uint8_t* smem;   // Ep::kSmemBytes of shared scratch (16-byte aligned), shared by all epilogue threads
+  float* wf;       // per-warp scratch: 32 floats (column norms of the current 32-column chunk)
+  int32_t* wi;     // per-warp scratch: 32 ints   (column labels of the current chunk)
+  int erow;        // this thread's row inside the tile, 0..127
+  int half;        // which column share of the row this thread owns, 0..EPI_H-1
+  int lane;
 };
+
+// Stage the per-column side data of a 32-column chunk once per warp (one coalesced load) instead of one broadcast
+// global load per element per thread; read back with 128-bit shared loads (4 columns per instruction).
+__device__ __forceinline__ void stage_columns(const Ctx& ctx, const float* __restrict__ norms,
+                                              const int32_t* __restrict__ labels, int64_t col0, int64_t n_cols) {
+  const int64_t c = col0 + ctx.lane;
+  __syncwarp();
+  ctx.wf[ctx.lane] = (norms != nullptr && c < n_cols) ? __ldg(&norms[c]) : 0.f;
+  if (labels != nullptr) ctx.wi[ctx.lane] = c < n_cols ? __ldg(&labels[c]) : 0;
+  __syncwarp();
+}
 
 template <class Ep>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -74,7 +99,8 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   // 128B swizzle atoms need 1024-byte aligned tile bases.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
-  uint8_t* ep_smem = smem + STAGES * STAGE_BYTES + 256;
+  uint8_t* warp_scratch = smem + STAGES * STAGE_BYTES + 256;
+  uint8_t* ep_smem = warp_scratch + EPI_WARPS * WARP_SCRATCH_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,7 +117,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       ptx::mbar_init(&bars->tmem_full[a], 1);
-      ptx::mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&bars->tmem_empty[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -177,9 +203,12 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM -> registers)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are reachable from this warp
+    const int half = (warp - 2) >> 2;
     uint32_t acc_it = 0;
     typename Ep::Row rs;
-    const Ctx ctx{ep_smem, quarter * 32 + lane};
+    uint8_t* ws = warp_scratch + (warp - 2) * WARP_SCRATCH_BYTES;
+    const Ctx ctx{ep_smem, reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + 128), quarter * 32 + lane,
+                  half, lane};
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile_m = item / shape.n_splits;
       const int split = item % shape.n_splits;
@@ -195,7 +224,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * (COLS_PER_EPI_WARP / 32); c < (half + 1) * (COLS_PER_EPI_WARP / 32); ++c) {
           float dot[32];
           ptx::tmem_ld_32x32(taddr + c * 32, dot);
           if (shape.passes > 1) {

@@ -1,0 +1,30 @@
+"""Small driver for ncu: a few batch-hard steps at C3 plus a reduced bank scan (kept short: ncu replays kernels)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from embeddingnet_b200 import synth, losses_and_accuracies as lac
+from embeddingnet_b200.fused import BatchHardStep
+from embeddingnet_b200.models import BankKNNClassifier
+import numpy as np
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda", 0)
+if what in ("all", "triplet"):
+    raw, labels = synth.make_device(4096, 512, n_classes=512, rows_per_class=8, noise=0.5, relu=True, device=dev)
+    emb = lac.l2_normalize(raw).detach()
+    st = BatchHardStep(4096, 512, 0.5)
+    for _ in range(4):
+        st.step(emb, labels)
+    torch.cuda.synchronize()
+if what in ("all", "knn"):
+    n, Q = 400_000, 8192
+    bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
+    ids = (torch.arange(n, device=dev) % 100000).to(torch.int32)
+    clf = BankKNNClassifier(5, device=dev).fit_shard(bank, ids, 0, n, classes=np.arange(100000))
+    q, _ = synth.make_device(Q, 512, seed_noise=synth.SEED_QUERY, n_classes=100000, noise=0.5, device=dev)
+    for _ in range(2):
+        clf.kneighbors_device(q)
+    for _ in range(2):
+        clf.kneighbors_device(q[:8].contiguous())
+        clf.kneighbors_device(q[:1].contiguous())
+    torch.cuda.synchronize()

@@ -57,7 +57,7 @@ struct EpRowMax {
   }
   static __device__ void tile_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int) {}
   static __device__ void item_end(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int split) {
-    if (valid) p.out[row * p.n_splits + split] = r.m;
+    if (valid) p.out[(row * p.n_splits + split) * tc::EPI_H + 0] = r.m;  // both halves write (timing only)
   }
 };
 
@@ -157,7 +157,7 @@ static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int
   tc::make_plane_tmap(&tah, ahi, M, dpad);
   tc::make_plane_tmap(&tal, alo, M, dpad);
   tc::Shape sh = tc::make_shape(M, N, d, n_splits, passes);
-  CK(cudaMalloc(&out, M * sh.n_splits * 4));
+  CK(cudaMalloc(&out, M * sh.n_splits * tc::EPI_H * 4));
   EpRowMax::Params ep{out, sh.n_splits};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
