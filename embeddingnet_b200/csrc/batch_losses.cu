@@ -57,27 +57,44 @@ __device__ __forceinline__ void top2_min(float& v1, int& i1, float& v2, int& i2,
   i1 = g1 ? c : i1;
 }
 
+// Symmetric schedule: only tiles (I, J) with J >= I are computed.  A strictly-upper tile serves both the anchors
+// of row tile I (row view: candidates among the columns) and the anchors of row tile J (column view: candidates
+// among the rows), so every dot product is computed once.  Record slots per (anchor, other tile T):
+//   T >= tile(anchor): slots 0,1 = the two column halves of the row view;
+//   T <  tile(anchor): slots 0..3 = the four 32-row quarters of the column view.
+constexpr int BH_SLOTS = 4;
+
 struct EpBatchHard {
   struct Params {
     const int32_t* labels;
     const float* norms;
-    BhCand* cand;  // [B][tiles_n][EPI_H]
+    BhCand* cand;  // [B][tiles_n][BH_SLOTS]
     int64_t B;
     int tiles_n;
   };
   struct Row {
     int32_t la;
+    float na;
+    int tile_m;
     BhCand c;
   };
-  static constexpr int kSmemBytes = 0;
-  static __device__ void reset(Row& r) {
-    r.c.p1 = r.c.p2 = -kBig;
-    r.c.n1 = r.c.n2 = kBig;
-    r.c.p1i = r.c.p2i = r.c.n1i = r.c.n2i = -1;
+  // per-warp 32x32 transposition scratch for the column view
+  static constexpr int kSmemBytes = tc::EPI_WARPS * 32 * 32 * 4;
+  static __device__ void reset(BhCand& c) {
+    c.p1 = c.p2 = -kBig;
+    c.n1 = c.n2 = kBig;
+    c.p1i = c.p2i = c.n1i = c.n2i = -1;
   }
-  static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int) {
+  static __device__ void store(BhCand* out, const BhCand& c) {
+    reinterpret_cast<float4*>(out)[0] = make_float4(c.p1, c.p2, c.n1, c.n2);
+    reinterpret_cast<int4*>(out)[1] = make_int4(c.p1i, c.p2i, c.n1i, c.n2i);
+  }
+  static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int tile_m,
+                                    int) {
     r.la = valid ? p.labels[row] : 0;
-    reset(r);
+    r.na = valid ? p.norms[row] : 0.f;
+    r.tile_m = tile_m;
+    reset(r.c);
   }
   static __device__ void chunk(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid, int64_t col0,
                                const float (&dot)[32]) {
@@ -86,9 +103,10 @@ struct EpBatchHard {
     const float4* n4 = reinterpret_cast<const float4*>(ctx.wf);
     const int4* l4 = reinterpret_cast<const int4*>(ctx.wi);
     const int c0 = static_cast<int>(col0);
-    // rows and columns are both tiled in aligned groups of 32, so the diagonal can only fall into the chunk whose
-    // first column equals this warp's first row
-    const bool edge = (col0 + 32 > p.B) || (col0 == row - ctx.lane);
+    const int64_t row0 = row - ctx.lane;  // first row served by this warp
+    // ---- row view.  Rows and columns are tiled in aligned groups of 32, so the diagonal can only fall into the
+    // chunk whose first column equals this warp's first row.
+    const bool edge = (col0 + 32 > p.B) || (col0 == row0);
     if (!edge) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -116,16 +134,37 @@ struct EpBatchHard {
         top2_min(r.c.n1, r.c.n1i, r.c.n2, r.c.n2i, (ok && !same) ? t : kBig, c0 + j);
       }
     }
+    // ---- column view (strictly-upper tiles only): transpose the 32x32 block through shared memory so that
+    // lane c owns column col0 + c and scans this warp's 32 rows.
+    const int tile_n = static_cast<int>(col0 / tc::BN);
+    if (tile_n > r.tile_m) {
+      float* sc = reinterpret_cast<float*>(ctx.smem) + (ctx.quarter + 4 * ctx.half) * 1024;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[ctx.lane * 32 + ((j + ctx.lane) & 31)] = fmaf(-2.f, dot[j], r.na);
+      __syncwarp();
+      const int32_t lc = ctx.wi[ctx.lane];
+      const bool col_ok = col0 + ctx.lane < p.B;
+      BhCand cc;
+      reset(cc);
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const float v = sc[i * 32 + ((ctx.lane + i) & 31)];
+        const int32_t li = __shfl_sync(0xffffffffu, r.la, i);
+        const bool ok = col_ok && (row0 + i < p.B);
+        const bool same = li == lc;
+        const int ri = static_cast<int>(row0) + i;
+        top2_max(cc.p1, cc.p1i, cc.p2, cc.p2i, (ok && same) ? v : -kBig, ri);
+        top2_min(cc.n1, cc.n1i, cc.n2, cc.n2i, (ok && !same) ? v : kBig, ri);
+      }
+      if (col_ok)
+        store(p.cand + ((col0 + ctx.lane) * p.tiles_n + r.tile_m) * BH_SLOTS + ctx.quarter, cc);
+    }
   }
   static __device__ void tile_end(const Params& p, Row& r, const tc::Ctx& ctx, int64_t row, bool valid,
                                   int tile_n) {
-    if (valid) {
-      // two 16-byte stores
-      BhCand* out = p.cand + (row * p.tiles_n + tile_n) * tc::EPI_H + ctx.half;
-      reinterpret_cast<float4*>(out)[0] = make_float4(r.c.p1, r.c.p2, r.c.n1, r.c.n2);
-      reinterpret_cast<int4*>(out)[1] = make_int4(r.c.p1i, r.c.p2i, r.c.n1i, r.c.n2i);
-    }
-    reset(r);
+    if (valid) store(p.cand + (row * p.tiles_n + tile_n) * BH_SLOTS + ctx.half, r.c);
+    reset(r.c);
   }
   static __device__ void item_end(const Params&, Row&, const tc::Ctx&, int64_t, bool, int, int) {}
 };
@@ -165,7 +204,7 @@ __device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict
 
 __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                            const float* __restrict__ norms, const BhCand* __restrict__ cand,
-                                           int64_t B, int d, int n_cand, float margin, int squared, int soft,
+                                           int64_t B, int d, int tiles_n, float margin, int squared, int soft,
                                            int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
                                            float* __restrict__ hp_out, float* __restrict__ hn_out,
                                            float* __restrict__ coef, double* __restrict__ partial,
@@ -175,11 +214,16 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   double hinge = 0.0;
   if (row < B) {
+    const int n_cand = tiles_n * BH_SLOTS;
+    const int my_tile = static_cast<int>(row / tc::BM);
     const BhCand* mine = cand + row * n_cand;
     const float na = norms[row];
+    // slots 2,3 exist only for tiles left of the anchor's own (column view); see EpBatchHard
+    auto slot_valid = [&](int t) { return t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile); };
     // pass 1: best proxies over all records
     float bp = -kBig, bn = kBig;
     for (int t = lane; t < n_cand; t += 32) {
+      if (!slot_valid(t)) continue;
       const float4 v = reinterpret_cast<const float4*>(mine + t)[0];
       bp = fmaxf(bp, v.x);  // p1 >= p2
       bn = fminf(bn, v.z);  // n1 <= n2
@@ -195,7 +239,7 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       const int t = t0 + lane;
       float4 v = make_float4(-kBig, -kBig, kBig, kBig);
       int4 ix = make_int4(-1, -1, -1, -1);
-      if (t < n_cand) {
+      if (slot_valid(t)) {
         v = reinterpret_cast<const float4*>(mine + t)[0];
         ix = reinterpret_cast<const int4*>(mine + t)[1];
       }
@@ -235,6 +279,7 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
     }
   }
   // deterministic mean: per-block partials, the last block to finish adds them in index order
+  __shared__ bool is_last;
   if (lane == 0) sh[warp] = hinge;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -242,12 +287,21 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
     for (int w = 0; w < 8; ++w) s += sh[w];
     partial[blockIdx.x] = s;
     __threadfence();
-    const unsigned done = atomicAdd(counter, 1u);
-    if (done == gridDim.x - 1) {
-      __threadfence();
-      double tot = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) tot += reinterpret_cast<volatile double*>(partial)[b];
-      loss[0] = static_cast<float>(tot / static_cast<double>(B));
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-shape tree over the block partials: the result does not depend on which block finishes last
+    double tot = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) tot += __ldcg(&partial[b]);
+    tot = warp_sum(tot);
+    if (lane == 0) sh[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += sh[w];
+      loss[0] = static_cast<float>(s / static_cast<double>(B));
       *counter = 0;  // re-armed for the next call on this workspace
     }
   }
@@ -746,7 +800,7 @@ extern "C" {
 size_t en_ws_bytes_batch_hard(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles_n = static_cast<size_t>((B + tc::BN - 1) / tc::BN);
-  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * tc::EPI_H * sizeof(BhCand)) +
+  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * BH_SLOTS * sizeof(BhCand)) +
          align_up(static_cast<size_t>((B + 7) / 8) * sizeof(double)) + align_up(sizeof(unsigned));
 }
 
@@ -764,19 +818,19 @@ int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d,
   TcOperands o;
   if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
   const int tiles_n = static_cast<int>((B + tc::BN - 1) / tc::BN);
-  BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * tc::EPI_H);
+  BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * BH_SLOTS);
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
   double* partial = w.take<double>(blocks);
   unsigned* counter = w.take<unsigned>(1);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_hard_fwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-  tc::Shape sh = tc::make_shape(B, B, d, tiles_n, 3);  // one column tile per item: candidates are per tile
+  tc::Shape sh = tc::make_shape_symmetric(B, d, 3);  // upper-triangular tiles, one per work item
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
   prof_begin(st);
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
   prof_end(st);
   ++launch_counter();
-  batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n * tc::EPI_H, margin, squared, soft,
+  batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft,
                                                      hp_idx, hn_idx, hp, hn, coef, partial, counter, loss);
   EN_LAUNCHED("batch_hard_finalize_kernel");
   return EN_OK;

@@ -38,8 +38,9 @@ constexpr int EPI_WARPS = 4 * EPI_H;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // 320
 constexpr int COLS_PER_EPI_WARP = BN / EPI_H;      // 64
 constexpr int WARP_SCRATCH_BYTES = 256;            // per-epilogue-warp column cache: 32 floats + 32 ints
-constexpr int SMEM_BASE_BYTES =
-    STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * WARP_SCRATCH_BYTES;
+// No alignment slack: the kernel has no static shared memory, so the dynamic window starts at the CTA's shared
+// base, which is 1024-byte aligned; the kernel traps if that ever stops being true.
+constexpr int SMEM_BASE_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + EPI_WARPS * WARP_SCRATCH_BYTES;
 constexpr int SMEM_EP_MAX = 232448 - SMEM_BASE_BYTES;  // what is left of the 227 KB for an epilogue's scratch
 static_assert(BN == BM, "A and B tiles share TILE_BYTES");
 
@@ -52,7 +53,37 @@ struct Shape {
   int n_splits;     // column-tile ranges per row tile (work item = (row tile, range))
   int tiles_per_split;
   int passes;       // 3 = hi*hi+hi*lo+lo*hi (fp32 faithful), 1 = hi*hi only (plain TF32; diagnostics)
+  int symmetric;    // A == B: only tiles with column tile >= row tile are computed (one tile per work item);
+                    // the epilogue must reduce each tile both along rows and along columns
+  int num_items;
 };
+
+// Work item -> (row tile, column-tile range).  Same arithmetic in all three warp roles.
+struct Item {
+  int tile_m, split, nt0, nt1;
+};
+__device__ __forceinline__ Item decode_item(const Shape& sh, int item) {
+  Item it;
+  if (sh.symmetric) {
+    // upper-triangular enumeration, row-major: row I holds tiles_n - I items
+    int I = 0, rem = item, len = sh.tiles_n;
+    while (rem >= len) {
+      rem -= len;
+      --len;
+      ++I;
+    }
+    it.tile_m = I;
+    it.split = I + rem;
+    it.nt0 = I + rem;
+    it.nt1 = it.nt0 + 1;
+  } else {
+    it.tile_m = item / sh.n_splits;
+    it.split = item % sh.n_splits;
+    it.nt0 = it.split * sh.tiles_per_split;
+    it.nt1 = min(it.nt0 + sh.tiles_per_split, sh.tiles_n);
+  }
+  return it;
+}
 
 struct Barriers {
   uint64_t full[STAGES];
@@ -77,6 +108,7 @@ struct Ctx {
   int erow;        // this thread's row inside the tile, 0..127
   int half;        // which column share of the row this thread owns, 0..EPI_H-1
   int lane;
+  int quarter;     // TMEM lane quarter = 32-row group of the tile this warp serves
 };
 
 // Stage the per-column side data of a 32-column chunk once per warp (one coalesced load) instead of one broadcast
@@ -95,16 +127,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const Shape shape, const typename Ep::Params ep) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tile bases.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
   uint8_t* warp_scratch = smem + STAGES * STAGE_BYTES + 256;
   uint8_t* ep_smem = warp_scratch + EPI_WARPS * WARP_SCRATCH_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_items = shape.tiles_m * shape.n_splits;
+  const int num_items = shape.num_items;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -134,11 +167,9 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile_m = item / shape.n_splits;
-        const int split = item % shape.n_splits;
-        const int nt0 = split * shape.tiles_per_split;
-        const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
-        for (int nt = nt0; nt < nt1; ++nt) {
+        const Item it = decode_item(shape, item);
+        const int tile_m = it.tile_m;
+        for (int nt = it.nt0; nt < it.nt1; ++nt) {
           for (int kb = 0; kb < shape.kblocks; ++kb) {
             ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * STAGE_BYTES;
@@ -163,10 +194,8 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       uint32_t phase = 0;
       uint32_t acc_it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item % shape.n_splits;
-        const int nt0 = split * shape.tiles_per_split;
-        const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
-        for (int nt = nt0; nt < nt1; ++nt, ++acc_it) {
+        const Item it = decode_item(shape, item);
+        for (int nt = it.nt0; nt < it.nt1; ++nt, ++acc_it) {
           const uint32_t acc = acc_it % NUM_ACC;
           const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
           ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
@@ -208,12 +237,10 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     typename Ep::Row rs;
     uint8_t* ws = warp_scratch + (warp - 2) * WARP_SCRATCH_BYTES;
     const Ctx ctx{ep_smem, reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + 128), quarter * 32 + lane,
-                  half, lane};
+                  half, lane, quarter};
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile_m = item / shape.n_splits;
-      const int split = item % shape.n_splits;
-      const int nt0 = split * shape.tiles_per_split;
-      const int nt1 = min(nt0 + shape.tiles_per_split, shape.tiles_n);
+      const Item it = decode_item(shape, item);
+      const int tile_m = it.tile_m, split = it.split, nt0 = it.nt0, nt1 = it.nt1;
       const int64_t row = static_cast<int64_t>(tile_m) * BM + quarter * 32 + lane;
       const bool row_valid = row < shape.M;
       Ep::item_begin(ep, rs, ctx, row, row_valid, tile_m, split);
@@ -299,6 +326,16 @@ inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes) {
   s.tiles_per_split = (s.tiles_n + n_splits - 1) / n_splits;
   s.n_splits = (s.tiles_n + s.tiles_per_split - 1) / s.tiles_per_split;
   s.passes = passes;
+  s.symmetric = 0;
+  s.num_items = s.tiles_m * s.n_splits;
+  return s;
+}
+
+// A == B (M == N): upper-triangular tile schedule, one tile per item.
+inline Shape make_shape_symmetric(int64_t N, int d, int passes) {
+  Shape s = make_shape(N, N, d, 1 << 30, passes);
+  s.symmetric = 1;
+  s.num_items = s.tiles_n * (s.tiles_n + 1) / 2;
   return s;
 }
 
@@ -312,7 +349,7 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   cudaError_t e =
       cudaFuncSetAttribute(dist_gemm_kernel<Ep>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const int items = shape.tiles_m * shape.n_splits;
+  const int items = shape.num_items;
   const int grid = items < num_sms ? items : num_sms;
   dist_gemm_kernel<Ep><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, shape, ep);
   return cudaGetLastError();
