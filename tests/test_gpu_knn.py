@@ -154,3 +154,22 @@ def test_embeddingnet_predict_api(tmp_path):
         _, ri = O.knn_exact(bank, q[i:i + 1], 5)
         assert top5 == [names[j] for j in ri[0]]
         assert pred.shape == (1,) and pred[0] == O.knn_vote(np.array(names)[ri])[0]
+
+
+def test_sharded_knn_over_nccl():
+    """The only partitioned path: bank rows sharded over >= 2 GPUs, NCCL all-gather + merge (skipped on 1 GPU)."""
+    import os
+    import subprocess
+    import sys
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_knn_worker.py")
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), worker],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "dist knn ok" in r.stdout
