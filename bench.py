@@ -219,6 +219,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        os.environ["NCCL_DEBUG"] = os.environ.get("EN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     lib = _lib.load()  # raises if the CUDA extension is missing

@@ -56,7 +56,7 @@ SIGNATURES = {
     "en_ws_bytes_knn": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "en_knn_shard_topk": (c_int, [P, c_int64, c_int, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_knn_stream": (c_size_t, [c_int64, c_int64, c_int, c_int]),
-    "en_knn_stream_topk": (c_int, [P, c_int64, c_int, P, c_int64, c_int64, c_int, P, P, P, c_size_t, P]),
+    "en_knn_stream_topk": (c_int, [P, c_int64, c_int, P, P, c_int64, c_int64, c_int, P, P, P, c_size_t, P]),
     "en_knn_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
     "en_knn_finalize_dist": (c_int, [P, c_int64, P, P]),
     "en_knn_vote": (c_int, [P, c_int64, c_int, P, c_int64, P, P]),

@@ -113,10 +113,13 @@ struct EpTopK {
 // bandwidth, not by math.  One warp streams two bank rows at a time (all 128-bit loads of both rows are issued
 // before any arithmetic, evict-first), the (<= 8, zero padded to QT) queries sit in shared memory, lane q keeps
 // query q's running list, and the eight warps of a block merge their lists in shared memory before writing out.
-template <int KC, int DV, int QT>  // DV = float4 per lane per row (d == 128 * DV), 0 = any d; QT = padded queries
+// With bank norms available (a fitted bank) the proxy is |b|^2 - 2 q.b: one FMA per (element, query) instead of a
+// subtract + FMA, which keeps the 8-query case on the HBM roofline instead of the FP32 pipe.
+template <int KC, int DV, int QT, bool NORM>  // DV = float4 per lane per row (d == 128*DV), 0 = any d; QT = padded Q
 __global__ void __launch_bounds__(256)
-knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank, int64_t n_bank,
-                  int64_t rows_per_warp, Cand* __restrict__ lists) {
+knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank,
+                  const float* __restrict__ bank_norms, int64_t n_bank, int64_t rows_per_warp,
+                  Cand* __restrict__ lists) {
   extern __shared__ float qs[];  // [QT][d], then the block's merge area
   for (int i = threadIdx.x; i < QT * d; i += blockDim.x) qs[i] = i < Q * d ? queries[i] : 0.f;
   __syncthreads();
@@ -149,15 +152,22 @@ knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* 
 #pragma unroll
         for (int q = 0; q < QT; ++q) {
           const float4 qv = *reinterpret_cast<const float4*>(qs + q * d + 4 * (lane + 32 * i));
-          float t;
-          t = qv.x - x0[i].x; s0[q] = fmaf(t, t, s0[q]);
-          t = qv.y - x0[i].y; s0[q] = fmaf(t, t, s0[q]);
-          t = qv.z - x0[i].z; s0[q] = fmaf(t, t, s0[q]);
-          t = qv.w - x0[i].w; s0[q] = fmaf(t, t, s0[q]);
-          t = qv.x - x1[i].x; s1[q] = fmaf(t, t, s1[q]);
-          t = qv.y - x1[i].y; s1[q] = fmaf(t, t, s1[q]);
-          t = qv.z - x1[i].z; s1[q] = fmaf(t, t, s1[q]);
-          t = qv.w - x1[i].w; s1[q] = fmaf(t, t, s1[q]);
+          if (NORM) {
+            s0[q] = fmaf(qv.x, x0[i].x, s0[q]); s0[q] = fmaf(qv.y, x0[i].y, s0[q]);
+            s0[q] = fmaf(qv.z, x0[i].z, s0[q]); s0[q] = fmaf(qv.w, x0[i].w, s0[q]);
+            s1[q] = fmaf(qv.x, x1[i].x, s1[q]); s1[q] = fmaf(qv.y, x1[i].y, s1[q]);
+            s1[q] = fmaf(qv.z, x1[i].z, s1[q]); s1[q] = fmaf(qv.w, x1[i].w, s1[q]);
+          } else {
+            float t;
+            t = qv.x - x0[i].x; s0[q] = fmaf(t, t, s0[q]);
+            t = qv.y - x0[i].y; s0[q] = fmaf(t, t, s0[q]);
+            t = qv.z - x0[i].z; s0[q] = fmaf(t, t, s0[q]);
+            t = qv.w - x0[i].w; s0[q] = fmaf(t, t, s0[q]);
+            t = qv.x - x1[i].x; s1[q] = fmaf(t, t, s1[q]);
+            t = qv.y - x1[i].y; s1[q] = fmaf(t, t, s1[q]);
+            t = qv.z - x1[i].z; s1[q] = fmaf(t, t, s1[q]);
+            t = qv.w - x1[i].w; s1[q] = fmaf(t, t, s1[q]);
+          }
         }
       }
     } else {
@@ -168,20 +178,30 @@ knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* 
 #pragma unroll
         for (int q = 0; q < QT; ++q) {
           const float qv = qs[q * d + c];
-          float t = qv - y0;
-          s0[q] = fmaf(t, t, s0[q]);
-          t = qv - y1;
-          s1[q] = fmaf(t, t, s1[q]);
+          if (NORM) {
+            s0[q] = fmaf(qv, y0, s0[q]);
+            s1[q] = fmaf(qv, y1, s1[q]);
+          } else {
+            float t = qv - y0;
+            s0[q] = fmaf(t, t, s0[q]);
+            t = qv - y1;
+            s1[q] = fmaf(t, t, s1[q]);
+          }
         }
       }
     }
     float m0 = kInf, m1 = kInf;
+    float nb0 = 0.f, nb1 = 0.f;
+    if (NORM) {
+      nb0 = __ldg(&bank_norms[r]);
+      nb1 = __ldg(&bank_norms[two ? r + 1 : r]);
+    }
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
       const float t0 = warp_sum(s0[q]), t1 = warp_sum(s1[q]);
       if (lane == q) {
-        m0 = t0;
-        m1 = t1;
+        m0 = NORM ? fmaf(-2.f, t0, nb0) : t0;
+        m1 = NORM ? fmaf(-2.f, t1, nb1) : t1;
       }
     }
     if (lane < Q) {
@@ -444,40 +464,47 @@ inline void stream_geometry(int64_t n_bank, int sms, int64_t* rows_per_warp, int
   *blocks = static_cast<int>((used + STREAM_WARPS - 1) / STREAM_WARPS);
 }
 
-template <int KC, int DV, int QT>
-int launch_stream(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw, int blocks,
-                  Cand* lists, cudaStream_t st) {
+template <int KC, int DV, int QT, bool NORM>
+int launch_stream(const float* queries, int64_t Q, int d, const float* bank, const float* norms, int64_t n_bank,
+                  int64_t rpw, int blocks, Cand* lists, cudaStream_t st) {
   size_t smem = static_cast<size_t>(QT) * d * 4;
   const size_t merge = static_cast<size_t>(STREAM_WARPS) * QT * KC * sizeof(Cand);
   if (merge > smem) smem = merge;
   if (smem > 48 * 1024)
-    EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KC, DV, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EN_CUDA(cudaFuncSetAttribute(knn_stream_kernel<KC, DV, QT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   prof_begin(st);
-  knn_stream_kernel<KC, DV, QT><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank,
-                                                                          rpw, lists);
+  knn_stream_kernel<KC, DV, QT, NORM><<<blocks, STREAM_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank,
+                                                                                norms, n_bank, rpw, lists);
   prof_end(st);
   EN_LAUNCHED("knn_stream_kernel");
   return EN_OK;
 }
 
-template <int KC, int DV>
-int launch_stream_q(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw,
-                    int blocks, Cand* lists, cudaStream_t st) {
-  if (Q == 1) return launch_stream<KC, DV, 1>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  if (Q == 2) return launch_stream<KC, DV, 2>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  if (Q <= 4) return launch_stream<KC, DV, 4>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  return launch_stream<KC, DV, 8>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+template <int KC, int DV, bool NORM>
+int launch_stream_q(const float* queries, int64_t Q, int d, const float* bank, const float* norms, int64_t n_bank,
+                    int64_t rpw, int blocks, Cand* lists, cudaStream_t st) {
+  if (Q == 1) return launch_stream<KC, DV, 1, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  if (Q == 2) return launch_stream<KC, DV, 2, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  if (Q <= 4) return launch_stream<KC, DV, 4, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  return launch_stream<KC, DV, 8, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+}
+
+template <int KC, bool NORM>
+int launch_stream_n(const float* queries, int64_t Q, int d, const float* bank, const float* norms, int64_t n_bank,
+                    int64_t rpw, int blocks, Cand* lists, cudaStream_t st) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(bank) & 15) == 0;
+  if (aligned && d == 128) return launch_stream_q<KC, 1, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  if (aligned && d == 256) return launch_stream_q<KC, 2, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  if (aligned && d == 512) return launch_stream_q<KC, 4, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  return launch_stream_q<KC, 0, NORM>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
 }
 
 template <int KC>
-int launch_stream_d(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t rpw,
-                    int blocks, Cand* lists, cudaStream_t st) {
-  const bool aligned = (reinterpret_cast<uintptr_t>(bank) & 15) == 0;
-  if (aligned && d == 128) return launch_stream_q<KC, 1>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  if (aligned && d == 256) return launch_stream_q<KC, 2>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  if (aligned && d == 512) return launch_stream_q<KC, 4>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  return launch_stream_q<KC, 0>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+int launch_stream_d(const float* queries, int64_t Q, int d, const float* bank, const float* norms, int64_t n_bank,
+                    int64_t rpw, int blocks, Cand* lists, cudaStream_t st) {
+  if (norms) return launch_stream_n<KC, true>(queries, Q, d, bank, norms, n_bank, rpw, blocks, lists, st);
+  return launch_stream_n<KC, false>(queries, Q, d, bank, nullptr, n_bank, rpw, blocks, lists, st);
 }
 
 }  // namespace
@@ -561,8 +588,9 @@ size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k) {
   return align_up(static_cast<size_t>(Q) * (blocks + 8) * kc_for(k) * sizeof(Cand));
 }
 
-int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
-                       int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes, void* stream) {
+int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_norms,
+                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes,
+                       void* stream) {
   EN_REQUIRE(queries && bank && d2 && ids && Q > 0 && n_bank > 0 && d > 0, "en_knn_stream_topk: bad arguments");
   EN_REQUIRE(Q <= EN_KNN_STREAM_MAX_Q, "en_knn_stream_topk: at most %d queries per call (got %lld)",
              EN_KNN_STREAM_MAX_Q, (long long)Q);
@@ -580,9 +608,9 @@ int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank
   const int KC = kc_for(k);
   Cand* lists = static_cast<Cand*>(ws);
   int rc;
-  if (KC == 8) rc = launch_stream_d<8>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  else if (KC == 16) rc = launch_stream_d<16>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
-  else rc = launch_stream_d<32>(queries, Q, d, bank, n_bank, rpw, blocks, lists, st);
+  if (KC == 8) rc = launch_stream_d<8>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
+  else if (KC == 16) rc = launch_stream_d<16>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
+  else rc = launch_stream_d<32>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
   if (rc) return rc;
   if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
   if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);

@@ -120,8 +120,8 @@ class BankKNNClassifier:
             if Q <= _lib.EN_KNN_STREAM_MAX_Q and ql is None:
                 # the reference's own call pattern: one image per predict() -> HBM-bound streaming scan
                 ws = workspace(lib.en_ws_bytes_knn_stream(Q, n, d, k), dev, "knn")
-                _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), n, self._offset, k, ptr(d2), ptr(ids),
-                          ptr(ws), ws.numel(), stream_ptr())
+                _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._norms), n, self._offset, k,
+                          ptr(d2), ptr(ids), ptr(ws), ws.numel(), stream_ptr())
             else:
                 ws = workspace(lib.en_ws_bytes_knn(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_shard_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._hi), ptr(self._lo),

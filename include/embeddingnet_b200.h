@@ -162,11 +162,14 @@ int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank,
                       const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids, void* ws,
                       size_t ws_bytes, void* stream);
 /* Small-batch variant for the reference's actual call pattern (one query per predict(), models.py:122,135):
- * a CUDA-core fp32 streaming scan bounded by HBM bandwidth; Q <= EN_KNN_STREAM_MAX_Q.  Same outputs. */
+ * a CUDA-core fp32 streaming scan bounded by HBM bandwidth; Q <= EN_KNN_STREAM_MAX_Q.  Same outputs.
+ * bank_norms (n_bank squared row norms from en_bank_prepare) may be NULL: the scan then evaluates
+ * sum (q-b)^2 directly instead of |b|^2 - 2 q.b (twice the FP32 work per element). */
 #define EN_KNN_STREAM_MAX_Q 8
 size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k);
-int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
-                       int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes, void* stream);
+int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_norms,
+                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes,
+                       void* stream);
 /* Merge P per-shard lists (P, Q, k) (as gathered by an NCCL all-gather) into the global top-k by (d2, id). */
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
                  int64_t* ids, void* stream);
