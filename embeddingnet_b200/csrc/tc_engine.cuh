@@ -304,12 +304,13 @@ inline PFN_encodeTiled get_encode_fn() {
 
 // Tensor map over a split plane: `rows` x `cols_padded` fp32, row-major, box = (BK cols, 128 rows), 128B swizzle.
 // Rows past `rows` are zero-filled by TMA, so ragged M/N need no host padding.
-inline int make_plane_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols_padded) {
+inline int make_plane_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols_padded,
+                           int box_rows = BM) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols_padded), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols_padded) * 4};
-  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -9,7 +9,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
-#include "tc_engine.cuh"
+#include "tc_engine_pair.cuh"
 
 #define CK(x)                                                                            \
   do {                                                                                   \
@@ -77,7 +77,7 @@ static uint64_t splitmix(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_sms) {
+static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_sms, bool pair = false) {
   int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
   std::vector<float> ha(M * d), hb(N * d);
   for (int64_t i = 0; i < M * d; ++i) ha[i] = (float)((double)(splitmix(i + 17) >> 40) / 8388608.0 - 1.0);
@@ -101,14 +101,16 @@ static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_
   CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
   CK(tc::launch_split(b, N, d, d, dpad, bhi, blo, nb, 0));
   CUtensorMap tah, tal, tbh, tbl;
+  const int bbox = pair ? tc::BN / 2 : tc::BN;
   if (tc::make_plane_tmap(&tah, ahi, M, dpad) || tc::make_plane_tmap(&tal, alo, M, dpad) ||
-      tc::make_plane_tmap(&tbh, bhi, N, dpad) || tc::make_plane_tmap(&tbl, blo, N, dpad)) {
+      tc::make_plane_tmap(&tbh, bhi, N, dpad, bbox) || tc::make_plane_tmap(&tbl, blo, N, dpad, bbox)) {
     printf("tensor map encode failed\n");
     return 1;
   }
   tc::Shape sh = tc::make_shape(M, N, d, 1 << 30, passes);
   EpStore::Params ep{out, N, N};
-  CK(tc::launch<EpStore>(tah, tal, tbh, tbl, sh, ep, num_sms, 0));
+  if (pair) CK(tc::pair::launch<EpStore>(tah, tal, tbh, tbl, sh, ep, num_sms, 0));
+  else CK(tc::launch<EpStore>(tah, tal, tbh, tbl, sh, ep, num_sms, 0));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("case M=%lld N=%lld d=%d passes=%d: kernel failed: %s\n", (long long)M, (long long)N, d, passes,
@@ -134,15 +136,15 @@ static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_
   double scale = d / 3.0;
   double tol = passes == 1 ? 2e-3 : 8e-6;
   if (max_abs / scale > tol) bad = 1;
-  printf("case M=%-5lld N=%-5lld d=%-4d passes=%d same=%d: max_abs_err=%.3e (rel to |a||b| %.3e) nan=%lld worst@(%lld,%lld) got=%.7f ref=%.7f  %s\n",
-         (long long)M, (long long)N, d, passes, (int)same, max_abs, max_abs / scale, (long long)nan,
+  printf("%s M=%-5lld N=%-5lld d=%-4d passes=%d same=%d: max_abs_err=%.3e (rel to |a||b| %.3e) nan=%lld worst@(%lld,%lld) got=%.7f ref=%.7f  %s\n",
+         pair ? "pair" : "case", (long long)M, (long long)N, d, passes, (int)same, max_abs, max_abs / scale, (long long)nan,
          (long long)(worst / N), (long long)(worst % N), ho[worst], hr[worst], (bad || nan) ? "FAIL" : "ok");
   cudaFree(a); cudaFree(b); cudaFree(ahi); cudaFree(alo); cudaFree(bhi); cudaFree(blo);
   cudaFree(na); cudaFree(nb); cudaFree(out); cudaFree(ref);
   return (bad || nan) ? 1 : 0;
 }
 
-static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int num_sms) {
+static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int num_sms, bool pair = false) {
   int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
   float *a, *ahi, *alo, *na, *out;
   CK(cudaMalloc(&a, M * d * 4));
@@ -153,28 +155,34 @@ static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int
   for (int64_t i = 0; i < M * d; ++i) ha[i] = (float)((double)(splitmix(i + 17) >> 40) / 8388608.0 - 1.0);
   CK(cudaMemcpy(a, ha.data(), M * d * 4, cudaMemcpyHostToDevice));
   CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
-  CUtensorMap tah, tal;
+  CUtensorMap tah, tal, tbh, tbl;
   tc::make_plane_tmap(&tah, ahi, M, dpad);
   tc::make_plane_tmap(&tal, alo, M, dpad);
+  tc::make_plane_tmap(&tbh, ahi, M, dpad, pair ? tc::BN / 2 : tc::BN);
+  tc::make_plane_tmap(&tbl, alo, M, dpad, pair ? tc::BN / 2 : tc::BN);
   tc::Shape sh = tc::make_shape(M, N, d, n_splits, passes);
   CK(cudaMalloc(&out, M * sh.n_splits * tc::EPI_H * 4));
   EpRowMax::Params ep{out, sh.n_splits};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i) CK(tc::launch<EpRowMax>(tah, tal, tah, tal, sh, ep, num_sms, 0));
+  auto go = [&]() {
+    return pair ? tc::pair::launch<EpRowMax>(tah, tal, tbh, tbl, sh, ep, num_sms, 0)
+                : tc::launch<EpRowMax>(tah, tal, tbh, tbl, sh, ep, num_sms, 0);
+  };
+  for (int i = 0; i < 3; ++i) CK(go());
   CK(cudaDeviceSynchronize());
   const int iters = 20;
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; ++i) CK(tc::launch<EpRowMax>(tah, tal, tah, tal, sh, ep, num_sms, 0));
+  for (int i = 0; i < iters; ++i) CK(go());
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   double us = ms * 1000.0 / iters;
   double flops = 2.0 * M * N * d;
-  printf("time M=%lld N=%lld d=%d passes=%d n_splits=%d items=%d: %.2f us/launch  -> %.1f TFLOP/s algorithmic, %.1f TFLOP/s TF32 issued\n",
-         (long long)M, (long long)N, d, passes, sh.n_splits, sh.tiles_m * sh.n_splits, us, flops / us * 1e-6,
+  printf("%s M=%lld N=%lld d=%d passes=%d n_splits=%d items=%d: %.2f us/launch  -> %.1f TFLOP/s algorithmic, %.1f TFLOP/s TF32 issued\n",
+         pair ? "time-pair" : "time", (long long)M, (long long)N, d, passes, sh.n_splits, sh.tiles_m * sh.n_splits, us, flops / us * 1e-6,
          flops * passes / us * 1e-6);
   cudaFree(a); cudaFree(ahi); cudaFree(alo); cudaFree(na); cudaFree(out);
 }
@@ -195,6 +203,14 @@ int main(int argc, char** argv) {
   fails += run_case(1000, 1000, 512, 1, true, sms);
   fails += run_case(1000, 1000, 512, 3, true, sms);
   fails += run_case(2048, 4096, 256, 3, false, sms);
+  if (argc > 1) {
+    fails += run_case(256, 128, 32, 1, false, sms, true);
+    fails += run_case(256, 128, 32, 3, false, sms, true);
+    fails += run_case(256, 384, 64, 3, false, sms, true);
+    fails += run_case(300, 200, 100, 3, false, sms, true);
+    fails += run_case(1000, 1000, 512, 3, true, sms, true);
+    fails += run_case(2048, 4096, 256, 3, false, sms, true);
+  }
   printf("selftest: %d failing cases\n", fails);
   if (true) {
     time_case(4096, 4096, 512, 3, 32, sms);
@@ -202,6 +218,11 @@ int main(int argc, char** argv) {
     time_case(4096, 4096, 512, 1, 32, sms);
     time_case(16384, 16384, 512, 3, 16, sms);
     time_case(16384, 16384, 512, 1, 16, sms);
+    if (argc > 1) {
+      time_case(4096, 4096, 512, 3, 32, sms, true);
+      time_case(16384, 16384, 512, 3, 16, sms, true);
+      time_case(16384, 16384, 512, 1, 16, sms, true);
+    }
   }
   return fails ? 1 : 0;
 }
