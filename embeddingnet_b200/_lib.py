@@ -44,6 +44,7 @@ SIGNATURES = {
     "en_loss_select": (c_int, [P, c_int64, c_float, c_int, c_int, P, P]),
     "en_ws_bytes_batch_hard": (c_size_t, [c_int64, c_int]),
     "en_batch_hard_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+    "en_batch_hard_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "en_batch_hard_bwd": (c_int, [P, c_int64, c_int, c_int, P, P, P, P, P, P, P, P]),
     "en_ws_bytes_batch_all": (c_size_t, [c_int64, c_int, c_int]),
     "en_batch_all_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, c_size_t, P]),

@@ -20,13 +20,26 @@ namespace {
 constexpr float kBig = 3.0e38f;
 
 // warp-cooperative exact squared distance between rows i and j (float64 accumulate); result in every lane
-__device__ __forceinline__ double exact_d2(const float* __restrict__ e, int d, int64_t i, int64_t j, int lane) {
+// (not inlined: it is called from many sites of kernels whose warps run the code once, where instruction fetch,
+// not issue, is the cost -- ncu round 1: stall_no_instruction 6.4 per issue in the finalize kernel)
+__device__ __noinline__ double exact_d2(const float* __restrict__ e, int d, int64_t i, int64_t j, int lane) {
   const float* a = e + i * d;
   const float* b = e + j * d;
   double acc = 0.0;
-  for (int c = lane; c < d; c += 32) {
-    const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
-    acc += t * t;
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0) {
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(a + c), y = *reinterpret_cast<const float4*>(b + c);
+      double t;
+      t = static_cast<double>(x.x) - static_cast<double>(y.x); acc = fma(t, t, acc);
+      t = static_cast<double>(x.y) - static_cast<double>(y.y); acc = fma(t, t, acc);
+      t = static_cast<double>(x.z) - static_cast<double>(y.z); acc = fma(t, t, acc);
+      t = static_cast<double>(x.w) - static_cast<double>(y.w); acc = fma(t, t, acc);
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) {
+      const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
+      acc = fma(t, t, acc);
+    }
   }
   return warp_sum(acc);
 }
@@ -177,14 +190,13 @@ struct BhPick {
 };
 
 template <bool kMax>
-__device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict__ emb, int d,
-                                            const float* __restrict__ norms, float na, int64_t row, float best,
-                                            float val, int idx, int lane) {
+__device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict__ emb, int d, float na, float nb,
+                                            int64_t row, float best, float val, int idx, int lane) {
   // error band of the 3xTF32 dot product: a few 1e-6 |a||b| <= 1e-5 (|a|^2 + |b|^2) / 2; the proxy error is twice
   // that, and both the best and the contender carry it
   bool contender = false;
   if (idx >= 0) {
-    const float band = 2.0e-5f * (na + norms[idx]) + 1e-30f;
+    const float band = 2.0e-5f * (na + nb) + 1e-30f;
     contender = kMax ? (val >= best - band) : (val <= best + band);
   }
   unsigned m = __ballot_sync(0xffffffffu, contender);
@@ -202,13 +214,37 @@ __device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict
   }
 }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// gemb += s * (e_i - e_j) on row `dst` (atomically: several anchors may select the same row)
+__device__ __noinline__ void red_axpy_diff(float* __restrict__ gemb, const float* __restrict__ emb, int d,
+                                              int64_t dst, int64_t i, int64_t j, float s, int lane) {
+  const float* a = emb + i * d;
+  const float* b = emb + j * d;
+  float* g = gemb + dst * d;
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(gemb) & 15) == 0) {
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(a + c), y = *reinterpret_cast<const float4*>(b + c);
+      red_add_v4(g + c, s * (x.x - y.x), s * (x.y - y.y), s * (x.z - y.z), s * (x.w - y.w));
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) atomicAdd(g + c, s * (a[c] - b[c]));
+  }
+}
+
+// kGrad: also accumulate d loss / d emb into a ZEROED gemb (fused loss + gradient: the rows of the selected
+// positive / negative are already hot from the exact re-evaluation).
+template <bool kGrad>
 __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                            const float* __restrict__ norms, const BhCand* __restrict__ cand,
                                            int64_t B, int d, int tiles_n, float margin, int squared, int soft,
                                            int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
                                            float* __restrict__ hp_out, float* __restrict__ hn_out,
                                            float* __restrict__ coef, double* __restrict__ partial,
-                                           unsigned* __restrict__ counter, float* __restrict__ loss) {
+                                           unsigned* __restrict__ counter, float* __restrict__ loss,
+                                           const float* __restrict__ gloss, float* __restrict__ gemb) {
   __shared__ double sh[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
@@ -233,20 +269,27 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
       bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
-    // pass 2: exact re-evaluation of everything inside the band
+    // pass 2: exact re-evaluation of everything inside the band (kept compact: each warp runs this code once, so
+    // instruction fetch dominates when it is unrolled)
     BhPick pos{-1.0, -1}, neg{1e300, -1};
+#pragma unroll 1
     for (int t0 = 0; t0 < n_cand; t0 += 32) {
       const int t = t0 + lane;
       float4 v = make_float4(-kBig, -kBig, kBig, kBig);
       int4 ix = make_int4(-1, -1, -1, -1);
       if (slot_valid(t)) {
-        v = reinterpret_cast<const float4*>(mine + t)[0];
-        ix = reinterpret_cast<const int4*>(mine + t)[1];
+        v = __ldcg(reinterpret_cast<const float4*>(mine + t));
+        ix = __ldcg(reinterpret_cast<const int4*>(mine + t) + 1);
       }
-      bh_consider<true>(pos, emb, d, norms, na, row, bp, v.x, ix.x, lane);
-      bh_consider<true>(pos, emb, d, norms, na, row, bp, v.y, ix.y, lane);
-      bh_consider<false>(neg, emb, d, norms, na, row, bn, v.z, ix.z, lane);
-      bh_consider<false>(neg, emb, d, norms, na, row, bn, v.w, ix.w, lane);
+      // the four norm loads are independent: issue them together, ahead of the dependent ballots
+      const float nb0 = ix.x >= 0 ? __ldg(&norms[ix.x]) : 0.f;
+      const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
+      const float nb2 = ix.z >= 0 ? __ldg(&norms[ix.z]) : 0.f;
+      const float nb3 = ix.w >= 0 ? __ldg(&norms[ix.w]) : 0.f;
+      bh_consider<true>(pos, emb, d, na, nb0, row, bp, v.x, ix.x, lane);
+      bh_consider<true>(pos, emb, d, na, nb1, row, bp, v.y, ix.y, lane);
+      bh_consider<false>(neg, emb, d, na, nb2, row, bn, v.z, ix.z, lane);
+      bh_consider<false>(neg, emb, d, na, nb3, row, bn, v.w, ix.w, lane);
     }
     if (neg.idx < 0) {
       // No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row
@@ -276,6 +319,22 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       hp_out[row] = static_cast<float>(hp);
       hn_out[row] = static_cast<float>(hn);
       coef[row] = static_cast<float>(g / static_cast<double>(B));
+    }
+    if (kGrad) {
+      const float gg = static_cast<float>(g / static_cast<double>(B)) * (gloss ? gloss[0] : 1.0f);
+      if (gg != 0.f) {
+        const float hpf = static_cast<float>(hp), hnf = static_cast<float>(hn);
+        const float sp = pos.idx >= 0 ? (squared ? 2.f * gg : (hpf > 0.f ? gg / hpf : 0.f)) : 0.f;
+        const float sn = neg.idx >= 0 ? (squared ? 2.f * gg : (hnf > 0.f ? gg / hnf : 0.f)) : 0.f;
+        if (sp != 0.f) {
+          red_axpy_diff(gemb, emb, d, row, row, pos.idx, sp, lane);
+          red_axpy_diff(gemb, emb, d, pos.idx, row, pos.idx, -sp, lane);
+        }
+        if (sn != 0.f) {
+          red_axpy_diff(gemb, emb, d, row, row, neg.idx, -sn, lane);
+          red_axpy_diff(gemb, emb, d, neg.idx, row, neg.idx, sn, lane);
+        }
+      }
     }
   }
   // deterministic mean: per-block partials, the last block to finish adds them in index order
@@ -334,9 +393,6 @@ __global__ void batch_hard_bwd_own_kernel(const float* __restrict__ emb, int64_t
   }
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // Backward, stage 2: scatter the mirrored terms into the selected positive / negative rows.
 __global__ void batch_hard_bwd_scatter_kernel(const float* __restrict__ emb, int64_t B, int d, int squared,
@@ -804,15 +860,15 @@ size_t en_ws_bytes_batch_hard(int64_t B, int d) {
          align_up(static_cast<size_t>((B + 7) / 8) * sizeof(double)) + align_up(sizeof(unsigned));
 }
 
-int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared, int soft,
-                      float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef, void* ws,
-                      size_t ws_bytes, void* stream) {
+static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                           int soft, float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn,
+                           float* coef, const float* gloss, float* gemb, void* ws, size_t ws_bytes, void* stream,
+                           const char* who) {
   EN_REQUIRE(emb && labels && loss && hp_idx && hn_idx && hp && hn && coef && B > 0 && d > 0,
-             "en_batch_hard_fwd: bad arguments (B=%lld d=%d)", (long long)B, d);
+             "%s: bad arguments (B=%lld d=%d)", who, (long long)B, d);
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < en_ws_bytes_batch_hard(B, d))
-    return fail(EN_ERR_WORKSPACE, "en_batch_hard_fwd: workspace too small (%zu < %zu)", ws_bytes,
-                en_ws_bytes_batch_hard(B, d));
+    return fail(EN_ERR_WORKSPACE, "%s: workspace too small (%zu < %zu)", who, ws_bytes, en_ws_bytes_batch_hard(B, d));
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
   TcOperands o;
@@ -822,18 +878,40 @@ int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d,
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
   double* partial = w.take<double>(blocks);
   unsigned* counter = w.take<unsigned>(1);
-  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_hard_fwd: workspace too small or misaligned");
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "%s: workspace too small or misaligned", who);
   EN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  if (gemb) EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * sizeof(float), st));
   tc::Shape sh = tc::make_shape_symmetric(B, d, 3);  // upper-triangular tiles, one per work item
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
   prof_begin(st);
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
   prof_end(st);
   ++launch_counter();
-  batch_hard_finalize_kernel<<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft,
-                                                     hp_idx, hn_idx, hp, hn, coef, partial, counter, loss);
+  if (gemb)
+    batch_hard_finalize_kernel<true><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
+                                                             squared, soft, hp_idx, hn_idx, hp, hn, coef, partial,
+                                                             counter, loss, gloss, gemb);
+  else
+    batch_hard_finalize_kernel<false><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
+                                                              squared, soft, hp_idx, hn_idx, hp, hn, coef, partial,
+                                                              counter, loss, nullptr, nullptr);
   EN_LAUNCHED("batch_hard_finalize_kernel");
   return EN_OK;
+}
+
+int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared, int soft,
+                      float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef, void* ws,
+                      size_t ws_bytes, void* stream) {
+  return batch_hard_core(emb, labels, B, d, margin, squared, soft, loss, hp_idx, hn_idx, hp, hn, coef, nullptr,
+                         nullptr, ws, ws_bytes, stream, "en_batch_hard_fwd");
+}
+
+int en_batch_hard_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                          int soft, float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef,
+                          const float* gloss, float* gemb, void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(gemb != nullptr, "en_batch_hard_fwd_bwd: gemb is null");
+  return batch_hard_core(emb, labels, B, d, margin, squared, soft, loss, hp_idx, hn_idx, hp, hn, coef, gloss, gemb,
+                         ws, ws_bytes, stream, "en_batch_hard_fwd_bwd");
 }
 
 int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int32_t* hp_idx, const int32_t* hn_idx,

@@ -36,9 +36,7 @@ class BatchHardStep:
         assert labels.dtype == torch.int32 and labels.numel() == B and labels.is_cuda
         s = stream_ptr()
         si, sf = self.saved_i, self.saved_f
-        _lib.call("en_batch_hard_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(self.margin), self.squared,
+        _lib.call("en_batch_hard_fwd_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(self.margin), self.squared,
                   self.soft, ptr(self.loss), ptr(si[0]), ptr(si[1]), ptr(sf[0]), ptr(sf[1]), ptr(sf[2]),
-                  ptr(self.ws), self.ws.numel(), s)
-        _lib.call("en_batch_hard_bwd", ptr(emb), B, d, self.squared, ptr(si[0]), ptr(si[1]), ptr(sf[0]), ptr(sf[1]),
-                  ptr(sf[2]), ptr(self.gloss), ptr(self.grad), s)
+                  ptr(self.gloss), ptr(self.grad), ptr(self.ws), self.ws.numel(), s)
         return self.loss, self.grad

@@ -195,32 +195,34 @@ def siamese_l1_distance(e1, e2):
 
 # ------------------------------------------------------------------------------------------------ batch-hard
 class _BatchHard(torch.autograd.Function):
+    """Forward computes the loss AND d loss / d emb in the same pass (en_batch_hard_fwd_bwd) whenever a gradient can
+    be asked for; backward is then a scalar multiply."""
+
     @staticmethod
     def forward(ctx, emb, labels, margin, squared, soft):
         B, d = emb.shape
         dev = emb.device
         lib = _lib.load()
-        ws_bytes = lib.en_ws_bytes_batch_hard(B, d)
-        ws = workspace(ws_bytes, dev, "batch_hard")
+        ws = workspace(lib.en_ws_bytes_batch_hard(B, d), dev, "batch_hard")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         saved_i = torch.empty((2, B), dtype=torch.int32, device=dev)
         saved_f = torch.empty((3, B), dtype=torch.float32, device=dev)
-        _lib.call("en_batch_hard_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared), int(soft),
-                  ptr(loss), ptr(saved_i[0]), ptr(saved_i[1]), ptr(saved_f[0]), ptr(saved_f[1]), ptr(saved_f[2]),
-                  ptr(ws), ws.numel(), stream_ptr())
-        ctx.save_for_backward(emb, saved_i, saved_f)
-        ctx.squared = int(squared)
+        if ctx.needs_input_grad[0]:
+            gemb = torch.empty_like(emb)
+            _lib.call("en_batch_hard_fwd_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
+                      int(soft), ptr(loss), ptr(saved_i[0]), ptr(saved_i[1]), ptr(saved_f[0]), ptr(saved_f[1]),
+                      ptr(saved_f[2]), None, ptr(gemb), ptr(ws), ws.numel(), stream_ptr())
+            ctx.save_for_backward(gemb)
+        else:
+            _lib.call("en_batch_hard_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
+                      int(soft), ptr(loss), ptr(saved_i[0]), ptr(saved_i[1]), ptr(saved_f[0]), ptr(saved_f[1]),
+                      ptr(saved_f[2]), ptr(ws), ws.numel(), stream_ptr())
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        emb, saved_i, saved_f = ctx.saved_tensors
-        B, d = emb.shape
-        g = g.contiguous().to(torch.float32).reshape(1)
-        gemb = torch.empty_like(emb)
-        _lib.call("en_batch_hard_bwd", ptr(emb), B, d, ctx.squared, ptr(saved_i[0]), ptr(saved_i[1]),
-                  ptr(saved_f[0]), ptr(saved_f[1]), ptr(saved_f[2]), ptr(g), ptr(gemb), stream_ptr())
-        return gemb, None, None, None, None
+        (gemb,) = ctx.saved_tensors
+        return gemb * g.to(torch.float32), None, None, None, None
 
 
 def batch_hard_triplet_loss(margin=0.5, squared=False, soft=False):

@@ -116,6 +116,12 @@ size_t en_ws_bytes_batch_hard(int64_t B, int d);
 int en_batch_hard_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared, int soft,
                       float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef, void* ws,
                       size_t ws_bytes, void* stream);
+/* Loss AND gradient in one call (what a training step needs): gemb (B, d) = gloss[0] * d loss / d emb, with
+ * gloss == NULL meaning 1.  The gradient is accumulated by the same kernel that picks the hardest pairs, so the
+ * step is prep + memset + distance GEMM + finalize.  Same saved outputs as en_batch_hard_fwd. */
+int en_batch_hard_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                          int soft, float* loss, int32_t* hp_idx, int32_t* hn_idx, float* hp, float* hn, float* coef,
+                          const float* gloss, float* gemb, void* ws, size_t ws_bytes, void* stream);
 /* gemb (B, d) = gloss[0] * d loss / d emb; gemb is fully overwritten. */
 int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int32_t* hp_idx, const int32_t* hn_idx,
                       const float* hp, const float* hn, const float* coef, const float* gloss, float* gemb,

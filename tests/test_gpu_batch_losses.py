@@ -81,6 +81,39 @@ def test_batch_hard_selected_indices_are_bit_exact():
     np.testing.assert_allclose(sf[1].cpu().numpy(), ref["hn"], rtol=1e-5, atol=1e-7)
 
 
+def test_fused_step_matches_separate_fwd_and_bwd():
+    """en_batch_hard_fwd_bwd (one pass, used by the autograd path and the CUDA-graph step) vs en_batch_hard_fwd +
+    en_batch_hard_bwd (two passes): same loss bits, same gradient up to atomic summation order."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr, workspace
+    from embeddingnet_b200.fused import BatchHardStep
+
+    x, lab = make_batch(40, 8, 96, True, True)
+    B, d = x.shape
+    e = torch.tensor(x, device="cuda")
+    l = torch.tensor(lab, device="cuda", dtype=torch.int32)
+    for squared, soft in ((0, 0), (1, 0), (0, 1)):
+        st = BatchHardStep(B, d, 0.5, squared=squared, soft=soft)
+        loss1, g1 = st.step(e, l)
+        lib = _lib.load()
+        ws = workspace(lib.en_ws_bytes_batch_hard(B, d), e.device, "t2")
+        loss2 = torch.empty((), device="cuda")
+        si = torch.empty((2, B), dtype=torch.int32, device="cuda")
+        sf = torch.empty((3, B), dtype=torch.float32, device="cuda")
+        _lib.call("en_batch_hard_fwd", ptr(e), ptr(l), B, d, ctypes.c_float(0.5), squared, soft, ptr(loss2),
+                  ptr(si[0]), ptr(si[1]), ptr(sf[0]), ptr(sf[1]), ptr(sf[2]), ptr(ws), ws.numel(), stream_ptr())
+        g2 = torch.empty_like(e)
+        one = torch.ones(1, device="cuda")
+        _lib.call("en_batch_hard_bwd", ptr(e), B, d, squared, ptr(si[0]), ptr(si[1]), ptr(sf[0]), ptr(sf[1]),
+                  ptr(sf[2]), ptr(one), ptr(g2), stream_ptr())
+        torch.cuda.synchronize()
+        assert loss1.item() == loss2.item()
+        assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 1e-6
+        _, g = O.batch_hard_grad(lab, x, 0.5, bool(squared), bool(soft))
+        assert rel_err(g1.cpu().numpy(), g) < 1e-4
+
+
 def test_batch_hard_edge_cases():
     from embeddingnet_b200 import losses_and_accuracies as lac
 
