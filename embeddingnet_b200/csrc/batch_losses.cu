@@ -15,9 +15,17 @@
 #include "tc_engine.cuh"
 
 namespace en {
+
+// csrc/pair_bwd_tc.cu: tensor-core backward of the pair losses (two chained tcgen05 GEMMs)
+size_t pair_bwd_tc_ws_bytes(int64_t B, int d);
+int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
+                       float scale_c, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
+                       const float* gloss, float* gemb, void* ws, size_t ws_bytes, cudaStream_t st);
+
 namespace {
 
 constexpr float kBig = 3.0e38f;
+constexpr int kTcBwdMaxPos = 8;  // pair_bwd_tc_kernel keeps the positives lists in registers / 1 KB of smem
 
 // warp-cooperative exact squared distance between rows i and j (float64 accumulate); result in every lane
 // (not inlined: it is called from many sites of kernels whose warps run the code once, where instruction fetch,
@@ -937,7 +945,10 @@ static size_t pos_bytes(int64_t B, int cap) {
 size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
   if (B <= 0 || d <= 0 || max_positives <= 0 || max_positives > kMaxPos) return 0;
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
-  return operand_bytes(B, d) + pos_bytes(B, max_positives) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
+  const size_t fwd = operand_bytes(B, d) + pos_bytes(B, max_positives) +
+                     align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
+  const size_t bwd = pos_bytes(B, kTcBwdMaxPos) + pair_bwd_tc_ws_bytes(B, d);
+  return fwd > bwd ? fwd : bwd;
 }
 
 struct PosLists {
@@ -1006,28 +1017,35 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
     return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
-  // same carve-up as the forward so a shared workspace keeps the positive lists in place
-  const size_t dpad = static_cast<size_t>((d + tc::BK - 1) / tc::BK * tc::BK);
-  w.take<float>(static_cast<size_t>(B) * dpad);
-  w.take<float>(static_cast<size_t>(B) * dpad);
-  w.take<float>(B);
-  PosLists pl = take_pos(w, B, max_positives);
+  const bool tensor = max_positives <= kTcBwdMaxPos;
+  const int cap = tensor ? kTcBwdMaxPos : max_positives;
+  PosLists pl = take_pos(w, B, cap);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
   collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, max_positives, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
   EN_LAUNCHED("collect_positives_kernel");
-  EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * max_positives * 4, st));
-  EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * 4, st));
-  CoefBatchAll ba{pl.pos_d, pl.pos_n, max_positives, margin, squared, 0.0};
-  const unsigned blocks = static_cast<unsigned>((B + PT - 1) / PT);
-  for (int d_off = 0; d_off < d; d_off += PDMAX) {
-    pair_bwd_kernel<0><<<blocks, 256, 0, st>>>(emb, labels, B, d, d_off, ba, stats, 0.f, gloss, pl.pos_cnt, gemb);
-    EN_LAUNCHED("pair_bwd_kernel<batch_all>");
+  EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
+  if (tensor) {
+    // negatives: two chained tcgen05 GEMMs (csrc/pair_bwd_tc.cu); overwrites gemb
+    void* rest = w.base + w.off;
+    if (int rc = pair_bwd_tc_launch(emb, labels, B, d, 0, squared, margin, 0.f, pl.pos_d, pl.pos_n, pl.pos_cnt, stats,
+                                    gloss, gemb, rest, ws_bytes - w.off, st))
+      return rc;
+  } else {
+    // classes with more than 8 positives per anchor: CUDA-core tile kernel
+    EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * 4, st));
+    CoefBatchAll ba{pl.pos_d, pl.pos_n, cap, margin, squared, 0.0};
+    const unsigned blocks = static_cast<unsigned>((B + PT - 1) / PT);
+    for (int d_off = 0; d_off < d; d_off += PDMAX) {
+      pair_bwd_kernel<0><<<blocks, 256, 0, st>>>(emb, labels, B, d, d_off, ba, stats, 0.f, gloss, pl.pos_cnt, gemb);
+      EN_LAUNCHED("pair_bwd_kernel<batch_all>");
+    }
   }
-  const int64_t warps = B * max_positives;
+  // positives: sparse, one warp per (anchor, positive slot), added atomically
+  const int64_t warps = B * cap;
   batch_all_bwd_pos_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
-      emb, B, d, max_positives, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb);
+      emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb);
   EN_LAUNCHED("batch_all_bwd_pos_kernel");
   return EN_OK;
 }
@@ -1036,7 +1054,9 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
 size_t en_ws_bytes_contrastive_allpairs(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
-  return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
+  const size_t fwd = operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
+  const size_t bwd = pair_bwd_tc_ws_bytes(B, d);
+  return fwd > bwd ? fwd : bwd;
 }
 
 int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float* loss, void* ws,
@@ -1066,18 +1086,11 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
 int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t B, int d, const float* gloss,
                                 float* gemb, void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(emb && labels && gloss && gemb && B > 1 && d > 0, "en_contrastive_allpairs_bwd: bad arguments");
-  (void)ws;
-  (void)ws_bytes;
-  cudaStream_t st = as_stream(stream);
-  EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * 4, st));
-  CoefBatchAll ba{nullptr, nullptr, 0, 0.f, 0, 0.0};
+  if (!ws || ws_bytes < en_ws_bytes_contrastive_allpairs(B, d))
+    return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_bwd: workspace too small");
   const float scale = static_cast<float>(1.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
-  const unsigned blocks = static_cast<unsigned>((B + PT - 1) / PT);
-  for (int d_off = 0; d_off < d; d_off += PDMAX) {
-    pair_bwd_kernel<1><<<blocks, 256, 0, st>>>(emb, labels, B, d, d_off, ba, nullptr, scale, gloss, nullptr, gemb);
-    EN_LAUNCHED("pair_bwd_kernel<contrastive>");
-  }
-  return EN_OK;
+  return pair_bwd_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, gemb, ws,
+                            ws_bytes, as_stream(stream));
 }
 
 }  // extern "C"

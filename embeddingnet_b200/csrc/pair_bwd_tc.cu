@@ -1,0 +1,470 @@
+// Tensor-core backward for the pair losses (batch-all triplet negatives, all-pairs contrastive):
+//
+//     d L / d E  =  rowsum(C) o E  -  C . E ,       C_ik = symmetrised pair coefficient, a function of D_ik
+//
+// One kernel, two chained tcgen05 GEMMs per 128 x 128 tile, nothing of size B x B ever stored:
+//   GEMM1  S  = E_I . E_J^T            3xTF32, operands by TMA, accumulator in TMEM
+//   epilogue  C_IJ = f(S, labels, positives lists)   8 warps pull S out of TMEM into registers (releasing the
+//                                     accumulator at once), build C and write it BACK to TMEM with tcgen05.st as
+//                                     two TF32 planes C_hi + C_lo
+//   GEMM2  G += C_IJ . E_J[:, slice]   A operand from TMEM (tcgen05.mma [d],[a],b), B operand = E^T tiles by TMA;
+//                                     C_hi.E_hi + C_hi.E_lo + C_lo.E_hi
+// A CTA owns (row tile I, 128-column slice of the gradient) and walks all column tiles J; GEMM1 of tile J+1 is
+// issued before GEMM2 of tile J so the tensor pipe has work while the epilogue warps build C_J.
+//
+// Cancellation: grad_i = sum_k c_ik (e_i - e_k) is computed as rowsum_i e_i - (C.E)_i.  For post-ReLU embeddings
+// (all components >= 0, cosines ~0.8) the two terms are ~10x larger than their difference, which amplified the
+// tensor core's accumulation bias to 1e-4.  The expression is invariant under E -> E - mu, so GEMM2 and the
+// rowsum term both use the mean-centred embeddings (mu = column mean), which removes the cancellation.
+//
+// This replaces the O(B^2 d) CUDA-core kernel (csrc/batch_losses.cu: pair_bwd_kernel, kept for classes with more
+// than 8 positives per anchor).  Math: see en_batch_all_bwd / en_contrastive_allpairs_bwd.
+#include "common.cuh"
+#include "tc_engine.cuh"
+
+namespace en {
+namespace pbt {
+
+using tc::BK;
+using tc::BM;
+using tc::BN;
+using tc::UMMA_K;
+
+constexpr int DN = 128;                 // gradient columns per work item (UMMA N of GEMM2)
+constexpr int TILE_BYTES = BM * BK * 4; // 16 KiB
+constexpr int G1_STAGES = 2;            // GEMM1 ring: A_hi | A_lo | B_hi | B_lo
+constexpr int G1_STAGE_BYTES = 4 * TILE_BYTES;
+constexpr int ET_STAGES = 2;            // GEMM2 B ring: ET_hi | ET_lo, each [128 gradient columns x 32 rows j]
+constexpr int ET_STAGE_BYTES = 2 * TILE_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MAXP = 8;                 // positives per anchor handled by this kernel
+constexpr int WARP_SCR = 128 + 128 + 32 * MAXP * 4;  // norms | labels | column positives lists
+constexpr int SMEM_BYTES = G1_STAGES * G1_STAGE_BYTES + ET_STAGES * ET_STAGE_BYTES + 256 + EPI_WARPS * WARP_SCR +
+                           BM * 2 * 4;
+constexpr uint32_t TM_ACC1 = 0;    // 128 columns: S (single buffer: the epilogue copies it to registers and releases it)
+constexpr uint32_t TM_CHI = 128;   // 128 columns: coefficient tile, TF32 high part (A operand of GEMM2)
+constexpr uint32_t TM_CLO = 256;   // 128 columns: coefficient tile, TF32 low part
+constexpr uint32_t TM_ACC2 = 384;  // 128 columns: the gradient slice accumulator
+
+struct Bars {
+  uint64_t g1_full[G1_STAGES], g1_empty[G1_STAGES];
+  uint64_t et_full[ET_STAGES], et_empty[ET_STAGES];
+  uint64_t acc1_full, acc1_empty;
+  uint64_t c_full, c_empty, acc2_full, acc2_empty;
+  uint32_t tmem_base;
+};
+
+struct Params {
+  const float* emb;
+  const int32_t* labels;
+  const float* norms;
+  const float* pos_d;     // [B][MAXP] (batch-all)
+  const int32_t* pos_n;   // [B]
+  int32_t* pos_cnt;       // [B][MAXP] out: active negatives per (anchor, positive slot)
+  const double* stats;    // stats[1] = number of positive triplets
+  const float* gloss;
+  const float* mu;        // [d] column means of emb
+  float* gemb;
+  int64_t B;
+  int d, tiles, n_slices, kblocks;
+  int mode;               // 0 = batch-all, 1 = all-pairs contrastive
+  int squared;
+  float margin, scale_c;
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                   const __grid_constant__ CUtensorMap tm_et_hi, const __grid_constant__ CUtensorMap tm_et_lo,
+                   const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* g1 = smem;
+  uint8_t* et = smem + G1_STAGES * G1_STAGE_BYTES;
+  Bars* bars = reinterpret_cast<Bars*>(et + ET_STAGES * ET_STAGE_BYTES);
+  uint8_t* warp_scr = reinterpret_cast<uint8_t*>(bars) + 256;
+  float* rowsum_x = reinterpret_cast<float*>(warp_scr + EPI_WARPS * WARP_SCR);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.tiles * p.n_slices;
+  const int T = p.tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+    ptx::prefetch_tmap(&tm_et_hi);
+    ptx::prefetch_tmap(&tm_et_lo);
+    for (int s = 0; s < G1_STAGES; ++s) { ptx::mbar_init(&bars->g1_full[s], 1); ptx::mbar_init(&bars->g1_empty[s], 1); }
+    for (int s = 0; s < ET_STAGES; ++s) { ptx::mbar_init(&bars->et_full[s], 1); ptx::mbar_init(&bars->et_empty[s], 1); }
+    ptx::mbar_init(&bars->acc1_full, 1);
+    ptx::mbar_init(&bars->acc1_empty, EPI_WARPS);
+    ptx::mbar_init(&bars->c_full, EPI_WARPS);
+    ptx::mbar_init(&bars->c_empty, 1);
+    ptx::mbar_init(&bars->acc2_full, 1);
+    ptx::mbar_init(&bars->acc2_empty, EPI_WARPS);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int gs = 0, es = 0;
+      uint32_t gph = 0, eph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ti = item % T, slice = item / T;
+        auto load_g1 = [&](int J) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&bars->g1_empty[gs], gph ^ 1);
+            uint8_t* st = g1 + gs * G1_STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&bars->g1_full[gs], G1_STAGE_BYTES);
+            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 0 * TILE_BYTES, kb * BK, ti * BM);
+            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 1 * TILE_BYTES, kb * BK, ti * BM);
+            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 2 * TILE_BYTES, kb * BK, J * BN);
+            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 3 * TILE_BYTES, kb * BK, J * BN);
+            if (++gs == G1_STAGES) { gs = 0; gph ^= 1; }
+          }
+        };
+        auto load_et = [&](int J) {
+          for (int kb2 = 0; kb2 < BN / BK; ++kb2) {
+            ptx::mbar_wait(&bars->et_empty[es], eph ^ 1);
+            uint8_t* st = et + es * ET_STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&bars->et_full[es], ET_STAGE_BYTES);
+            ptx::tma_load_2d(&tm_et_hi, &bars->et_full[es], st, J * BN + kb2 * BK, slice * DN);
+            ptx::tma_load_2d(&tm_et_lo, &bars->et_full[es], st + TILE_BYTES, J * BN + kb2 * BK, slice * DN);
+            if (++es == ET_STAGES) { es = 0; eph ^= 1; }
+          }
+        };
+        // same order as the MMA warp consumes: G1(0), then per tile G1(J+1), ET(J)
+        load_g1(0);
+        for (int J = 0; J < T; ++J) {
+          if (J + 1 < T) load_g1(J + 1);
+          load_et(J);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN);
+      int gs = 0, es = 0;
+      uint32_t gph = 0, eph = 0, acc1_it = 0, c_it = 0, item_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+        auto gemm1 = [&]() {
+          ptx::mbar_wait(&bars->acc1_empty, (acc1_it & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tm = tmem + TM_ACC1;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&bars->g1_full[gs], gph);
+            ptx::tc_fence_after();
+            const uint32_t st = ptx::smem_u32(g1 + gs * G1_STAGE_BYTES);
+            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st), a_lo = ptx::make_kmajor_sw128_desc(st + TILE_BYTES);
+            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(st + 2 * TILE_BYTES),
+                           b_lo = ptx::make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
+              // one accumulator for all three products here: the backward only needs S to decide hinge activity
+              // and 1/D factors, where the ~6e-6 accumulation bias is far inside the gradient tolerance
+              ptx::mma_tf32_ss(d_tm, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+              ptx::mma_tf32_ss(d_tm, a_hi + koff, b_lo + koff, idesc, 1);
+              ptx::mma_tf32_ss(d_tm, a_hi + koff, b_hi + koff, idesc, 1);
+            }
+            ptx::mma_commit(&bars->g1_empty[gs]);
+            if (++gs == G1_STAGES) { gs = 0; gph ^= 1; }
+          }
+          ptx::mma_commit(&bars->acc1_full);
+          ++acc1_it;
+        };
+        ptx::mbar_wait(&bars->acc2_empty, (item_it & 1) ^ 1);
+        ptx::tc_fence_after();
+        gemm1();
+        for (int J = 0; J < T; ++J) {
+          if (J + 1 < T) gemm1();
+          ptx::mbar_wait(&bars->c_full, c_it & 1);
+          ptx::tc_fence_after();
+          for (int kb2 = 0; kb2 < BN / BK; ++kb2) {
+            ptx::mbar_wait(&bars->et_full[es], eph);
+            ptx::tc_fence_after();
+            const uint32_t st = ptx::smem_u32(et + es * ET_STAGE_BYTES);
+            const uint64_t e_hi = ptx::make_kmajor_sw128_desc(st), e_lo = ptx::make_kmajor_sw128_desc(st + TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
+              const uint32_t a_hi = tmem + TM_CHI + kb2 * BK + k * UMMA_K;
+              const uint32_t a_lo = tmem + TM_CLO + kb2 * BK + k * UMMA_K;
+              ptx::mma_tf32_ts(tmem + TM_ACC2, a_lo, e_hi + koff, idesc, (J | kb2 | k) != 0);
+              ptx::mma_tf32_ts(tmem + TM_ACC2, a_hi, e_lo + koff, idesc, 1);
+              ptx::mma_tf32_ts(tmem + TM_ACC2, a_hi, e_hi + koff, idesc, 1);
+            }
+            ptx::mma_commit(&bars->et_empty[es]);
+            if (++es == ET_STAGES) { es = 0; eph ^= 1; }
+          }
+          ptx::mma_commit(&bars->c_empty);
+          ++c_it;
+        }
+        ptx::mma_commit(&bars->acc2_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps: build C, then write the slice
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* ws = warp_scr + (warp - 2) * WARP_SCR;
+    float* wf = reinterpret_cast<float*>(ws);
+    int32_t* wi = reinterpret_cast<int32_t*>(ws + 128);
+    float* wpos = reinterpret_cast<float*>(ws + 256);  // [32 columns][MAXP], margin added, -inf padded
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t e_it = 0, item_it = 0;
+    const float gl = p.gloss ? p.gloss[0] : 1.f;
+    const float inv_np = p.mode == 0 ? static_cast<float>(1.0 / (p.stats[1] + 1e-16)) : 0.f;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+      const int ti = item % T, slice = item / T;
+      const int64_t row = static_cast<int64_t>(ti) * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.B;
+      const int32_t la = row_ok ? p.labels[row] : -1;
+      const float na = row_ok ? p.norms[row] : 0.f;
+      float pi[MAXP];
+      int cnt_s[MAXP];
+      int npi = 0;
+      if (p.mode == 0) {
+        npi = row_ok ? p.pos_n[row] : 0;
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s) {
+          pi[s] = (s < npi) ? p.pos_d[row * MAXP + s] + p.margin : -INFINITY;
+          cnt_s[s] = 0;
+        }
+      }
+      double rowsum = 0.0;
+      for (int J = 0; J < T; ++J, ++e_it) {
+        ptx::mbar_wait(&bars->acc1_full, e_it & 1);
+        ptx::tc_fence_after();
+        // pull this thread's 64 columns of S into registers and hand the accumulator straight back to the MMA warp
+        float sv[2][32];
+        ptx::tmem_ld_32x32(tmem + lane_base + TM_ACC1 + (half * 2 + 0) * 32, sv[0]);
+        ptx::tmem_ld_32x32(tmem + lane_base + TM_ACC1 + (half * 2 + 1) * 32, sv[1]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->acc1_empty);
+#pragma unroll
+        for (int cc2 = 0; cc2 < 2; ++cc2) {
+          const int c = half * 2 + cc2;
+          const int64_t col0 = static_cast<int64_t>(J) * BN + c * 32;
+          float (&v)[32] = sv[cc2];
+          // stage the 32 columns' norms / labels / positives lists
+          {
+            const int64_t cc = col0 + lane;
+            const bool ok = cc < p.B;
+            __syncwarp();
+            wf[lane] = ok ? __ldg(&p.norms[cc]) : 0.f;
+            wi[lane] = ok ? __ldg(&p.labels[cc]) : -2;
+            if (p.mode == 0) {
+              const int npk = ok ? p.pos_n[cc] : 0;
+#pragma unroll
+              for (int s = 0; s < MAXP; ++s)
+                wpos[lane * MAXP + s] = (s < npk) ? p.pos_d[cc * MAXP + s] + p.margin : -INFINITY;
+            }
+            __syncwarp();
+          }
+          float lo[32];
+          float chunk_sum = 0.f;
+          // interior chunks (no ragged edge, no diagonal) skip the per-element index checks
+          const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = interior || (row_ok && col0 + j < p.B && col0 + j != row);
+            const float d2 = fmaxf(na + wf[j] - 2.f * v[j], 0.f);
+            // 1/sqrt via the SFU (relative error ~1e-7): 1/d and d = d2/d come from one MUFU instead of an IEEE
+            // sqrt plus an IEEE divide per element -- the epilogue, not the tensor pipe, bounds this kernel
+            const float rs = d2 > 0.f ? rsqrtf(d2) : 0.f;
+            float cv = 0.f;
+            if (p.mode == 1) {
+              // t'(d2) = 1 (same label) or -max(1 - d, 0) / d = -max(1/d - 1, 0); clamp region d2 < 1e-7 has zero slope
+              const float diff = -fmaxf(rs - 1.f, 0.f);
+              cv = (ok && d2 >= 1e-7f) ? 4.f * p.scale_c * (wi[j] == la ? 1.f : diff) : 0.f;
+            } else {
+              const bool isneg = ok && wi[j] != la;
+              const float dn = p.squared ? d2 : d2 * rs;
+              int cnt = 0;
+#pragma unroll
+              for (int s = 0; s < MAXP; ++s) {
+                const int act = (isneg && (pi[s] - dn) > 1e-16f) ? 1 : 0;
+                cnt += act;
+                cnt_s[s] += act;
+              }
+              const float4 q0 = *reinterpret_cast<const float4*>(wpos + j * MAXP);
+              const float4 q1 = *reinterpret_cast<const float4*>(wpos + j * MAXP + 4);
+              cnt += (q0.x - dn > 1e-16f) + (q0.y - dn > 1e-16f) + (q0.z - dn > 1e-16f) + (q0.w - dn > 1e-16f) +
+                     (q1.x - dn > 1e-16f) + (q1.y - dn > 1e-16f) + (q1.z - dn > 1e-16f) + (q1.w - dn > 1e-16f);
+              const float sfac = p.squared ? 2.f : rs;
+              cv = isneg ? -static_cast<float>(cnt) * inv_np * sfac : 0.f;
+            }
+            const float h = tf32_round(cv);
+            const float l = tf32_round(cv - h);
+            chunk_sum += h + l;   // exactly what the two MMAs will see
+            v[j] = h;
+            lo[j] = l;
+          }
+          rowsum += static_cast<double>(chunk_sum);
+          if (cc2 == 0) {
+            ptx::mbar_wait(&bars->c_empty, (e_it & 1) ^ 1);  // GEMM2 of the previous tile has consumed C
+            ptx::tc_fence_after();
+          }
+          ptx::tmem_st_32x32(tmem + lane_base + TM_CHI + c * 32, v);
+          ptx::tmem_st_32x32(tmem + lane_base + TM_CLO + c * 32, lo);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->c_full);
+      }
+      // ---- the gradient slice: gl * (rowsum_i * e_i - (C.E)_i)
+      rowsum_x[half * BM + quarter * 32 + lane] = static_cast<float>(rowsum);
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      const float rs = rowsum_x[quarter * 32 + lane] + rowsum_x[BM + quarter * 32 + lane];
+      ptx::mbar_wait(&bars->acc2_full, item_it & 1);
+      ptx::tc_fence_after();
+      for (int c = half * 2; c < half * 2 + 2; ++c) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem + lane_base + TM_ACC2 + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          const int col0 = slice * DN + c * 32;
+          const float* er = p.emb + row * p.d;
+          float* gr = p.gemb + row * p.d;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.d) gr[col0 + j] = gl * (rs * (er[col0 + j] - __ldg(&p.mu[col0 + j])) - v[j]);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->acc2_empty);
+      ptx::named_bar_sync(1, EPI_WARPS * 32);  // rowsum_x may be rewritten by the next item
+      if (p.mode == 0 && slice == 0 && row_ok) {
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s)
+          if (s < npi && cnt_s[s] != 0) atomicAdd(&p.pos_cnt[row * MAXP + s], cnt_s[s]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
+// E (B x d) -> E^T planes: ET_hi/lo [rows_t = n_slices*128][bpad], zero padded, TF32 split (K-major B operand of GEMM2)
+__global__ void column_mean_kernel(const float* __restrict__ e, int64_t B, int d, float* __restrict__ mu) {
+  // one block per 32 columns; 8 row groups reduced through shared memory (deterministic)
+  __shared__ double part[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (c < d)
+    for (int64_t r = threadIdx.y; r < B; r += 8) acc += static_cast<double>(e[r * d + c]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    double s = 0.0;
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+    mu[c] = static_cast<float>(s / static_cast<double>(B));
+  }
+}
+
+__global__ void transpose_split_kernel(const float* __restrict__ e, const float* __restrict__ mu, int64_t B, int d,
+                                       int rows_t, int64_t bpad, float* __restrict__ et_hi,
+                                       float* __restrict__ et_lo) {
+  __shared__ float tile[32][33];
+  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t j = j0 + r;
+    const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (j < B && c < d) ? e[j * d + c] - mu[c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const int64_t j = j0 + threadIdx.x;
+    if (c < rows_t && j < bpad) {
+      const float v = tile[threadIdx.x][r];
+      const float h = tc::to_tf32(v);
+      et_hi[static_cast<int64_t>(c) * bpad + j] = h;
+      et_lo[static_cast<int64_t>(c) * bpad + j] = tc::to_tf32(v - h);
+    }
+  }
+}
+
+}  // namespace pbt
+
+// ---------------------------------------------------------------------------------------------- host entry
+size_t pair_bwd_tc_ws_bytes(int64_t B, int d) {
+  const size_t dpad = static_cast<size_t>((d + tc::BK - 1) / tc::BK * tc::BK);
+  const size_t n_slices = static_cast<size_t>((d + pbt::DN - 1) / pbt::DN);
+  const size_t bpad = static_cast<size_t>((B + 31) / 32 * 32);
+  return 2 * align_up(static_cast<size_t>(B) * dpad * 4) + align_up(static_cast<size_t>(B) * 4) +
+         2 * align_up(n_slices * pbt::DN * bpad * 4) + align_up(static_cast<size_t>(d) * 4);
+}
+
+// mode 0 = batch-all (pos_* describe lists with capacity 8), mode 1 = contrastive.  gemb is fully overwritten
+// (the caller adds the sparse positive-pair terms of batch-all afterwards).
+int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
+                       float scale_c, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
+                       const float* gloss, float* gemb, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (int rc = check_sm100()) return rc;
+  if (!ws || ws_bytes < pair_bwd_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small");
+  Workspace w(ws, ws_bytes);
+  const int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
+  const int n_slices = (d + pbt::DN - 1) / pbt::DN;
+  const int rows_t = n_slices * pbt::DN;
+  const int64_t bpad = (B + 31) / 32 * 32;
+  float* hi = w.take<float>(static_cast<size_t>(B) * dpad);
+  float* lo = w.take<float>(static_cast<size_t>(B) * dpad);
+  float* norms = w.take<float>(B);
+  float* et_hi = w.take<float>(static_cast<size_t>(rows_t) * bpad);
+  float* et_lo = w.take<float>(static_cast<size_t>(rows_t) * bpad);
+  float* mu = w.take<float>(d);
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small or misaligned");
+  EN_CUDA(tc::launch_split(emb, B, d, d, dpad, hi, lo, norms, st));
+  ++launch_counter();
+  dim3 tb(32, 8), tg(static_cast<unsigned>(bpad / 32), static_cast<unsigned>(rows_t / 32));
+  pbt::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), tb, 0, st>>>(emb, B, d, mu);
+  EN_LAUNCHED("column_mean_kernel");
+  pbt::transpose_split_kernel<<<tg, tb, 0, st>>>(emb, mu, B, d, rows_t, bpad, et_hi, et_lo);
+  EN_LAUNCHED("transpose_split_kernel");
+  CUtensorMap th, tl, teh, tel;
+  if (tc::make_plane_tmap(&th, hi, B, dpad) || tc::make_plane_tmap(&tl, lo, B, dpad) ||
+      tc::make_plane_tmap(&teh, et_hi, rows_t, bpad) || tc::make_plane_tmap(&tel, et_lo, rows_t, bpad))
+    return fail(EN_ERR_DRIVER, "pair backward: cuTensorMapEncodeTiled failed");
+  pbt::Params p;
+  p.emb = emb; p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt;
+  p.stats = stats; p.gloss = gloss; p.mu = mu; p.gemb = gemb; p.B = B; p.d = d;
+  p.tiles = static_cast<int>((B + tc::BM - 1) / tc::BM);
+  p.n_slices = n_slices; p.kblocks = dpad / tc::BK; p.mode = mode; p.squared = squared; p.margin = margin;
+  p.scale_c = scale_c;
+  EN_CUDA(cudaFuncSetAttribute(pbt::pair_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pbt::SMEM_BYTES));
+  const int items = p.tiles * p.n_slices;
+  const int sms = device_sm_count();
+  const int grid = items < sms ? items : sms;
+  prof_begin(st);
+  pbt::pair_bwd_tc_kernel<<<grid, pbt::NUM_THREADS, pbt::SMEM_BYTES, st>>>(th, tl, teh, tel, p);
+  prof_end(st);
+  EN_LAUNCHED("pair_bwd_tc_kernel");
+  return EN_OK;
+}
+
+}  // namespace en

