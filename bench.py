@@ -343,6 +343,54 @@ def main():
         "gpu_launches_per_step": int(launches_per_step), "e2e_gpu_launches_per_step": int(e2e_launches),
     }
 
+    # ------------------------------------------------------------------ the other BASELINE configs (parity-test
+    # cases, timed here for the record; rank-local, not part of `value`)
+    def time_ms(fn, n=10, w=3):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    def fwd_bwd(loss_fn, x):
+        e = x.detach().clone().requires_grad_(True)
+        loss_fn(labels, e).backward()
+        return e.grad
+
+    others = {}
+    if rank == 0:
+        ba = lac.batch_all_triplet_loss(MARGIN, max_positives=PER_CLASS - 1)
+        ca = lac.contrastive_loss_all_pairs()
+        emb7 = (emb * 0.7).contiguous()
+        t_ba = time_ms(lambda: fwd_bwd(ba, emb))
+        t_ca = time_ms(lambda: fwd_bwd(ca, emb7))
+        others["C3_batch_all_loss_grad"] = {"ms": t_ba, "embeddings_per_sec": B / (t_ba * 1e-3)}
+        others["C3_contrastive_all_pairs_loss_grad"] = {"ms": t_ca, "embeddings_per_sec": B / (t_ca * 1e-3)}
+        # C1: reference-semantics in-batch mining, 32 classes x 8 samples, d = 128 (host arrays in, triplets out)
+        from embeddingnet_b200.datagenerators import mine_batch_triplets
+
+        x1, l1 = synth.make_numpy(256, 128, n_classes=32, rows_per_class=8, noise=0.5, relu=True)
+        x1 = x1 / np.sqrt(np.maximum((x1.astype(np.float64) ** 2).sum(1, keepdims=True), 1e-12)).astype(np.float32)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            trip, _ = mine_batch_triplets(x1, l1, margin=MARGIN, mode="semihard")
+        t_c1 = (time.perf_counter() - t0) / 20
+        others["C1_mining_semihard_256x128_host_to_triplets"] = {"ms": t_c1 * 1e3, "triplets": int(len(trip)),
+                                                                 "embeddings_per_sec": 256 / t_c1}
+        # C2-shaped step: B = 128, d = 256 batch-hard loss + grad (launch-latency bound)
+        x2, l2 = synth.make_device(128, 256, n_classes=16, rows_per_class=8, noise=0.5, relu=True, device=dev)
+        x2 = lac.l2_normalize(x2).detach()
+        st2 = BatchHardStep(128, 256, margin=MARGIN)
+        t_c2 = time_ms(lambda: st2.step(x2, l2), n=50)
+        others["C2_batch_hard_loss_grad_128x256"] = {"ms": t_c2, "embeddings_per_sec": 128 / (t_c2 * 1e-3)}
+    line["other_configs"] = others
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu_value, cpu_dt = cpu_triplet_baseline(30, 2)
@@ -419,7 +467,32 @@ def main():
         barrier()
         stream_call_ms = max_over_ranks(s0.elapsed_time(s1) / 5)
         stream_bytes = float(hi - lo) * D * 4
-        # spot check against the oracle on a few queries (device results are what was timed)
+        # C4: offline hard-negative mining over a bank = label-excluded nearest neighbours (1M x 256, 64k anchors)
+        mining = None
+        if args.knn_bank >= 1_000_000:
+            del clf, bank, queries
+            torch.cuda.empty_cache()
+            n4 = 1_000_000
+            lo4, hi4 = BankKNNClassifier.shard_bounds(n4, world, rank)
+            bank4, _ = synth.make_device(hi4 - lo4, 256, row_offset=lo4, n_classes=10_000, noise=0.5, device=dev)
+            ids4 = (torch.arange(n4, dtype=torch.int64, device=dev) % 10_000).to(torch.int32)
+            clf4 = BankKNNClassifier(n_neighbors=1, process_group=group, device=dev)
+            clf4.fit_shard(bank4, ids4, lo4, n4, classes=np.arange(10_000))
+            a_idx = torch.arange(0, n4, n4 // 65536, device=dev)[:65536]
+            anchors, _ = synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev) if world > 1 else (bank4, None)
+            anchors = anchors[a_idx].contiguous()
+            a_lab = ids4[a_idx].contiguous()
+            for _ in range(2):
+                clf4.kneighbors_device(anchors, n_neighbors=1, exclude_labels=a_lab)
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            clf4.kneighbors_device(anchors, n_neighbors=1, exclude_labels=a_lab)
+            m1.record()
+            barrier()
+            m_ms = max_over_ranks(m0.elapsed_time(m1))
+            mining = {"workload": "C4: hardest negative of 65536 anchors over a 1M x 256 bank (label-excluded 1-NN), "
+                                  "%d GPU(s)" % world, "ms": m_ms, "anchors_per_sec": 65536 / (m_ms * 1e-3)}
         knn = {
             "metric": "knn_queries_per_sec_10M_bank", "value": knn_value, "unit": "queries/s", "n_gpus": world,
             "steps": kk, "warmup": kw, "ms_per_step": knn_ms / kk, "scaling": "strong",
@@ -444,6 +517,8 @@ def main():
                                          "kernel": "knn_stream_kernel<8>", "kernel_ms": stream_ms,
                                          "algorithmic_bytes_per_launch": stream_bytes}},
         }
+        if mining is not None:
+            knn["bank_mining"] = mining
         if rank == 0 and world == 1 and not args.skip_cpu:
             qps, sample = cpu_knn_baseline()
             knn["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",

@@ -16,6 +16,27 @@ if what in ("all", "triplet"):
     for _ in range(4):
         st.step(emb, labels)
     torch.cuda.synchronize()
+if what == "knn_full":
+    # one full-size C5 scan (100k queries vs 10M x 512) for the DRAM-traffic metric
+    n, Q = 10_000_000, 100_000
+    bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
+    ids = (torch.arange(n, device=dev) % 100000).to(torch.int32)
+    clf = BankKNNClassifier(5, device=dev).fit_shard(bank, ids, 0, n, classes=np.arange(100000))
+    q, _ = synth.make_device(Q, 512, seed_noise=synth.SEED_QUERY, n_classes=100000, noise=0.5, device=dev)
+    clf.kneighbors_device(q)
+    clf.kneighbors_device(q[:8].contiguous())
+    clf.kneighbors_device(q[:1].contiguous())
+    torch.cuda.synchronize()
+if what == "pairbwd":
+    raw, labels = synth.make_device(4096, 512, n_classes=512, rows_per_class=8, noise=0.5, relu=True, device=dev)
+    emb = lac.l2_normalize(raw).detach()
+    ba = lac.batch_all_triplet_loss(0.5, max_positives=7)
+    ca = lac.contrastive_loss_all_pairs()
+    for fn, x in ((ba, emb), (ca, (emb * 0.7).contiguous())):
+        for _ in range(2):
+            e = x.clone().requires_grad_(True)
+            fn(labels, e).backward()
+    torch.cuda.synchronize()
 if what in ("all", "knn"):
     n, Q = 400_000, 8192
     bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
