@@ -56,6 +56,7 @@ struct Shape {
   int symmetric;    // A == B: only tiles with column tile >= row tile are computed (one tile per work item);
                     // the epilogue must reduce each tile both along rows and along columns
   int num_items;
+  int nt_base;      // first column tile of this launch (bank scans walk the bank in L2-sized chunks, one launch each)
 };
 
 // Work item -> (row tile, column-tile range).  Same arithmetic in all three warp roles.
@@ -179,10 +180,10 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             const bool lo = shape.passes > 1;
             ptx::mbar_arrive_expect_tx(&bars->full[stage], lo ? STAGE_BYTES : 2 * TILE_BYTES);
             ptx::tma_load_2d(&tm_a_hi, &bars->full[stage], st + 0 * TILE_BYTES, kb * BK, tile_m * BM);
-            ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st + 2 * TILE_BYTES, kb * BK, nt * BN);
+            ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st + 2 * TILE_BYTES, kb * BK, (shape.nt_base + nt) * BN);
             if (lo) {
               ptx::tma_load_2d(&tm_a_lo, &bars->full[stage], st + 1 * TILE_BYTES, kb * BK, tile_m * BM);
-              ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + 3 * TILE_BYTES, kb * BK, nt * BN);
+              ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + 3 * TILE_BYTES, kb * BK, (shape.nt_base + nt) * BN);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -266,12 +267,12 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           } else {
             ptx::tmem_ld_wait();
           }
-          Ep::chunk(ep, rs, ctx, row, row_valid, static_cast<int64_t>(nt) * BN + c * 32, dot);
+          Ep::chunk(ep, rs, ctx, row, row_valid, static_cast<int64_t>(shape.nt_base + nt) * BN + c * 32, dot);
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
-        Ep::tile_end(ep, rs, ctx, row, row_valid, nt);
+        Ep::tile_end(ep, rs, ctx, row, row_valid, shape.nt_base + nt);
       }
       Ep::item_end(ep, rs, ctx, row, row_valid, tile_m, split);
     }
@@ -332,6 +333,7 @@ inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes) {
   s.passes = passes;
   s.symmetric = 0;
   s.num_items = s.tiles_m * s.n_splits;
+  s.nt_base = 0;
   return s;
 }
 
