@@ -824,13 +824,24 @@ struct TcOperands {
   CUtensorMap th, tl;
 };
 
-int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStream_t st, TcOperands& o) {
+// `centre`: subtract the column mean before the TF32 split (norms become the centred norms).  Distances do not
+// change; the tensor core's accumulation truncates toward zero, which biases all-positive dot products (post-ReLU
+// embeddings) by ~6e-6 -- enough to flip ~1e-5 of the batch-all hinge decisions against float64.  Centred dot
+// products have mixed signs and the bias averages out (measured: all-pairs contrastive gradient 4e-6 -> 3e-7).
+// Batch-hard does not need it: its finalize kernel re-evaluates the candidates exactly.
+int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStream_t st, TcOperands& o,
+                     bool centre = false) {
   o.dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
   o.hi = w.take<float>(static_cast<size_t>(B) * o.dpad);
   o.lo = w.take<float>(static_cast<size_t>(B) * o.dpad);
   o.norms = w.take<float>(B);
+  float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "workspace too small or misaligned");
-  EN_CUDA(tc::launch_split(emb, B, d, d, o.dpad, o.hi, o.lo, o.norms, st));
+  if (centre) {
+    tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, 8), 0, st>>>(emb, B, d, mu);
+    EN_LAUNCHED("column_mean_kernel");
+  }
+  EN_CUDA(tc::launch_split(emb, B, d, d, o.dpad, o.hi, o.lo, o.norms, st, centre ? mu : nullptr));
   ++launch_counter();
   if (tc::make_plane_tmap(&o.th, o.hi, B, o.dpad) || tc::make_plane_tmap(&o.tl, o.lo, B, o.dpad))
     return fail(EN_ERR_DRIVER, "cuTensorMapEncodeTiled failed");
@@ -839,7 +850,8 @@ int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStrea
 
 size_t operand_bytes(int64_t B, int d) {
   const size_t dpad = static_cast<size_t>((d + tc::BK - 1) / tc::BK * tc::BK);
-  return 2 * align_up(static_cast<size_t>(B) * dpad * 4) + align_up(static_cast<size_t>(B) * 4);
+  return 2 * align_up(static_cast<size_t>(B) * dpad * 4) + align_up(static_cast<size_t>(B) * 4) +
+         align_up(static_cast<size_t>(d) * 4);
 }
 
 int splits_for(int64_t B, int sms) {
@@ -981,7 +993,7 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
   TcOperands o;
-  if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
+  if (int rc = prepare_operands(emb, B, d, w, st, o, true)) return rc;
   PosLists pl = take_pos(w, B, max_positives);
   const int sms = device_sm_count();
   tc::Shape sh = tc::make_shape(B, B, d, splits_for(B, sms), 3);
@@ -1068,7 +1080,7 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
   TcOperands o;
-  if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
+  if (int rc = prepare_operands(emb, B, d, w, st, o, true)) return rc;
   const int sms = device_sm_count();
   tc::Shape sh = tc::make_shape(B, B, d, splits_for(B, sms), 3);
   PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * sh.n_splits * tc::EPI_H);

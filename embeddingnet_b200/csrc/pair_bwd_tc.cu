@@ -79,6 +79,9 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(r);
 }
 
+// kMode is a template parameter so that each instantiation carries only its own coefficient code: the fully
+// unrolled epilogue of both modes together overflowed the instruction cache (ncu: stall_no_instruction 5.4 / issue).
+template <int kMode>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                    const __grid_constant__ CUtensorMap tm_et_hi, const __grid_constant__ CUtensorMap tm_et_lo,
@@ -227,7 +230,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t e_it = 0, item_it = 0;
     const float gl = p.gloss ? p.gloss[0] : 1.f;
-    const float inv_np = p.mode == 0 ? static_cast<float>(1.0 / (p.stats[1] + 1e-16)) : 0.f;
+    const float inv_np = kMode == 0 ? static_cast<float>(1.0 / (p.stats[1] + 1e-16)) : 0.f;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
       const int ti = item % T, slice = item / T;
       const int64_t row = static_cast<int64_t>(ti) * BM + quarter * 32 + lane;
@@ -237,7 +240,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
       float pi[MAXP];
       int cnt_s[MAXP];
       int npi = 0;
-      if (p.mode == 0) {
+      if (kMode == 0) {
         npi = row_ok ? p.pos_n[row] : 0;
 #pragma unroll
         for (int s = 0; s < MAXP; ++s) {
@@ -269,7 +272,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
             __syncwarp();
             wf[lane] = ok ? __ldg(&p.norms[cc]) : 0.f;
             wi[lane] = ok ? __ldg(&p.labels[cc]) : -2;
-            if (p.mode == 0) {
+            if (kMode == 0) {
               const int npk = ok ? p.pos_n[cc] : 0;
 #pragma unroll
               for (int s = 0; s < MAXP; ++s)
@@ -289,7 +292,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
             // sqrt plus an IEEE divide per element -- the epilogue, not the tensor pipe, bounds this kernel
             const float rs = d2 > 0.f ? rsqrtf(d2) : 0.f;
             float cv = 0.f;
-            if (p.mode == 1) {
+            if (kMode == 1) {
               // t'(d2) = 1 (same label) or -max(1 - d, 0) / d = -max(1/d - 1, 0); clamp region d2 < 1e-7 has zero slope
               const float diff = -fmaxf(rs - 1.f, 0.f);
               cv = (ok && d2 >= 1e-7f) ? 4.f * p.scale_c * (wi[j] == la ? 1.f : diff) : 0.f;
@@ -352,7 +355,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc2_empty);
       ptx::named_bar_sync(1, EPI_WARPS * 32);  // rowsum_x may be rewritten by the next item
-      if (p.mode == 0 && slice == 0 && row_ok) {
+      if (kMode == 0 && slice == 0 && row_ok) {
 #pragma unroll
         for (int s = 0; s < MAXP; ++s)
           if (s < npi && cnt_s[s] != 0) atomicAdd(&p.pos_cnt[row * MAXP + s], cnt_s[s]);
@@ -369,22 +372,6 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
 }
 
 // E (B x d) -> E^T planes: ET_hi/lo [rows_t = n_slices*128][bpad], zero padded, TF32 split (K-major B operand of GEMM2)
-__global__ void column_mean_kernel(const float* __restrict__ e, int64_t B, int d, float* __restrict__ mu) {
-  // one block per 32 columns; 8 row groups reduced through shared memory (deterministic)
-  __shared__ double part[8][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double acc = 0.0;
-  if (c < d)
-    for (int64_t r = threadIdx.y; r < B; r += 8) acc += static_cast<double>(e[r * d + c]);
-  part[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < d) {
-    double s = 0.0;
-    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
-    mu[c] = static_cast<float>(s / static_cast<double>(B));
-  }
-}
-
 __global__ void transpose_split_kernel(const float* __restrict__ e, const float* __restrict__ mu, int64_t B, int d,
                                        int rows_t, int64_t bpad, float* __restrict__ et_hi,
                                        float* __restrict__ et_lo) {
@@ -439,11 +426,13 @@ int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d
   float* et_lo = w.take<float>(static_cast<size_t>(rows_t) * bpad);
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small or misaligned");
-  EN_CUDA(tc::launch_split(emb, B, d, d, dpad, hi, lo, norms, st));
-  ++launch_counter();
   dim3 tb(32, 8), tg(static_cast<unsigned>(bpad / 32), static_cast<unsigned>(rows_t / 32));
-  pbt::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), tb, 0, st>>>(emb, B, d, mu);
+  tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), tb, 0, st>>>(emb, B, d, mu);
   EN_LAUNCHED("column_mean_kernel");
+  // GEMM1 also runs on the centred rows (norms are the centred norms): ||a-b|| is unchanged, S loses its
+  // one-sided truncation bias, and with it the hinge-activity flips against the float64 oracle
+  EN_CUDA(tc::launch_split(emb, B, d, d, dpad, hi, lo, norms, st, mu));
+  ++launch_counter();
   pbt::transpose_split_kernel<<<tg, tb, 0, st>>>(emb, mu, B, d, rows_t, bpad, et_hi, et_lo);
   EN_LAUNCHED("transpose_split_kernel");
   CUtensorMap th, tl, teh, tel;
@@ -456,12 +445,16 @@ int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d
   p.tiles = static_cast<int>((B + tc::BM - 1) / tc::BM);
   p.n_slices = n_slices; p.kblocks = dpad / tc::BK; p.mode = mode; p.squared = squared; p.margin = margin;
   p.scale_c = scale_c;
-  EN_CUDA(cudaFuncSetAttribute(pbt::pair_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pbt::SMEM_BYTES));
+  if (mode == 0)
+    EN_CUDA(cudaFuncSetAttribute(pbt::pair_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pbt::SMEM_BYTES));
+  else
+    EN_CUDA(cudaFuncSetAttribute(pbt::pair_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pbt::SMEM_BYTES));
   const int items = p.tiles * p.n_slices;
   const int sms = device_sm_count();
   const int grid = items < sms ? items : sms;
   prof_begin(st);
-  pbt::pair_bwd_tc_kernel<<<grid, pbt::NUM_THREADS, pbt::SMEM_BYTES, st>>>(th, tl, teh, tel, p);
+  if (mode == 0) pbt::pair_bwd_tc_kernel<0><<<grid, pbt::NUM_THREADS, pbt::SMEM_BYTES, st>>>(th, tl, teh, tel, p);
+  else pbt::pair_bwd_tc_kernel<1><<<grid, pbt::NUM_THREADS, pbt::SMEM_BYTES, st>>>(th, tl, teh, tel, p);
   prof_end(st);
   EN_LAUNCHED("pair_bwd_tc_kernel");
   return EN_OK;

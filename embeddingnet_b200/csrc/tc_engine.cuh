@@ -371,8 +371,11 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// `mu` (optional, d floats): subtracted from every row first.  Distances are translation invariant, and centred
+// rows give dot products of mixed sign, which removes the tensor core's one-sided accumulation (truncation) bias.
 static __global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
-                                    float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norms) {
+                                    float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norms,
+                                    const float* __restrict__ mu) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -382,6 +385,7 @@ static __global__ void split_planes_kernel(const float* __restrict__ x, int64_t 
   double acc = 0.0;
   for (int c = lane; c < dpad; c += 32) {
     float v = c < d ? xr[c] : 0.0f;
+    if (mu != nullptr && c < d) v -= __ldg(&mu[c]);
     float h = to_tf32(v);
     float l = to_tf32(v - h);
     hr[c] = h;
@@ -393,12 +397,30 @@ static __global__ void split_planes_kernel(const float* __restrict__ x, int64_t 
   if (lane == 0 && norms) norms[row] = static_cast<float>(acc);
 }
 
+// Column means of x (B x d), float64 accumulation in a fixed order (deterministic): one block of (32, 8) threads per
+// 32 columns.  Used to centre the operands (see split_planes_kernel).
+static __global__ void column_mean_kernel(const float* __restrict__ e, int64_t B, int d, float* __restrict__ mu) {
+  // one block per 32 columns; 8 row groups reduced through shared memory (deterministic)
+  __shared__ double part[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (c < d)
+    for (int64_t r = threadIdx.y; r < B; r += 8) acc += static_cast<double>(e[r * d + c]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    double s = 0.0;
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+    mu[c] = static_cast<float>(s / static_cast<double>(B));
+  }
+}
+
 inline cudaError_t launch_split(const float* x, int64_t rows, int d, int64_t ldx, int dpad, float* hi, float* lo,
-                                float* norms, cudaStream_t stream) {
+                                float* norms, cudaStream_t stream, const float* mu = nullptr) {
   if (rows == 0) return cudaSuccess;
   const int threads = 256;
   const int64_t blocks = (rows * 32 + threads - 1) / threads;
-  split_planes_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, rows, d, ldx, dpad, hi, lo, norms);
+  split_planes_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, rows, d, ldx, dpad, hi, lo, norms, mu);
   return cudaGetLastError();
 }
 

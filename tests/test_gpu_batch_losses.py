@@ -26,17 +26,49 @@ def make_batch(n_classes, per, d, normalize=True, shuffle=False, noise=0.5):
     return x, lab.astype(np.int64)
 
 
-def assert_grad_close_up_to_hinge_flips(got, want, median_tol=1e-5):
-    """Batch-all gradients: a triplet whose hinge argument is within ~1e-6 of zero can be active in float32 and
-    inactive in float64 (or vice versa); each such flip moves the few rows involved by ~1/num_positive.  So: almost
-    every row must agree to 1e-4 (median far tighter), and the whole gradient to 1e-3."""
-    got = got.astype(np.float64)
-    want = want.astype(np.float64)
+def hinge_boundary_rows(lab, x, margin, squared, tau_rel=1e-6):
+    """Rows that take part in a triplet whose hinge argument D_ap + m - D_an lies within float32 rounding (tau) of
+    the activity threshold, per the float64 oracle; returns (touched mask, per-row count of such triplets, #active).
+    A float32 implementation -- the reference's TF graph included -- may legitimately decide those triplets the
+    other way; each such flip moves the rows a, p, n by ~1/#active (the hinge is non-smooth there)."""
+    D = O._dist_matrix64(np.asarray(x, np.float64), squared)
+    B = len(lab)
+    tau = tau_rel * max(1.0, float(D.max()))
+    near = np.zeros(B, np.int64)
+    n_active = 0
+    idx = np.arange(B)
+    for i in range(B):
+        same = lab == lab[i]
+        p = np.where(same & (idx != i))[0]
+        n = np.where(~same)[0]
+        if p.size == 0 or n.size == 0:
+            continue
+        T = D[i, p][:, None] - D[i, n][None, :] + margin
+        n_active += int((T > 1e-16).sum())
+        pi, ni = np.where(np.abs(T - 1e-16) < tau)
+        if pi.size:
+            near[i] += pi.size
+            np.add.at(near, p[pi], 1)
+            np.add.at(near, n[ni], 1)
+    return near > 0, near, n_active
+
+
+def assert_grad_close_up_to_hinge_flips(got, want, lab, x, margin, squared, tol=1e-4):
+    """Batch-all gradients vs the float64 oracle: every row agrees to `tol` (relative to the mean row norm) unless
+    it takes part in a hinge-boundary triplet, in which case it may differ by at most its boundary-triplet count
+    times the size of one flip; such rows must stay rare; the whole gradient agrees to north_star's 1e-4 plus
+    the flip allowance (the full-size test additionally asserts the plain 1e-4)."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    touched, near, n_active = hinge_boundary_rows(lab, x, margin, squared)
     scale = np.linalg.norm(want, axis=1).mean() + 1e-30
     rows = np.linalg.norm(got - want, axis=1) / scale
-    assert np.median(rows) < median_tol, np.median(rows)
-    assert np.mean(rows < 1e-4) >= 0.97, np.mean(rows < 1e-4)
-    assert np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30) < 1e-3
+    assert rows[~touched].max(initial=0.0) < tol, (rows[~touched].max(), int(np.argmax(np.where(touched, 0, rows))))
+    # one flipped triplet moves a row by (a sum of two unit-ish vectors) / #active: bound it by 4 / #active
+    flip = 4.0 / max(n_active, 1) / scale
+    assert (rows[touched] <= tol + near[touched] * flip).all()
+    assert (rows >= tol).mean() < 0.08, (rows >= tol).mean()
+    assert np.linalg.norm(got - want) <= tol * np.linalg.norm(want) + flip * scale * np.sqrt((near ** 2).sum())
 
 
 def rel_err(a, b):
@@ -201,7 +233,7 @@ def test_batch_all_fwd_bwd(ncls, per, d, norm, shuf, squared):
     if len(lab) <= 400:
         _, g = O.batch_all_grad(lab, x, margin, squared)
         if np.linalg.norm(g) > 0:
-            assert_grad_close_up_to_hinge_flips(e.grad.cpu().numpy(), 0.6 * g)
+            assert_grad_close_up_to_hinge_flips(e.grad.cpu().numpy(), 0.6 * g, lab, x, margin, squared)
         else:
             assert np.abs(e.grad.cpu().numpy()).max() == 0
 
@@ -217,7 +249,12 @@ def test_batch_all_tensor_core_backward_matches_cuda_core_backward():
             e = torch.tensor(x, device="cuda", requires_grad=True)
             lac.batch_all_triplet_loss(0.5, squared=squared, max_positives=mp)(lab, e).backward()
             grads.append(e.grad.cpu().numpy())
-        assert rel_err(grads[0], grads[1]) < 2e-5
+        # the two kernels round the distances differently, so they may decide a hinge-boundary triplet differently
+        touched, _, _ = hinge_boundary_rows(lab, x, 0.5, squared)
+        assert rel_err(grads[0][~touched], grads[1][~touched]) < 2e-5
+        ga = O.batch_all_grad_analytic(lab, x, 0.5, squared)
+        for g in grads:
+            assert_grad_close_up_to_hinge_flips(g, ga, lab, x, 0.5, squared)
 
 
 def test_batch_all_rejects_too_small_max_positives():
@@ -258,8 +295,8 @@ def test_batch_all_and_contrastive_full_size():
     assert np.isfinite(g).all() and np.abs(g).max() > 0
     ga = O.batch_all_grad_analytic(lab, x, 0.5, False)
     # 1.17e8 valid triplets: a few hundred sit within float32 rounding of the hinge boundary
-    assert_grad_close_up_to_hinge_flips(g, ga, median_tol=1e-4)
-    assert rel_err(g, ga) < 3e-4
+    assert_grad_close_up_to_hinge_flips(g, ga, lab, x, 0.5, False)
+    assert rel_err(g, ga) < 1e-4
     x7 = (x * 0.7).astype(np.float32)
     refc = O.contrastive_allpairs(lab, x7)
     e7 = torch.tensor(x7, device="cuda", requires_grad=True)
