@@ -290,16 +290,19 @@ def main():
     gemm_ms_avg = sum(gemm_ms[2:]) / len(gemm_ms[2:])
     flops = 2.0 * B * B * D
     achieved = flops / (gemm_ms_avg * 1e-3) / 1e12
-    peak = peaks["bf16"] / 2.0 / 3.0
+    # the batch-hard GEMM runs on split-BF16 operands (3 kind::f16 MMAs per k-step): its own tensor roofline is
+    # dense bf16 / 3; north_star's "TF32-emulated roofline" (dense bf16 / 2 / 3) is reported beside it
+    peak = peaks["bf16"] / 3.0
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": ncu_traffic("batch_hard_gemm_dram_bytes_per_launch"),
-        "kernel": "dist_gemm_kernel<EpBatchHard> (tcgen05 kind::tf32, 3 MMAs per k-step)",
+        "kernel": "dist_gemm_kernel<EpBatchHard> (tcgen05 kind::f16 on split-BF16 planes, 3 MMAs per k-step)",
         "kernel_ms": gemm_ms_avg, "share_of_step": gemm_ms_avg / ms_per_step,
         "algorithmic_flops_per_launch": flops,
-        "peak_note": "%s bf16 dense %.1f TFLOP/s (burst) / 2 (TF32 rate) / 3 (hi*hi + hi*lo + lo*hi passes)" % (
+        "peak_note": "%s bf16 dense %.1f TFLOP/s (burst) / 3 (hi*hi + hi*lo + lo*hi passes)" % (
             peaks["source"], peaks["bf16"]),
         "frac_of_bf16_peak": achieved / peaks["bf16"],
+        "frac_of_tf32x3_roofline": achieved / (peaks["bf16"] / 6.0),
     }
 
     # end to end through the reference-shaped public API, host buffers in and out
@@ -421,6 +424,7 @@ def main():
             kev[i][1].record()
         barrier()
         knn_launches = launch_count()
+        knn_uncertified = clf.last_uncertified
         knn_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev))
         knn_value = Q * kk / (knn_ms * 1e-3)
         lib.en_prof_enable(1)
@@ -431,7 +435,7 @@ def main():
         scan_ms = max_over_ranks(ms.value)
         kflops = 2.0 * Q * (hi - lo) * D
         kach = kflops / (scan_ms * 1e-3) / 1e12
-        kpeak = peaks["bf16_sustained"] / 6.0
+        kpeak = peaks["bf16_sustained"] / 3.0  # split-BF16 scan: 3 kind::f16 MMAs per k-step
         # end to end: pinned host queries in, (dist, ids) out
         q_h = queries.cpu().pin_memory()
         out_d = torch.empty((Q, KNN_K), dtype=torch.float32).pin_memory()
@@ -509,14 +513,18 @@ def main():
             "config": {"workload": "C5: %d queries vs %d x %d fp32 bank, k=%d, bank sharded row-wise over %d GPU(s), "
                        "NCCL all-gather + merge; inputs >> L2 (no flush needed)" % (Q, n_total, D, KNN_K, world)},
             "roofline": {"bound": "tensor", "achieved": kach, "peak": kpeak, "unit": "TFLOP/s", "frac": kach / kpeak,
-                         "traffic": ncu_traffic("knn_scan_dram_bytes_per_launch"), "kernel": "dist_gemm_kernel<EpTopK<8>>",
+                         "traffic": ncu_traffic("knn_scan_dram_bytes_per_launch"), "kernel": "dist_gemm_kernel<EpTopK<8>> (split-BF16 planes)",
                          "kernel_ms": scan_ms, "share_of_step": scan_ms / (knn_ms / kk),
                          "algorithmic_flops_per_launch": kflops,
-                         "peak_note": "%s bf16 dense %.1f TFLOP/s (sustained) / 2 / 3, per GPU" % (
-                             peaks["source"], peaks["bf16_sustained"])},
+                         "peak_note": "%s bf16 dense %.1f TFLOP/s (sustained) / 3, per GPU" % (
+                             peaks["source"], peaks["bf16_sustained"]),
+                         "frac_of_tf32x3_roofline": kach / (peaks["bf16_sustained"] / 6.0)},
             "e2e": {"value": Q / knn_e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
                     "d2h_bytes_per_step": Q * KNN_K * 12, "api": "BankKNNClassifier.kneighbors (pinned host queries)"},
             "gpu_launches": int(knn_launches),
+            "certificate": {"uncertified_queries_this_rank": int(knn_uncertified), "of": Q,
+                            "note": "queries whose exactness proof failed are redone by float64 brute force "
+                                    "inside the timed call"},
             "stream_scan": stream[1], "stream_scan_q8": stream[8],
         }
         if mining is not None:

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libembeddingnet_b200.so")
 
 EN_MODE_SEMIHARD, EN_MODE_HARDEST, EN_MODE_RANDOM_HARD = 0, 1, 2
-EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q = 3, 29, 8
+EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q = 3, 29, 8, 64
+EN_PREC_TF32X3, EN_PREC_BF16X3 = 0, 1
 
 P = c_void_p  # every device pointer / stream crosses the boundary as an opaque address
 
@@ -52,12 +53,16 @@ SIGNATURES = {
     "en_ws_bytes_contrastive_allpairs": (c_size_t, [c_int64, c_int]),
     "en_contrastive_allpairs_fwd": (c_int, [P, P, c_int64, c_int, P, P, c_size_t, P]),
     "en_contrastive_allpairs_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, c_size_t, P]),
-    "en_bank_dpad": (c_int, [c_int]),
-    "en_bank_prepare": (c_int, [P, c_int64, c_int, P, P, P, P]),
+    "en_bank_dpad": (c_int, [c_int, c_int]),
+    "en_bank_plane_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "en_bank_prepare": (c_int, [P, c_int64, c_int, c_int, P, P, P, P]),
     "en_ws_bytes_knn": (c_size_t, [c_int64, c_int64, c_int, c_int]),
-    "en_knn_shard_topk": (c_int, [P, c_int64, c_int, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P, P, c_size_t, P]),
+    "en_knn_shard_topk": (c_int, [P, c_int64, c_int, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, P, P, P,
+                                  c_size_t, P]),
+    "en_ws_bytes_knn_exact": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "en_knn_exact_topk": (c_int, [P, c_int64, c_int, P, c_int64, c_int64, c_int, P, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_knn_stream": (c_size_t, [c_int64, c_int64, c_int, c_int]),
-    "en_knn_stream_topk": (c_int, [P, c_int64, c_int, P, P, c_int64, c_int64, c_int, P, P, P, c_size_t, P]),
+    "en_knn_stream_topk": (c_int, [P, c_int64, c_int, P, P, c_int64, c_int64, c_int, P, P, P, P, c_size_t, P]),
     "en_knn_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
     "en_knn_finalize_dist": (c_int, [P, c_int64, P, P]),
     "en_knn_vote": (c_int, [P, c_int64, c_int, P, c_int64, P, P]),

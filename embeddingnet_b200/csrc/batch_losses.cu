@@ -8,7 +8,7 @@
 // Contrastive keeps losses_and_accuracies.py:4-11 (margin 1, label 1 = same) with the Siamese head's distance
 // clamp from embedding_net/models.py:225.
 //
-// Numerics: the tensor-core pass (3xTF32) only *selects* (arg-max positive, arg-min negative) or feeds sums whose
+// Numerics: the tensor-core pass (3xTF32; split-BF16 for batch-hard) only *selects* (arg-max positive, arg-min negative) or feeds sums whose
 // terms are O(1); every distance that reaches a loss value or a gradient of the batch-hard path is re-evaluated
 // exactly (float64 sum (a-b)^2) for the one or two candidates per anchor that matter.
 #include "common.cuh"
@@ -199,12 +199,12 @@ struct BhPick {
 
 template <bool kMax>
 __device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict__ emb, int d, float na, float nb,
-                                            int64_t row, float best, float val, int idx, int lane) {
-  // error band of the 3xTF32 dot product: a few 1e-6 |a||b| <= 1e-5 (|a|^2 + |b|^2) / 2; the proxy error is twice
-  // that, and both the best and the contender carry it
+                                            int64_t row, float best, float val, int idx, int lane, float band_c) {
+  // error band of the split-BF16 dot product (band_c, see bh_band()) times |a||b| <= (|a|^2 + |b|^2) / 2; the proxy
+  // error is twice the dot error, and both the best and the contender carry it
   bool contender = false;
   if (idx >= 0) {
-    const float band = 2.0e-5f * (na + nb) + 1e-30f;
+    const float band = band_c * (na + nb) + 1e-30f;
     contender = kMax ? (val >= best - band) : (val <= best + band);
   }
   unsigned m = __ballot_sync(0xffffffffu, contender);
@@ -242,13 +242,46 @@ __device__ __noinline__ void red_axpy_diff(float* __restrict__ gemb, const float
   }
 }
 
+// Deterministic mean over all anchors: per-block partials, the last block to finish adds them in a fixed-shape
+// tree (the result does not depend on which block finishes last).  Called by all 256 threads of every block.
+__device__ __forceinline__ void block_mean(double hinge, double* sh, double* __restrict__ partial,
+                                           unsigned* __restrict__ counter, float* __restrict__ loss, int64_t B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ bool is_last;
+  if (lane == 0) sh[warp] = hinge;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) tot += __ldcg(&partial[b]);
+    tot = warp_sum(tot);
+    __syncthreads();
+    if (lane == 0) sh[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += sh[w];
+      loss[0] = static_cast<float>(s / static_cast<double>(B));
+      *counter = 0;  // re-armed for the next call on this workspace
+    }
+  }
+}
+
 // kGrad: also accumulate d loss / d emb into a ZEROED gemb (fused loss + gradient: the rows of the selected
 // positive / negative are already hot from the exact re-evaluation).
 template <bool kGrad>
 __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                            const float* __restrict__ norms, const BhCand* __restrict__ cand,
                                            int64_t B, int d, int tiles_n, float margin, int squared, int soft,
-                                           int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                           float band_c, int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
                                            float* __restrict__ hp_out, float* __restrict__ hn_out,
                                            float* __restrict__ coef, double* __restrict__ partial,
                                            unsigned* __restrict__ counter, float* __restrict__ loss,
@@ -294,10 +327,10 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
       const float nb2 = ix.z >= 0 ? __ldg(&norms[ix.z]) : 0.f;
       const float nb3 = ix.w >= 0 ? __ldg(&norms[ix.w]) : 0.f;
-      bh_consider<true>(pos, emb, d, na, nb0, row, bp, v.x, ix.x, lane);
-      bh_consider<true>(pos, emb, d, na, nb1, row, bp, v.y, ix.y, lane);
-      bh_consider<false>(neg, emb, d, na, nb2, row, bn, v.z, ix.z, lane);
-      bh_consider<false>(neg, emb, d, na, nb3, row, bn, v.w, ix.w, lane);
+      bh_consider<true>(pos, emb, d, na, nb0, row, bp, v.x, ix.x, lane, band_c);
+      bh_consider<true>(pos, emb, d, na, nb1, row, bp, v.y, ix.y, lane, band_c);
+      bh_consider<false>(neg, emb, d, na, nb2, row, bn, v.z, ix.z, lane, band_c);
+      bh_consider<false>(neg, emb, d, na, nb3, row, bn, v.w, ix.w, lane, band_c);
     }
     if (neg.idx < 0) {
       // No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row
@@ -345,33 +378,187 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       }
     }
   }
-  // deterministic mean: per-block partials, the last block to finish adds them in index order
-  __shared__ bool is_last;
-  if (lane == 0) sh[warp] = hinge;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += sh[w];
-    partial[blockIdx.x] = s;
-    __threadfence();
-    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    // fixed-shape tree over the block partials: the result does not depend on which block finishes last
-    double tot = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) tot += __ldcg(&partial[b]);
-    tot = warp_sum(tot);
-    if (lane == 0) sh[warp] = tot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += sh[w];
-      loss[0] = static_cast<float>(s / static_cast<double>(B));
-      *counter = 0;  // re-armed for the next call on this workspace
+  block_mean(hinge, sh, partial, counter, loss, B);
+}
+
+// ---- fast finalize: d = 128 * DV, at most 128 candidate records per anchor (B <= 4096) ----------------------
+// The generic kernel above is a chain of dependent round trips per warp (records, records again, norms, rows for
+// each exact distance, rows again for each gradient term; ncu round 1: 8.6 long-scoreboard stalls per issue, 31 us
+// at B = 4096 with one wave of warps).  Here every stage is ONE batch of independent loads: all records into
+// registers, the 16 candidate norms, then the anchor / positive / negative rows (kept in registers and reused for
+// the two exact distances AND the gradient).  Anything unusual -- several contenders inside the error band, no
+// negative at all -- takes the generic per-candidate path on the same registers.
+template <bool kGrad, int DV>
+__global__ void __launch_bounds__(256)
+batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B,
+                                int tiles_n, float margin, int squared, int soft, float band_c,
+                                int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                float* __restrict__ hp_out, float* __restrict__ hn_out, float* __restrict__ coef,
+                                double* __restrict__ partial, unsigned* __restrict__ counter,
+                                float* __restrict__ loss, const float* __restrict__ gloss,
+                                float* __restrict__ gemb) {
+  __shared__ double sh[8];
+  constexpr int d = 128 * DV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  double hinge = 0.0;
+  if (row < B) {
+    const int n_cand = tiles_n * BH_SLOTS;  // <= 128
+    const int my_tile = static_cast<int>(row / tc::BM);
+    const BhCand* mine = cand + row * n_cand;
+    // the anchor's own row is needed whatever happens: issue it with the records
+    const float4* arow = reinterpret_cast<const float4*>(emb + row * d) + lane;
+    float4 a[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) a[i] = arow[32 * i];
+    const float na = norms[row];
+    float4 v[4];
+    int4 ix[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = lane + 32 * u;
+      v[u] = make_float4(-kBig, -kBig, kBig, kBig);
+      ix[u] = make_int4(-1, -1, -1, -1);
+      if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) {  // slots 2,3: column view, tiles left of the anchor's
+        v[u] = __ldcg(reinterpret_cast<const float4*>(mine + t));
+        ix[u] = __ldcg(reinterpret_cast<const int4*>(mine + t) + 1);
+      }
+    }
+    float bp = fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x));  // p1 >= p2, n1 <= n2 inside a record
+    float bn = fminf(fminf(v[0].z, v[1].z), fminf(v[2].z, v[3].z));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+      bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+    }
+    float nb[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      nb[u][0] = ix[u].x >= 0 ? __ldg(&norms[ix[u].x]) : 0.f;
+      nb[u][1] = ix[u].y >= 0 ? __ldg(&norms[ix[u].y]) : 0.f;
+      nb[u][2] = ix[u].z >= 0 ? __ldg(&norms[ix[u].z]) : 0.f;
+      nb[u][3] = ix[u].w >= 0 ? __ldg(&norms[ix[u].w]) : 0.f;
+    }
+    // contenders inside the error band of the best proxy
+    int pc = 0, nc = 0, pi = -1, ni = -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (ix[u].x >= 0 && v[u].x >= bp - (band_c * (na + nb[u][0]) + 1e-30f)) { ++pc; pi = ix[u].x; }
+      if (ix[u].y >= 0 && v[u].y >= bp - (band_c * (na + nb[u][1]) + 1e-30f)) { ++pc; pi = ix[u].y; }
+      if (ix[u].z >= 0 && v[u].z <= bn + (band_c * (na + nb[u][2]) + 1e-30f)) { ++nc; ni = ix[u].z; }
+      if (ix[u].w >= 0 && v[u].w <= bn + (band_c * (na + nb[u][3]) + 1e-30f)) { ++nc; ni = ix[u].w; }
+    }
+    const int tp = __reduce_add_sync(0xffffffffu, pc), tn = __reduce_add_sync(0xffffffffu, nc);
+    BhPick pos{-1.0, -1}, neg{1e300, -1};
+    float4 pr[DV], nr[DV];
+    bool rows_cached = false;
+    if (tp <= 1 && tn == 1) {
+      // the usual case: one candidate each (tp == 0: the anchor is alone in its class)
+      const int p_idx = tp ? __shfl_sync(0xffffffffu, pi, __ffs(__ballot_sync(0xffffffffu, pc > 0)) - 1) : -1;
+      const int n_idx = __shfl_sync(0xffffffffu, ni, __ffs(__ballot_sync(0xffffffffu, nc > 0)) - 1);
+      const float4* prow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(p_idx >= 0 ? p_idx : row) * d) + lane;
+      const float4* nrow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(n_idx) * d) + lane;
+#pragma unroll
+      for (int i = 0; i < DV; ++i) pr[i] = prow[32 * i];
+#pragma unroll
+      for (int i = 0; i < DV; ++i) nr[i] = nrow[32 * i];
+      double dp = 0.0, dn = 0.0;
+#pragma unroll
+      for (int i = 0; i < DV; ++i) {
+        // same element order as exact_d2(): c = lane * 4 + 128 * i + {0, 1, 2, 3}
+        double t;
+        t = static_cast<double>(a[i].x) - static_cast<double>(pr[i].x); dp = fma(t, t, dp);
+        t = static_cast<double>(a[i].y) - static_cast<double>(pr[i].y); dp = fma(t, t, dp);
+        t = static_cast<double>(a[i].z) - static_cast<double>(pr[i].z); dp = fma(t, t, dp);
+        t = static_cast<double>(a[i].w) - static_cast<double>(pr[i].w); dp = fma(t, t, dp);
+        t = static_cast<double>(a[i].x) - static_cast<double>(nr[i].x); dn = fma(t, t, dn);
+        t = static_cast<double>(a[i].y) - static_cast<double>(nr[i].y); dn = fma(t, t, dn);
+        t = static_cast<double>(a[i].z) - static_cast<double>(nr[i].z); dn = fma(t, t, dn);
+        t = static_cast<double>(a[i].w) - static_cast<double>(nr[i].w); dn = fma(t, t, dn);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dp += __shfl_xor_sync(0xffffffffu, dp, o);
+        dn += __shfl_xor_sync(0xffffffffu, dn, o);
+      }
+      if (p_idx >= 0) pos = BhPick{dp, p_idx};
+      neg = BhPick{dn, n_idx};
+      rows_cached = true;
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        bh_consider<true>(pos, emb, d, na, nb[u][0], row, bp, v[u].x, ix[u].x, lane, band_c);
+        bh_consider<true>(pos, emb, d, na, nb[u][1], row, bp, v[u].y, ix[u].y, lane, band_c);
+        bh_consider<false>(neg, emb, d, na, nb[u][2], row, bn, v[u].z, ix[u].z, lane, band_c);
+        bh_consider<false>(neg, emb, d, na, nb[u][3], row, bn, v[u].w, ix[u].w, lane, band_c);
+      }
+      if (neg.idx < 0) {  // no other-label row at all: Moindrot's degenerate row maximum (see the generic kernel)
+        BhPick rmx{-1.0, -1};
+        for (int64_t j = 0; j < B; ++j) {
+          if (j == row) continue;
+          const double d2 = exact_d2(emb, d, row, j, lane);
+          if (rmx.idx < 0 || d2 > rmx.d2) { rmx.d2 = d2; rmx.idx = static_cast<int>(j); }
+        }
+        neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
+      }
+    }
+    const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
+    const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
+    const double z = hp - hn;
+    double g;
+    if (soft) {
+      hinge = z > 0 ? z + log1p(exp(-z)) : log1p(exp(z));
+      g = 1.0 / (1.0 + exp(-z));
+    } else {
+      hinge = fmax(z + static_cast<double>(margin), 0.0);
+      g = (z + static_cast<double>(margin)) >= 0.0 ? 1.0 : 0.0;
+    }
+    if (lane == 0) {
+      hp_idx[row] = pos.idx;
+      hn_idx[row] = neg.idx;
+      hp_out[row] = static_cast<float>(hp);
+      hn_out[row] = static_cast<float>(hn);
+      coef[row] = static_cast<float>(g / static_cast<double>(B));
+    }
+    if (kGrad) {
+      const float gg = static_cast<float>(g / static_cast<double>(B)) * (gloss ? gloss[0] : 1.0f);
+      if (gg != 0.f) {
+        const float hpf = static_cast<float>(hp), hnf = static_cast<float>(hn);
+        const float sp = pos.idx >= 0 ? (squared ? 2.f * gg : (hpf > 0.f ? gg / hpf : 0.f)) : 0.f;
+        const float sn = neg.idx >= 0 ? (squared ? 2.f * gg : (hnf > 0.f ? gg / hnf : 0.f)) : 0.f;
+        if (rows_cached && (reinterpret_cast<uintptr_t>(gemb) & 15) == 0) {
+          // same products and the same four atomic adds per element as red_axpy_diff(), from registers
+          float* ga = gemb + row * d + 4 * lane;
+          float* gp = gemb + static_cast<int64_t>(pos.idx >= 0 ? pos.idx : row) * d + 4 * lane;
+          float* gn = gemb + static_cast<int64_t>(neg.idx) * d + 4 * lane;
+#pragma unroll
+          for (int i = 0; i < DV; ++i) {
+            if (sp != 0.f) {
+              const float x = a[i].x - pr[i].x, y = a[i].y - pr[i].y, zz = a[i].z - pr[i].z, w = a[i].w - pr[i].w;
+              red_add_v4(ga + 128 * i, sp * x, sp * y, sp * zz, sp * w);
+              red_add_v4(gp + 128 * i, -sp * x, -sp * y, -sp * zz, -sp * w);
+            }
+            if (sn != 0.f) {
+              const float x = a[i].x - nr[i].x, y = a[i].y - nr[i].y, zz = a[i].z - nr[i].z, w = a[i].w - nr[i].w;
+              red_add_v4(ga + 128 * i, -sn * x, -sn * y, -sn * zz, -sn * w);
+              red_add_v4(gn + 128 * i, sn * x, sn * y, sn * zz, sn * w);
+            }
+          }
+        } else {
+          if (sp != 0.f) {
+            red_axpy_diff(gemb, emb, d, row, row, pos.idx, sp, lane);
+            red_axpy_diff(gemb, emb, d, pos.idx, row, pos.idx, -sp, lane);
+          }
+          if (sn != 0.f) {
+            red_axpy_diff(gemb, emb, d, row, row, neg.idx, -sn, lane);
+            red_axpy_diff(gemb, emb, d, neg.idx, row, neg.idx, sn, lane);
+          }
+        }
+      }
     }
   }
+  block_mean(hinge, sh, partial, counter, loss, B);
 }
 
 // Backward, stage 1: the anchor's own row, overwritten (no zero-fill pass needed).
@@ -829,17 +1016,27 @@ struct TcOperands {
 // embeddings) by ~6e-6 -- enough to flip ~1e-5 of the batch-all hinge decisions against float64.  Centred dot
 // products have mixed signs and the bias averages out (measured: all-pairs contrastive gradient 4e-6 -> 3e-7).
 // Batch-hard does not need it: its finalize kernel re-evaluates the candidates exactly.
+// `bf16`: BF16 planes instead (selection-only paths; they fit in the same buffers).
 int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStream_t st, TcOperands& o,
-                     bool centre = false) {
-  o.dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
-  o.hi = w.take<float>(static_cast<size_t>(B) * o.dpad);
-  o.lo = w.take<float>(static_cast<size_t>(B) * o.dpad);
+                     bool centre = false, bool bf16 = false, float* zero_rows = nullptr,
+                     unsigned* zero_word = nullptr) {
+  o.dpad = tc::dpad_for(d, bf16);
+  const size_t dpad32 = static_cast<size_t>(tc::dpad_for(d, 0));
+  o.hi = w.take<float>(static_cast<size_t>(B) * dpad32);
+  o.lo = w.take<float>(static_cast<size_t>(B) * dpad32);
   o.norms = w.take<float>(B);
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "workspace too small or misaligned");
   if (centre) {
     tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, 8), 0, st>>>(emb, B, d, mu);
     EN_LAUNCHED("column_mean_kernel");
+  }
+  if (bf16) {
+    EN_CUDA(tc::launch_split_bf16(emb, B, d, d, o.dpad, o.hi, o.lo, o.norms, st, zero_rows, zero_word));
+    ++launch_counter();
+    if (tc::make_plane_tmap_bf16(&o.th, o.hi, B, o.dpad) || tc::make_plane_tmap_bf16(&o.tl, o.lo, B, o.dpad))
+      return fail(EN_ERR_DRIVER, "cuTensorMapEncodeTiled failed");
+    return EN_OK;
   }
   EN_CUDA(tc::launch_split(emb, B, d, d, o.dpad, o.hi, o.lo, o.norms, st, centre ? mu : nullptr));
   ++launch_counter();
@@ -892,29 +1089,52 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
   TcOperands o;
-  if (int rc = prepare_operands(emb, B, d, w, st, o)) return rc;
+  // The GEMM only SELECTS (top-2 candidates per anchor and tile slot); the finalize kernel re-evaluates everything
+  // inside the error band exactly.  Split-BF16 operands run the tensor pipe at twice the TF32 rate.
   const int tiles_n = static_cast<int>((B + tc::BN - 1) / tc::BN);
   BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * BH_SLOTS);
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
   double* partial = w.take<double>(blocks);
   unsigned* counter = w.take<unsigned>(1);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "%s: workspace too small or misaligned", who);
-  EN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-  if (gemb) EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * sizeof(float), st));
-  tc::Shape sh = tc::make_shape_symmetric(B, d, 3);  // upper-triangular tiles, one per work item
+  // the operand split also zeroes the gradient buffer and the finalize counter (no memset nodes in the step)
+  if (int rc = prepare_operands(emb, B, d, w, st, o, false, true, gemb, counter)) return rc;
+  // |dot~ - dot| <= c |a||b| with c = 3 * 2^-16 (dropped lo*lo and residual products of the BF16 split) +
+  // 2^-22 (d/16 + 1) (accumulator truncation): 5.4e-5 at d = 512 (measured maximum: 4e-6).  Proxy = |b|^2 - 2 dot,
+  // |a||b| <= (|a|^2 + |b|^2) / 2, best and contender both off by it: band = 2 c (|a|^2 + |b|^2).
+  const float band_c = 2.0f * (3.0f / 65536.0f + (o.dpad / 16 + 1) / 4194304.0f);
+  tc::Shape sh = tc::make_shape_symmetric(B, d, 3, 1);  // upper-triangular tiles, one per work item; BF16 planes
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
   prof_begin(st);
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
   prof_end(st);
   ++launch_counter();
-  if (gemb)
+  const bool fast = d % 128 == 0 && d <= 512 && tiles_n * BH_SLOTS <= 128 &&
+                    (reinterpret_cast<uintptr_t>(emb) & 15) == 0;
+#define EN_BH_FAST(G, DV)                                                                                          \
+  batch_hard_finalize_fast_kernel<G, DV><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, tiles_n, margin,   \
+                                                                 squared, soft, band_c, hp_idx, hn_idx, hp, hn,    \
+                                                                 coef, partial, counter, loss, G ? gloss : nullptr, \
+                                                                 G ? gemb : nullptr)
+  if (fast && gemb) {
+    if (d == 128) EN_BH_FAST(true, 1);
+    else if (d == 256) EN_BH_FAST(true, 2);
+    else if (d == 384) EN_BH_FAST(true, 3);
+    else EN_BH_FAST(true, 4);
+  } else if (fast) {
+    if (d == 128) EN_BH_FAST(false, 1);
+    else if (d == 256) EN_BH_FAST(false, 2);
+    else if (d == 384) EN_BH_FAST(false, 3);
+    else EN_BH_FAST(false, 4);
+  } else if (gemb)
     batch_hard_finalize_kernel<true><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
-                                                             squared, soft, hp_idx, hn_idx, hp, hn, coef, partial,
+                                                             squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial,
                                                              counter, loss, gloss, gemb);
   else
     batch_hard_finalize_kernel<false><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
-                                                              squared, soft, hp_idx, hn_idx, hp, hn, coef, partial,
+                                                              squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial,
                                                               counter, loss, nullptr, nullptr);
+#undef EN_BH_FAST
   EN_LAUNCHED("batch_hard_finalize_kernel");
   return EN_OK;
 }

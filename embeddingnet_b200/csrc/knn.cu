@@ -8,6 +8,10 @@
 //                                 fp32 streaming scan bounded by HBM bandwidth;
 //   stage 2   exact re-rank     : the surviving candidates are re-evaluated as float64 sum (q-b)^2 and ordered by
 //                                 (distance, global id) -- lowest id wins ties, shard-invariant by construction;
+//                                 a CERTIFICATE per query proves that no row the scan rejected can beat the k-th
+//                                 result (rigorous bound on the scan's arithmetic error); queries without one are
+//                                 flagged and redone by
+//   stage 3   en_knn_exact_topk : float64 brute force over the shard for those few queries;
 //   merge / vote / accuracy     : k-way merge of per-shard lists (after the NCCL all-gather), majority vote
 //                                 (KNeighborsClassifier.predict), top-1 / top-5 tallies (models.py:144-161).
 #include "common.cuh"
@@ -253,10 +257,25 @@ knn_stream_kernel(const float* __restrict__ queries, int Q, int d, const float* 
 // One block per query (32 threads when the candidate lists are short, 256 when the streaming scan left thousands).
 // Extract the KC best proxies over all lists in (t, idx) order, re-evaluate them exactly in float64, order by
 // (d2, global id), emit the first k.
+//
+// Certificate.  Let t~ be the scan's proxy of a bank row and t its exact value, |t~ - t| <= E for every row (E from
+// the operand split and the accumulation of the scan arithmetic, see cert_bound()).  Every row that is NOT among
+// the KC re-evaluated candidates was rejected against a list threshold or sorts after the KC-th extracted proxy
+// tau, so t~ >= tau and hence t >= tau - E.  If the exact k-th result satisfies t_k < tau - E, no rejected row can
+// precede it: the k results are THE k nearest rows.  Otherwise uncertified[q] = 1 and the caller re-does the query
+// with en_knn_exact_topk.  (Lists that ran dry before KC extractions mean every admissible row was re-evaluated.)
+struct CertParams {
+  int form;               // 0: proxy t = |b|^2 - 2 q.b, absolute bound;  1: proxy = d2 itself, relative bound
+  double c;               // form 0: |dot~ - dot| <= c |q| |b|;  form 1: |d2~ - d2| <= c d2
+  const unsigned* bmax2;  // form 0: bit pattern of max_b |b|^2 over the shard (device)
+  int32_t* uncertified;   // (Q,) flags, may be null
+};
+
 template <int KC>
 __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, int d,
                                   const float* __restrict__ bank, int64_t id_offset, const Cand* __restrict__ lists,
-                                  int n_lists, int k, double* __restrict__ d2_out, int64_t* __restrict__ ids_out) {
+                                  int n_lists, int k, double* __restrict__ d2_out, int64_t* __restrict__ ids_out,
+                                  const CertParams cert) {
   __shared__ float s_t[8];
   __shared__ int32_t s_i[8];
   const int64_t q = blockIdx.x;
@@ -267,6 +286,7 @@ __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, 
   int32_t last_i = -1;
   double my_d2 = 1e300;   // warp 0: lane r holds the r-th extracted candidate
   int32_t my_idx = -1;
+  int extracted = 0;
   for (int r = 0; r < KC; ++r) {
     float bt = kInf;
     int32_t bi = 0x7fffffff;
@@ -307,13 +327,14 @@ __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, 
     if (bi == 0x7fffffff) break;  // lists exhausted (block-uniform)
     last_t = bt;
     last_i = bi;
+    ++extracted;
     if (warp == 0) {
       const float* a = queries + q * d;
       const float* b = bank + static_cast<int64_t>(bi) * d;
       double acc = 0.0;
       for (int c = lane; c < d; c += 32) {
         const double t = static_cast<double>(a[c]) - static_cast<double>(b[c]);
-        acc += t * t;
+        acc = fma(t, t, acc);
       }
       acc = warp_sum(acc);
       if (lane == r) {
@@ -341,6 +362,56 @@ __global__ void knn_rerank_kernel(const float* __restrict__ queries, int64_t Q, 
     d2_out[q * k + lane] = INFINITY;
     ids_out[q * k + lane] = -1;
   }
+  if (cert.uncertified != nullptr) {
+    bool certified = extracted < KC;  // lists ran dry: every admissible row was re-evaluated exactly
+    if (!certified) {
+      const unsigned kth = __ballot_sync(0xffffffffu, my_idx >= 0 && rank == k - 1);
+      const double dk = __shfl_sync(0xffffffffu, my_d2, kth ? __ffs(kth) - 1 : 0);
+      const double tau = static_cast<double>(last_t);  // the KC-th extracted proxy
+      if (kth == 0) {
+        certified = false;  // cannot happen (extracted == KC > k), be safe
+      } else if (cert.form == 1) {
+        certified = dk < tau * (1.0 - cert.c);
+      } else {
+        const float* a = queries + q * d;
+        double qn2 = 0.0;
+        for (int c = lane; c < d; c += 32) qn2 = fma(static_cast<double>(a[c]), static_cast<double>(a[c]), qn2);
+        qn2 = warp_sum(qn2);
+        const double bm2 = static_cast<double>(__uint_as_float(*cert.bmax2));
+        const double qb = sqrt(qn2 * bm2);
+        // dot error doubled by the proxy, plus the fp32 roundings of |b|^2 and of the final fma
+        const double E = 2.0 * cert.c * qb + 2.4e-7 * (bm2 + 2.0 * qb);
+        certified = (dk - qn2) + E < tau;
+      }
+    }
+    if (lane == 0) cert.uncertified[q] = certified ? 0 : 1;
+  }
+}
+
+// max over the shard of the squared row norms (non-negative floats order like their bit patterns)
+__global__ void max_norm_kernel(const float* __restrict__ norms, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, norms[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// Rigorous bound c with |dot~ - dot| <= c |q| |b| for the scan arithmetic (x1.5 safety):
+//   operand split: the dropped products lo*lo, r*b, q*r with |x - hi| <= u |x|, |x - hi - lo| <= u^2 |x|
+//                  (u = 2^-11 TF32 round-to-nearest, 2^-8 BF16)                      -> 3 u^2 (1 + u)
+//   accumulation : the tensor core truncates when it adds into the fp32 accumulator, <= 2^-22 of the partial sum
+//                  per MMA (measured bias on B200: ~2^-24 per link), d / K_mma links     -> 2^-22 (links + 1)
+//   fp32 stream  : d/32 sequential FMAs per lane + 5 shuffle adds, 2^-24 each.
+inline double cert_bound(int precision, int d) {
+  const double p22 = 1.0 / 4194304.0;
+  double c;
+  if (precision == EN_PREC_BF16X3) c = 3.0 / 65536.0 * (1.0 + 1.0 / 256.0) + p22 * ((d + 15) / 16 + 1);
+  else if (precision == EN_PREC_TF32X3) c = 3.0 * p22 * (1.0 + 1.0 / 2048.0) + p22 * ((d + 7) / 8 + 1);
+  else c = p22 / 4.0 * ((d + 31) / 32 + 8);
+  return 1.5 * c;
 }
 
 // ---------------------------------------------------------------- merge of per-shard lists
@@ -453,14 +524,14 @@ inline int knn_splits(int64_t Q, int64_t n_bank, int sms) {
 
 template <int KC>
 int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh, const CUtensorMap& bl, int64_t Q,
-             int64_t n_bank, int d, int splits_per_launch, const float* bank_norms, const int32_t* bank_labels,
-             const int32_t* query_labels, Cand* lists, int sms, cudaStream_t st) {
+             int64_t n_bank, int d, int bf16, int splits_per_launch, const float* bank_norms,
+             const int32_t* bank_labels, const int32_t* query_labels, Cand* lists, int sms, cudaStream_t st) {
   const int tiles_total = static_cast<int>((n_bank + tc::BN - 1) / tc::BN);
   const int chunk_tiles = splits_per_launch * kChunkTilesPerSplit;
   prof_begin(st);
   for (int base = 0, launch = 0; base < tiles_total; base += chunk_tiles, ++launch) {
     const int tiles_here = tiles_total - base < chunk_tiles ? tiles_total - base : chunk_tiles;
-    tc::Shape sh = tc::make_shape(Q, static_cast<int64_t>(tiles_here) * tc::BN, d, splits_per_launch, 3);
+    tc::Shape sh = tc::make_shape(Q, static_cast<int64_t>(tiles_here) * tc::BN, d, splits_per_launch, 3, bf16);
     // keep the split count (= list slots per query) fixed across launches, even for a short last chunk
     sh.n_splits = splits_per_launch;
     sh.tiles_per_split = (tiles_here + splits_per_launch - 1) / splits_per_launch;
@@ -477,12 +548,151 @@ int run_scan(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh
 
 template <int KC>
 int run_rerank(const float* queries, int64_t Q, int d, const float* bank, int64_t id_offset, const Cand* lists,
-               int n_lists, int k, double* d2, int64_t* ids, cudaStream_t st) {
+               int n_lists, int k, double* d2, int64_t* ids, const CertParams& cert, cudaStream_t st) {
   const int threads = n_lists * KC > 1024 ? 256 : 32;
   knn_rerank_kernel<KC><<<static_cast<unsigned>(Q), threads, 0, st>>>(queries, Q, d, bank, id_offset, lists, n_lists,
-                                                                       k, d2, ids);
+                                                                       k, d2, ids, cert);
   EN_LAUNCHED("knn_rerank_kernel");
   return EN_OK;
+}
+
+int dispatch_rerank(int KC, const float* queries, int64_t Q, int d, const float* bank, int64_t id_offset,
+                    const Cand* lists, int n_lists, int k, double* d2, int64_t* ids, const CertParams& cert,
+                    cudaStream_t st) {
+  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, cert, st);
+  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, cert, st);
+  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, n_lists, k, d2, ids, cert, st);
+}
+
+// bmax2 <- max squared row norm of the shard (for the certificate); one pass over 4 bytes per row
+int launch_max_norm(const float* norms, int64_t n, unsigned* bmax2, cudaStream_t st) {
+  EN_CUDA(cudaMemsetAsync(bmax2, 0, sizeof(unsigned), st));
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 1184) blocks = 1184;
+  max_norm_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(norms, n, bmax2);
+  EN_LAUNCHED("max_norm_kernel");
+  return EN_OK;
+}
+
+// ---------------------------------------------------------------- stage 3: float64 brute force (rare path)
+// For the few queries the certificate could not cover (near-ties at the candidate cut-off, duplicated bank rows).
+// Exact by construction: every admissible row's float64 sum (q-b)^2 (the re-rank's arithmetic, same loop order) is
+// compared by (d2, id).  grid = (bank blocks, query groups of EX_QT); each warp streams a contiguous row range and
+// keeps one sorted k-list per query in shared memory; per-block lists go to (P, Q, k) partials for knn_merge_kernel.
+constexpr int EX_QT = 4;
+constexpr int EX_KMAX = 32;
+constexpr int EX_WARPS = 8;
+
+__device__ __forceinline__ bool pair_less(double da, int32_t ia, double db, int32_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+__global__ void __launch_bounds__(EX_WARPS * 32)
+knn_exact_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank, int64_t n_bank,
+                 int64_t id_offset, int k, const int32_t* __restrict__ query_labels,
+                 const int32_t* __restrict__ bank_labels, int64_t rows_per_warp, double* __restrict__ pd2,
+                 int64_t* __restrict__ pid) {
+  extern __shared__ __align__(16) uint8_t ex_smem[];
+  float* qs = reinterpret_cast<float*>(ex_smem);                                       // [EX_QT][d]
+  double* ld = reinterpret_cast<double*>(ex_smem + ((static_cast<size_t>(EX_QT) * d * 4 + 15) / 16) * 16);
+  int32_t* li = reinterpret_cast<int32_t*>(ld + EX_WARPS * EX_QT * EX_KMAX);           // same shape as ld
+  const int q0 = blockIdx.y * EX_QT;
+  const int nq = min(EX_QT, Q - q0);
+  for (int i = threadIdx.x; i < EX_QT * d; i += blockDim.x) qs[i] = i < nq * d ? queries[static_cast<int64_t>(q0) * d + i] : 0.f;
+  for (int i = threadIdx.x; i < EX_WARPS * EX_QT * EX_KMAX; i += blockDim.x) {
+    ld[i] = INFINITY;
+    li[i] = -1;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * EX_WARPS + warp;
+  const int64_t r0 = gwarp * rows_per_warp;
+  const int64_t r1 = min(r0 + rows_per_warp, n_bank);
+  int32_t qlab = 0;
+  const bool exclude = query_labels != nullptr && bank_labels != nullptr;
+  if (exclude && lane < nq) qlab = query_labels[q0 + lane];
+  double* myd = ld + (warp * EX_QT + lane) * EX_KMAX;  // lane q < nq owns query q's list of this warp
+  int32_t* myi = li + (warp * EX_QT + lane) * EX_KMAX;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* b = bank + r * d;
+    double acc[EX_QT];
+#pragma unroll
+    for (int q = 0; q < EX_QT; ++q) acc[q] = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      const double y = static_cast<double>(b[c]);
+#pragma unroll
+      for (int q = 0; q < EX_QT; ++q) {
+        const double t = static_cast<double>(qs[q * d + c]) - y;
+        acc[q] = fma(t, t, acc[q]);
+      }
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int q = 0; q < EX_QT; ++q) {
+      const double v = warp_sum(acc[q]);
+      if (lane == q) mine = v;
+    }
+    if (lane < nq) {
+      const int32_t idx = static_cast<int32_t>(r);
+      if (!(exclude && __ldg(&bank_labels[r]) == qlab) && pair_less(mine, idx, myd[k - 1], myi[k - 1] < 0 ? 0x7fffffff : myi[k - 1])) {
+        int pos = k - 1;
+        while (pos > 0 && pair_less(mine, idx, myd[pos - 1], myi[pos - 1] < 0 ? 0x7fffffff : myi[pos - 1])) {
+          myd[pos] = myd[pos - 1];
+          myi[pos] = myi[pos - 1];
+          --pos;
+        }
+        myd[pos] = mine;
+        myi[pos] = idx;
+      }
+    }
+  }
+  __syncthreads();
+  // block merge: thread q selects the k best of the 8 warps' lists in (d2, id) order
+  if (threadIdx.x < nq) {
+    const int q = threadIdx.x;
+    double last_d = -1.0;
+    int32_t last_i = -1;
+    double* od = pd2 + (static_cast<int64_t>(blockIdx.x) * Q + q0 + q) * k;
+    int64_t* oi = pid + (static_cast<int64_t>(blockIdx.x) * Q + q0 + q) * k;
+    for (int r = 0; r < k; ++r) {
+      double bd = INFINITY;
+      int32_t bi = -1;
+      for (int w = 0; w < EX_WARPS; ++w) {
+        const double* wd = ld + (w * EX_QT + q) * EX_KMAX;
+        const int32_t* wi = li + (w * EX_QT + q) * EX_KMAX;
+        for (int c = 0; c < k; ++c) {
+          const int32_t i = wi[c];
+          if (i < 0) break;
+          const double x = wd[c];
+          const bool after = x > last_d || (x == last_d && i > last_i);
+          if (after && (bi < 0 || pair_less(x, i, bd, bi))) {
+            bd = x;
+            bi = i;
+          }
+        }
+      }
+      od[r] = bi >= 0 ? bd : INFINITY;
+      oi[r] = bi >= 0 ? id_offset + bi : -1;
+      if (bi < 0) {
+        for (int rr = r + 1; rr < k; ++rr) {
+          od[rr] = INFINITY;
+          oi[rr] = -1;
+        }
+        break;
+      }
+      last_d = bd;
+      last_i = bi;
+    }
+  }
+}
+
+inline void exact_geometry(int64_t n_bank, int sms, int64_t* rows_per_warp, int* blocks) {
+  int64_t warps = static_cast<int64_t>(sms) * 2 * EX_WARPS;
+  if (warps > n_bank) warps = n_bank;
+  const int64_t rpw = (n_bank + warps - 1) / warps;
+  *rows_per_warp = rpw;
+  const int64_t used = (n_bank + rpw - 1) / rpw;
+  *blocks = static_cast<int>((used + EX_WARPS - 1) / EX_WARPS);
 }
 
 constexpr int STREAM_WARPS = 8;
@@ -547,65 +757,89 @@ using namespace en;
 
 extern "C" {
 
-int en_bank_dpad(int d) { return d > 0 ? (d + tc::BK - 1) / tc::BK * tc::BK : 0; }
+int en_bank_dpad(int d, int precision) { return d > 0 ? tc::dpad_for(d, precision == EN_PREC_BF16X3) : 0; }
 
-int en_bank_prepare(const float* bank, int64_t n, int d, float* hi, float* lo, float* norms, void* stream) {
+size_t en_bank_plane_bytes(int64_t n, int d, int precision) {
+  if (n <= 0 || d <= 0) return 0;
+  return static_cast<size_t>(n) * en_bank_dpad(d, precision) * (precision == EN_PREC_BF16X3 ? 2 : 4);
+}
+
+int en_bank_prepare(const float* bank, int64_t n, int d, int precision, void* hi, void* lo, float* norms,
+                    void* stream) {
   EN_REQUIRE(bank && hi && lo && norms && n >= 0 && d > 0, "en_bank_prepare: bad arguments");
+  EN_REQUIRE(precision == EN_PREC_TF32X3 || precision == EN_PREC_BF16X3, "en_bank_prepare: unknown precision %d",
+             precision);
   if (n == 0) return EN_OK;
-  EN_CUDA(tc::launch_split(bank, n, d, d, en_bank_dpad(d), hi, lo, norms, as_stream(stream)));
+  if (precision == EN_PREC_BF16X3)
+    EN_CUDA(tc::launch_split_bf16(bank, n, d, d, en_bank_dpad(d, precision), hi, lo, norms, as_stream(stream)));
+  else
+    EN_CUDA(tc::launch_split(bank, n, d, d, en_bank_dpad(d, precision), static_cast<float*>(hi),
+                             static_cast<float*>(lo), norms, as_stream(stream)));
   ++launch_counter();
   return EN_OK;
 }
 
 size_t en_ws_bytes_knn(int64_t Q, int64_t n_bank, int d, int k) {
   if (Q <= 0 || n_bank <= 0 || d <= 0 || k <= 0 || k > EN_KNN_MAX_K) return 0;
-  const size_t dpad = static_cast<size_t>(en_bank_dpad(d));
+  const size_t dpad = static_cast<size_t>(en_bank_dpad(d, EN_PREC_TF32X3));  // the larger of the two plane formats
   const int s = knn_splits(Q, n_bank, 160);  // sized for the largest SM count
-  return 2 * align_up(static_cast<size_t>(Q) * dpad * 4) + align_up(static_cast<size_t>(Q) * 4) +
+  return 2 * align_up(static_cast<size_t>(Q) * dpad * 4) + align_up(static_cast<size_t>(Q) * 4) + align_up(4) +
          align_up(static_cast<size_t>(Q) * s * tc::EPI_H * kc_for(k) * sizeof(Cand));
 }
 
-int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_hi,
-                      const float* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
-                      const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids, void* ws,
-                      size_t ws_bytes, void* stream) {
+int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const void* bank_hi,
+                      const void* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                      int precision, const int32_t* query_labels, const int32_t* bank_labels, double* d2,
+                      int64_t* ids, int32_t* uncertified, void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(queries && bank && bank_hi && bank_lo && bank_norms && d2 && ids && Q > 0 && n_bank > 0 && d > 0,
              "en_knn_shard_topk: bad arguments");
   EN_REQUIRE(k > 0 && k <= EN_KNN_MAX_K, "en_knn_shard_topk: k must be in [1, %d] (got %d)", EN_KNN_MAX_K, k);
   EN_REQUIRE((query_labels == nullptr) == (bank_labels == nullptr) || query_labels == nullptr,
              "en_knn_shard_topk: query_labels requires bank_labels");
   EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_shard_topk: shard too large (%lld rows)", (long long)n_bank);
+  EN_REQUIRE(precision == EN_PREC_TF32X3 || precision == EN_PREC_BF16X3, "en_knn_shard_topk: unknown precision %d",
+             precision);
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < en_ws_bytes_knn(Q, n_bank, d, k))
     return fail(EN_ERR_WORKSPACE, "en_knn_shard_topk: workspace too small (%zu < %zu)", ws_bytes,
                 en_ws_bytes_knn(Q, n_bank, d, k));
   cudaStream_t st = as_stream(stream);
   const int sms = device_sm_count();
-  const int dpad = en_bank_dpad(d);
+  const int bf16 = precision == EN_PREC_BF16X3;
+  const int dpad = en_bank_dpad(d, precision);
   const int KC = kc_for(k);
   Workspace w(ws, ws_bytes);
-  float* qhi = w.take<float>(static_cast<size_t>(Q) * dpad);
-  float* qlo = w.take<float>(static_cast<size_t>(Q) * dpad);
+  float* qhi = w.take<float>(static_cast<size_t>(Q) * en_bank_dpad(d, EN_PREC_TF32X3));
+  float* qlo = w.take<float>(static_cast<size_t>(Q) * en_bank_dpad(d, EN_PREC_TF32X3));
   float* qn = w.take<float>(Q);
+  unsigned* bmax2 = w.take<unsigned>(1);
   const int splits = knn_splits(Q, n_bank, sms);
   Cand* lists = w.take<Cand>(static_cast<size_t>(Q) * splits * tc::EPI_H * KC);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_knn_shard_topk: workspace too small or misaligned");
-  EN_CUDA(tc::launch_split(queries, Q, d, d, dpad, qhi, qlo, qn, st));
-  ++launch_counter();
   CUtensorMap tqh, tql, tbh, tbl;
-  if (tc::make_plane_tmap(&tqh, qhi, Q, dpad) || tc::make_plane_tmap(&tql, qlo, Q, dpad) ||
-      tc::make_plane_tmap(&tbh, bank_hi, n_bank, dpad) || tc::make_plane_tmap(&tbl, bank_lo, n_bank, dpad))
-    return fail(EN_ERR_DRIVER, "en_knn_shard_topk: cuTensorMapEncodeTiled failed");
+  if (bf16) {
+    EN_CUDA(tc::launch_split_bf16(queries, Q, d, d, dpad, qhi, qlo, qn, st));
+    if (tc::make_plane_tmap_bf16(&tqh, qhi, Q, dpad) || tc::make_plane_tmap_bf16(&tql, qlo, Q, dpad) ||
+        tc::make_plane_tmap_bf16(&tbh, bank_hi, n_bank, dpad) || tc::make_plane_tmap_bf16(&tbl, bank_lo, n_bank, dpad))
+      return fail(EN_ERR_DRIVER, "en_knn_shard_topk: cuTensorMapEncodeTiled failed");
+  } else {
+    EN_CUDA(tc::launch_split(queries, Q, d, d, dpad, qhi, qlo, qn, st));
+    if (tc::make_plane_tmap(&tqh, qhi, Q, dpad) || tc::make_plane_tmap(&tql, qlo, Q, dpad) ||
+        tc::make_plane_tmap(&tbh, static_cast<const float*>(bank_hi), n_bank, dpad) ||
+        tc::make_plane_tmap(&tbl, static_cast<const float*>(bank_lo), n_bank, dpad))
+      return fail(EN_ERR_DRIVER, "en_knn_shard_topk: cuTensorMapEncodeTiled failed");
+  }
+  ++launch_counter();
   const int32_t* ql = bank_labels ? query_labels : nullptr;
   int rc;
-  if (KC == 8) rc = run_scan<8>(tqh, tql, tbh, tbl, Q, n_bank, d, splits, bank_norms, bank_labels, ql, lists, sms, st);
-  else if (KC == 16) rc = run_scan<16>(tqh, tql, tbh, tbl, Q, n_bank, d, splits, bank_norms, bank_labels, ql, lists, sms, st);
-  else rc = run_scan<32>(tqh, tql, tbh, tbl, Q, n_bank, d, splits, bank_norms, bank_labels, ql, lists, sms, st);
+  if (KC == 8) rc = run_scan<8>(tqh, tql, tbh, tbl, Q, n_bank, d, bf16, splits, bank_norms, bank_labels, ql, lists, sms, st);
+  else if (KC == 16) rc = run_scan<16>(tqh, tql, tbh, tbl, Q, n_bank, d, bf16, splits, bank_norms, bank_labels, ql, lists, sms, st);
+  else rc = run_scan<32>(tqh, tql, tbh, tbl, Q, n_bank, d, bf16, splits, bank_norms, bank_labels, ql, lists, sms, st);
   if (rc) return rc;
-  const int nl = splits * tc::EPI_H;
-  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
-  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
-  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, nl, k, d2, ids, st);
+  CertParams cert{0, cert_bound(precision, dpad), bmax2, uncertified};
+  if (uncertified != nullptr)
+    if (int rc2 = launch_max_norm(bank_norms, n_bank, bmax2, st)) return rc2;
+  return dispatch_rerank(KC, queries, Q, d, bank, id_offset, lists, splits * tc::EPI_H, k, d2, ids, cert, st);
 }
 
 size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k) {
@@ -613,12 +847,12 @@ size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k) {
   int64_t rpw;
   int blocks;
   stream_geometry(n_bank, 160, &rpw, &blocks);  // sized for the largest SM count
-  return align_up(static_cast<size_t>(Q) * (blocks + 8) * kc_for(k) * sizeof(Cand));
+  return align_up(static_cast<size_t>(Q) * (blocks + 8) * kc_for(k) * sizeof(Cand)) + align_up(4);
 }
 
 int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_norms,
-                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes,
-                       void* stream) {
+                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, int32_t* uncertified,
+                       void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(queries && bank && d2 && ids && Q > 0 && n_bank > 0 && d > 0, "en_knn_stream_topk: bad arguments");
   EN_REQUIRE(Q <= EN_KNN_STREAM_MAX_Q, "en_knn_stream_topk: at most %d queries per call (got %lld)",
              EN_KNN_STREAM_MAX_Q, (long long)Q);
@@ -635,14 +869,60 @@ int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank
   stream_geometry(n_bank, sms, &rpw, &blocks);
   const int KC = kc_for(k);
   Cand* lists = static_cast<Cand*>(ws);
+  unsigned* bmax2 = reinterpret_cast<unsigned*>(
+      static_cast<uint8_t*>(ws) + align_up(static_cast<size_t>(Q) * (blocks + 8) * KC * sizeof(Cand)));
   int rc;
   if (KC == 8) rc = launch_stream_d<8>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
   else if (KC == 16) rc = launch_stream_d<16>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
   else rc = launch_stream_d<32>(queries, Q, d, bank, bank_norms, n_bank, rpw, blocks, lists, st);
   if (rc) return rc;
-  if (KC == 8) return run_rerank<8>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
-  if (KC == 16) return run_rerank<16>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
-  return run_rerank<32>(queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, st);
+  // fp32 CUDA-core arithmetic: dot form (absolute bound) with norms, direct sum (q-b)^2 (relative bound) without
+  CertParams cert{bank_norms ? 0 : 1, bank_norms ? cert_bound(-1, d) : 1.5 * (d / 32 + 12) / 16777216.0, bmax2,
+                  uncertified};
+  if (uncertified != nullptr && bank_norms != nullptr)
+    if (int rc2 = launch_max_norm(bank_norms, n_bank, bmax2, st)) return rc2;
+  return dispatch_rerank(KC, queries, Q, d, bank, id_offset, lists, blocks, k, d2, ids, cert, st);
+}
+
+size_t en_ws_bytes_knn_exact(int64_t Q, int64_t n_bank, int d, int k) {
+  if (Q <= 0 || Q > EN_KNN_EXACT_MAX_Q || n_bank <= 0 || d <= 0 || k <= 0 || k > EN_KNN_MAX_K) return 0;
+  int64_t rpw;
+  int blocks;
+  exact_geometry(n_bank, 160, &rpw, &blocks);  // sized for the largest SM count
+  return 2 * align_up(static_cast<size_t>(blocks) * Q * k * 8);
+}
+
+int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                      int k, const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids,
+                      void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(queries && bank && d2 && ids && Q > 0 && n_bank > 0 && d > 0, "en_knn_exact_topk: bad arguments");
+  EN_REQUIRE(Q <= EN_KNN_EXACT_MAX_Q, "en_knn_exact_topk: at most %d queries per call (got %lld)",
+             EN_KNN_EXACT_MAX_Q, (long long)Q);
+  EN_REQUIRE(k > 0 && k <= EN_KNN_MAX_K, "en_knn_exact_topk: k must be in [1, %d]", EN_KNN_MAX_K);
+  EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_exact_topk: shard too large");
+  EN_REQUIRE((query_labels == nullptr) == (bank_labels == nullptr) || query_labels == nullptr,
+             "en_knn_exact_topk: query_labels requires bank_labels");
+  const size_t smem = (static_cast<size_t>(EX_QT) * d * 4 + 15) / 16 * 16 +
+                      static_cast<size_t>(EX_WARPS) * EX_QT * EX_KMAX * 12;
+  EN_REQUIRE(smem <= 200 * 1024, "en_knn_exact_topk: d too large for shared memory");
+  if (!ws || ws_bytes < en_ws_bytes_knn_exact(Q, n_bank, d, k) || (reinterpret_cast<uintptr_t>(ws) & 255) != 0)
+    return fail(EN_ERR_WORKSPACE, "en_knn_exact_topk: workspace too small or misaligned");
+  cudaStream_t st = as_stream(stream);
+  int64_t rpw;
+  int blocks;
+  exact_geometry(n_bank, device_sm_count(), &rpw, &blocks);
+  double* pd2 = static_cast<double*>(ws);
+  int64_t* pid = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(ws) + align_up(static_cast<size_t>(blocks) * Q * k * 8));
+  if (smem > 48 * 1024)
+    EN_CUDA(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>((Q + EX_QT - 1) / EX_QT));
+  const int32_t* ql = bank_labels ? query_labels : nullptr;
+  knn_exact_kernel<<<grid, EX_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank, id_offset, k, ql,
+                                                      bank_labels, rpw, pd2, pid);
+  EN_LAUNCHED("knn_exact_kernel");
+  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, st>>>(pd2, pid, blocks, Q, k, d2, ids);
+  EN_LAUNCHED("knn_merge_kernel");
+  return EN_OK;
 }
 
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,

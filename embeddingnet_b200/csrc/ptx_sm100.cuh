@@ -97,6 +97,17 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with BF16 inputs (kind::f16): 16 k-elements per instruction, i.e. twice the TF32 rate.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All prior tcgen05.mma of this thread arrive on the mbarrier when they complete.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -236,6 +247,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // c_format F32=1 [4,6) | a_format TF32=2 [7,10) | b_format TF32=2 [10,13) | N>>3 [17,23) | M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with BF16 operands (a_format / b_format BF16 = 1), FP32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -57,6 +57,10 @@ struct Shape {
                     // the epilogue must reduce each tile both along rows and along columns
   int num_items;
   int nt_base;      // first column tile of this launch (bank scans walk the bank in L2-sized chunks, one launch each)
+  int bf16;         // operand planes are BF16 (hi = bf16(x), lo = bf16(x - hi)), kind::f16 MMAs at twice the TF32
+                    // rate; ~2^-16 relative instead of ~2^-22: for paths that only SELECT candidates which are then
+                    // re-evaluated exactly (bank scan, batch-hard)
+  int bk;           // elements per k-block (one 128-byte swizzle row): 32 fp32/TF32 or 64 BF16
 };
 
 // Work item -> (row tile, column-tile range).  Same arithmetic in all three warp roles.
@@ -179,11 +183,12 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             uint8_t* st = smem + stage * STAGE_BYTES;
             const bool lo = shape.passes > 1;
             ptx::mbar_arrive_expect_tx(&bars->full[stage], lo ? STAGE_BYTES : 2 * TILE_BYTES);
-            ptx::tma_load_2d(&tm_a_hi, &bars->full[stage], st + 0 * TILE_BYTES, kb * BK, tile_m * BM);
-            ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st + 2 * TILE_BYTES, kb * BK, (shape.nt_base + nt) * BN);
+            const int kc = kb * shape.bk;
+            ptx::tma_load_2d(&tm_a_hi, &bars->full[stage], st + 0 * TILE_BYTES, kc, tile_m * BM);
+            ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st + 2 * TILE_BYTES, kc, (shape.nt_base + nt) * BN);
             if (lo) {
-              ptx::tma_load_2d(&tm_a_lo, &bars->full[stage], st + 1 * TILE_BYTES, kb * BK, tile_m * BM);
-              ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + 3 * TILE_BYTES, kb * BK, (shape.nt_base + nt) * BN);
+              ptx::tma_load_2d(&tm_a_lo, &bars->full[stage], st + 1 * TILE_BYTES, kc, tile_m * BM);
+              ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + 3 * TILE_BYTES, kc, (shape.nt_base + nt) * BN);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -194,6 +199,8 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc16 = ptx::make_idesc_bf16(BM, BN);
+      const bool bf16 = shape.bf16 != 0;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_it = 0;
@@ -217,8 +224,15 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 32 bytes along K inside the 128B swizzle row: +2 in the (addr>>4) field
+              // (8 TF32 or 16 BF16 elements per instruction: the same 32 bytes either way)
               const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
-              if (shape.passes > 1) {
+              if (bf16) {
+                if (shape.passes > 1) {
+                  ptx::mma_bf16_ss(tmem_x, a_lo + koff, b_hi + koff, idesc16, (kb | k) != 0);
+                  ptx::mma_bf16_ss(tmem_x, a_hi + koff, b_lo + koff, idesc16, 1);
+                }
+                ptx::mma_bf16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc16, (kb | k) != 0);
+              } else if (shape.passes > 1) {
                 ptx::mma_tf32_ss(tmem_x, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
                 ptx::mma_tf32_ss(tmem_x, a_hi + koff, b_lo + koff, idesc, 1);
                 ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
@@ -319,11 +333,31 @@ inline int make_plane_tmap(CUtensorMap* tm, const float* base, int64_t rows, int
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes) {
+// Same over a BF16 plane: `rows` x `cols_padded` bf16 (cols_padded a multiple of BK16 = 64), box = (64 cols, 128
+// rows) = the same 128-byte swizzle rows and 16 KiB tiles as the TF32 planes.
+constexpr int BK16 = 64;
+inline int make_plane_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols_padded,
+                                int box_rows = BM) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols_padded), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols_padded) * 2};
+  cuuint32_t box[2] = {BK16, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+inline int dpad_for(int d, int bf16) { return bf16 ? (d + BK16 - 1) / BK16 * BK16 : (d + BK - 1) / BK * BK; }
+
+inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes, int bf16 = 0) {
   Shape s;
   s.M = M;
   s.N = N;
-  s.kblocks = (d + BK - 1) / BK;
+  s.bf16 = bf16;
+  s.bk = bf16 ? BK16 : BK;
+  s.kblocks = (d + s.bk - 1) / s.bk;
   s.tiles_m = static_cast<int>((M + BM - 1) / BM);
   s.tiles_n = static_cast<int>((N + BN - 1) / BN);
   if (n_splits < 1) n_splits = 1;
@@ -338,8 +372,8 @@ inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes) {
 }
 
 // A == B (M == N): upper-triangular tile schedule, one tile per item.
-inline Shape make_shape_symmetric(int64_t N, int d, int passes) {
-  Shape s = make_shape(N, N, d, 1 << 30, passes);
+inline Shape make_shape_symmetric(int64_t N, int d, int passes, int bf16 = 0) {
+  Shape s = make_shape(N, N, d, 1 << 30, passes, bf16);
   s.symmetric = 1;
   s.num_items = s.tiles_n * (s.tiles_n + 1) / 2;
   return s;
@@ -397,6 +431,48 @@ static __global__ void split_planes_kernel(const float* __restrict__ x, int64_t 
   if (lane == 0 && norms) norms[row] = static_cast<float>(acc);
 }
 
+// BF16 variant: hi = bf16_rn(x), lo = bf16_rn(x - hi); x - hi - lo is below 2^-16 |x|.
+__device__ __forceinline__ uint16_t to_bf16_bits(float x) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// `zero_rows` (optional, rows x d floats) is cleared and `zero_word` (optional) reset on the way: the fused
+// loss + gradient step needs a zeroed gradient buffer and counter, and a store here is cheaper than memset nodes.
+static __global__ void split_planes_bf16_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
+                                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                float* __restrict__ norms, float* __restrict__ zero_rows,
+                                                unsigned* __restrict__ zero_word) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  if (zero_word != nullptr && row == 0 && lane == 0) *zero_word = 0u;
+  if (zero_rows != nullptr) {
+    float* z = zero_rows + row * d;
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(zero_rows) & 15) == 0)
+      for (int c = 4 * lane; c < d; c += 128) *reinterpret_cast<float4*>(z + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    else
+      for (int c = lane; c < d; c += 32) z[c] = 0.f;
+  }
+  const float* xr = x + row * ldx;
+  uint32_t* hr = reinterpret_cast<uint32_t*>(hi + row * dpad);  // dpad is even (multiple of 64): 2 bf16 per store
+  uint32_t* lr = reinterpret_cast<uint32_t*>(lo + row * dpad);
+  double acc = 0.0;
+  for (int c = 2 * lane; c < dpad; c += 64) {
+    const float v0 = c < d ? xr[c] : 0.0f;
+    const float v1 = c + 1 < d ? xr[c + 1] : 0.0f;
+    const uint16_t h0 = to_bf16_bits(v0), h1 = to_bf16_bits(v1);
+    const float r0 = v0 - __uint_as_float(static_cast<uint32_t>(h0) << 16);
+    const float r1 = v1 - __uint_as_float(static_cast<uint32_t>(h1) << 16);
+    hr[c >> 1] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+    lr[c >> 1] = static_cast<uint32_t>(to_bf16_bits(r0)) | (static_cast<uint32_t>(to_bf16_bits(r1)) << 16);
+    acc += static_cast<double>(v0) * static_cast<double>(v0) + static_cast<double>(v1) * static_cast<double>(v1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && norms) norms[row] = static_cast<float>(acc);
+}
+
 // Column means of x (B x d), float64 accumulation in a fixed order (deterministic): one block of (32, 8) threads per
 // 32 columns.  Used to centre the operands (see split_planes_kernel).
 static __global__ void column_mean_kernel(const float* __restrict__ e, int64_t B, int d, float* __restrict__ mu) {
@@ -421,6 +497,17 @@ inline cudaError_t launch_split(const float* x, int64_t rows, int d, int64_t ldx
   const int threads = 256;
   const int64_t blocks = (rows * 32 + threads - 1) / threads;
   split_planes_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, rows, d, ldx, dpad, hi, lo, norms, mu);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_split_bf16(const float* x, int64_t rows, int d, int64_t ldx, int dpad, void* hi, void* lo,
+                                     float* norms, cudaStream_t stream, float* zero_rows = nullptr,
+                                     unsigned* zero_word = nullptr) {
+  if (rows == 0) return cudaSuccess;
+  const int threads = 256;
+  const int64_t blocks = (rows * 32 + threads - 1) / threads;
+  split_planes_bf16_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      x, rows, d, ldx, dpad, static_cast<uint16_t*>(hi), static_cast<uint16_t*>(lo), norms, zero_rows, zero_word);
   return cudaGetLastError();
 }
 

@@ -7,8 +7,9 @@ shapes.  What the snapshot leaves undefined or unwritten is defined here from it
 ``calculate_distances`` (models.py:123) and a ``KNeighborsClassifier``-shaped object (``fit`` / ``predict`` /
 ``kneighbors``, models.py:58,136,138) stored under ``encoded_training_data['knn_classifier']``.
 
-The bank scan is a streaming tcgen05 distance GEMM with an in-register per-query top-k, followed by an exact
-float64 re-rank (``csrc/knn.cu``).  With a ``torch.distributed`` process group the bank is sharded row-wise, one
+The bank scan is a streaming tcgen05 distance GEMM (split-BF16 operands by default) with an in-register per-query
+top-k, followed by an exact float64 re-rank that also PROVES, per query, that no rejected row could have made the
+top-k; the rare queries without such a certificate are redone by float64 brute force (``csrc/knn.cu``).  With a ``torch.distributed`` process group the bank is sharded row-wise, one
 shard per GPU, and the per-shard top-k lists are merged after one NCCL all-gather; results do not depend on the
 number of shards.  Keras model construction, h5 / ONNX export and image IO are out of scope: ``base_model`` is any
 object with ``predict(images) -> (n, d) float32``.
@@ -30,17 +31,28 @@ from ._runtime import as_cuda_f32, ptr, require_cuda, stream_ptr, workspace
 class BankKNNClassifier:
     """``sklearn.neighbors.KNeighborsClassifier``-shaped brute-force classifier over an encoding bank on B200.
 
-    fit(X, y) uploads (this rank's shard of) the bank and prepares the TF32 planes; ``kneighbors`` returns
+    fit(X, y) uploads (this rank's shard of) the bank and prepares the operand planes (``precision``: "bf16x3",
+    the default -- two BF16 planes, the scan runs at twice the TF32 rate -- or "tf32x3"); ``kneighbors`` returns
     ``(dist (Q, k) float32, idx (Q, k) int64)`` ascending by (distance, index) -- lowest index wins ties;
     ``predict`` is the uniform majority vote with ties resolved to the smallest class (sklearn's rule).
 
     process_group: optional torch.distributed group; rank r keeps rows [r*ceil(N/P), (r+1)*ceil(N/P)).
+    certify: check the per-query exactness certificate after every scan (one scalar device->host read) and redo
+    uncertified queries with the float64 brute-force kernel; ``last_uncertified`` counts them.  ``certify=False``
+    skips the read (e.g. inside a CUDA graph); results are then exact only up to the scan's candidate slack.
     """
 
-    def __init__(self, n_neighbors=5, process_group=None, device=None):
+    PRECISIONS = {"tf32x3": _lib.EN_PREC_TF32X3, "bf16x3": _lib.EN_PREC_BF16X3}
+
+    def __init__(self, n_neighbors=5, process_group=None, device=None, precision="bf16x3", certify=True):
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(self.PRECISIONS))
         self.n_neighbors = int(n_neighbors)
         self.process_group = process_group
         self.device = device
+        self.precision = precision
+        self.certify = bool(certify)
+        self.last_uncertified = 0
         self._fitted = False
 
     # -- sharding helpers
@@ -77,13 +89,16 @@ class BankKNNClassifier:
             raise ValueError("BankKNNClassifier.fit: X must be (N, d)")
         n, d = self._bank.shape
         self._n_total, self._offset, self._d = int(n_total), int(id_offset), d
-        dpad = lib.en_bank_dpad(d)
-        self._hi = torch.empty((n, dpad), dtype=torch.float32, device=dev)
-        self._lo = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+        self._prec = self.PRECISIONS[self.precision]
+        dpad = lib.en_bank_dpad(d, self._prec)
+        plane_dtype = torch.bfloat16 if self._prec == _lib.EN_PREC_BF16X3 else torch.float32
+        self._hi = torch.empty((n, dpad), dtype=plane_dtype, device=dev)
+        self._lo = torch.empty((n, dpad), dtype=plane_dtype, device=dev)
+        assert self._hi.numel() * self._hi.element_size() == lib.en_bank_plane_bytes(n, d, self._prec) or n == 0
         self._norms = torch.empty(n, dtype=torch.float32, device=dev)
         if n > 0:
-            _lib.call("en_bank_prepare", ptr(self._bank), n, d, ptr(self._hi), ptr(self._lo), ptr(self._norms),
-                      stream_ptr())
+            _lib.call("en_bank_prepare", ptr(self._bank), n, d, self._prec, ptr(self._hi), ptr(self._lo),
+                      ptr(self._norms), stream_ptr())
         ids = label_ids_all if isinstance(label_ids_all, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(np.asarray(label_ids_all, dtype=np.int32)))
         self._labels = ids.to(dev, torch.int32).contiguous()
@@ -117,16 +132,19 @@ class BankKNNClassifier:
             if exclude_labels is not None:
                 ql = exclude_labels.to(dev, torch.int32).contiguous()
                 bl = self._labels[self._offset:self._offset + n]
+            flags = torch.empty(Q, dtype=torch.int32, device=dev) if self.certify else None
             if Q <= _lib.EN_KNN_STREAM_MAX_Q and ql is None:
                 # the reference's own call pattern: one image per predict() -> HBM-bound streaming scan
                 ws = workspace(lib.en_ws_bytes_knn_stream(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._norms), n, self._offset, k,
-                          ptr(d2), ptr(ids), ptr(ws), ws.numel(), stream_ptr())
+                          ptr(d2), ptr(ids), ptr(flags), ptr(ws), ws.numel(), stream_ptr())
             else:
                 ws = workspace(lib.en_ws_bytes_knn(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_shard_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._hi), ptr(self._lo),
-                          ptr(self._norms), n, self._offset, k, ptr(ql), ptr(bl), ptr(d2), ptr(ids), ptr(ws),
-                          ws.numel(), stream_ptr())
+                          ptr(self._norms), n, self._offset, k, self._prec, ptr(ql), ptr(bl), ptr(d2), ptr(ids),
+                          ptr(flags), ptr(ws), ws.numel(), stream_ptr())
+            if flags is not None:
+                self._redo_uncertified(q, k, ql, bl, flags, d2, ids)
         world, _ = self._world()
         if world > 1:
             import torch.distributed as dist
@@ -140,6 +158,28 @@ class BankKNNClassifier:
             _lib.call("en_knn_merge", ptr(d2_all), ptr(id_all), world, Q, k, ptr(d2m), ptr(idm), stream_ptr())
             d2, ids = d2m, idm
         return d2, ids
+
+    def _redo_uncertified(self, q, k, ql, bl, flags, d2, ids):
+        """Float64 brute force for the queries whose certificate failed (near-ties at the candidate cut-off)."""
+        self.last_uncertified = int(flags.sum().item())     # the one host read of the certified path
+        if self.last_uncertified == 0:
+            return
+        lib = _lib.load()
+        n, d = self._bank.shape
+        todo = flags.nonzero().reshape(-1)
+        step = _lib.EN_KNN_EXACT_MAX_Q
+        for s in range(0, todo.numel(), step):
+            sel = todo[s:s + step]
+            qq = q.index_select(0, sel).contiguous()
+            qq_l = ql.index_select(0, sel).contiguous() if ql is not None else None
+            m = qq.shape[0]
+            e_d2 = torch.empty((m, k), dtype=torch.float64, device=q.device)
+            e_id = torch.empty((m, k), dtype=torch.int64, device=q.device)
+            ws = workspace(lib.en_ws_bytes_knn_exact(m, n, d, k), q.device, "knn_exact")
+            _lib.call("en_knn_exact_topk", ptr(qq), m, d, ptr(self._bank), n, self._offset, k, ptr(qq_l), ptr(bl),
+                      ptr(e_d2), ptr(e_id), ptr(ws), ws.numel(), stream_ptr())
+            d2.index_copy_(0, sel, e_d2)
+            ids.index_copy_(0, sel, e_id)
 
     def kneighbors_device(self, X, n_neighbors=None, exclude_labels=None):
         """Device-resident variant: returns (dist float32, idx int64) CUDA tensors, no host copy."""

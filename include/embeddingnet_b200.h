@@ -146,27 +146,48 @@ int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t
                                 float* gemb, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- encoding bank: nearest neighbours */
+/* Operand format of the tensor-core scan.  Both split every fp32 value into two planes (hi, lo) and issue three
+ * MMAs per k-step (hi*hi + hi*lo + lo*hi):
+ *   EN_PREC_TF32X3  TF32 planes (4 B / element each), kind::tf32, ~1e-6 relative: fp32-faithful;
+ *   EN_PREC_BF16X3  BF16 planes (2 B / element each), kind::f16 at twice the rate, ~4e-6 relative: enough to SELECT
+ *                   candidates, which the exact float64 re-rank then orders. */
+#define EN_PREC_TF32X3 0
+#define EN_PREC_BF16X3 1
 /* Bank preparation (the `fit` of the KNeighborsClassifier-shaped object models.py:58 expects): splits the fp32
- * bank shard into the two TF32 planes the tensor-core scan streams and computes squared row norms.
- * dpad = en_bank_dpad(d); hi/lo are (n, dpad), norms (n,). */
-int en_bank_dpad(int d);
-int en_bank_prepare(const float* bank, int64_t n, int d, float* hi, float* lo, float* norms, void* stream);
+ * bank shard into the two planes the tensor-core scan streams and computes squared row norms.
+ * dpad = en_bank_dpad(d, precision); hi/lo are (n, dpad) planes of en_bank_plane_bytes() each, norms (n,). */
+int en_bank_dpad(int d, int precision);
+size_t en_bank_plane_bytes(int64_t n, int d, int precision);
+int en_bank_prepare(const float* bank, int64_t n, int d, int precision, void* hi, void* lo, float* norms,
+                    void* stream);
 
 /* k nearest bank rows of every query, ordered by (exact distance, global id) -- kneighbors() at models.py:138,
- * np.argmin at models.py:124 for k = 1.  Two stages inside one call: a tcgen05 3xTF32 scan keeps the best
- * k + EN_KNN_SLACK candidates per query in registers, then those few are re-evaluated exactly in float64
- * (sum (q-b)^2) and re-ranked, which makes ids independent of tensor-core rounding and of how the bank is sharded.
+ * np.argmin at models.py:124 for k = 1.  Two stages inside one call: a tcgen05 scan (3 MMAs per k-step on the
+ * split planes) keeps the best k + EN_KNN_SLACK candidates per query in registers, then those few are re-evaluated
+ * exactly in float64 (sum (q-b)^2) and re-ranked, which makes ids independent of tensor-core rounding and of how
+ * the bank is sharded.
  * bank / bank_hi / bank_lo / bank_norms describe THIS shard's n_bank rows whose global ids start at id_offset.
  * exclude_label (may be NULL): candidates whose bank label equals query_labels[q] are skipped -- offline
  * hard-negative mining over a bank (BASELINE config 4).  Outputs: d2 (Q, k) float64 squared distances,
- * ids (Q, k) int64 (-1 = fewer than k candidates), ascending. */
+ * ids (Q, k) int64 (-1 = fewer than k candidates), ascending.
+ * uncertified (Q,) int32, may be NULL: 0 when the call PROVED (rigorous bound on the scan's rounding error against
+ * the gap between the k-th result and the best rejected candidate) that the k ids are the exact nearest rows,
+ * 1 when it could not (near-ties at the cut-off, duplicated rows): redo those queries with en_knn_exact_topk. */
 #define EN_KNN_SLACK 3
 #define EN_KNN_MAX_K 29
 size_t en_ws_bytes_knn(int64_t Q, int64_t n_bank, int d, int k);
-int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_hi,
-                      const float* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
-                      const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids, void* ws,
-                      size_t ws_bytes, void* stream);
+int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank, const void* bank_hi,
+                      const void* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                      int precision, const int32_t* query_labels, const int32_t* bank_labels, double* d2,
+                      int64_t* ids, int32_t* uncertified, void* ws, size_t ws_bytes, void* stream);
+/* Float64 brute force over the shard (sum (q-b)^2 for every admissible row, ordered by (d2, id)): the reference
+ * semantics with no filter in front.  For the queries en_knn_shard_topk / en_knn_stream_topk flag as uncertified;
+ * Q <= EN_KNN_EXACT_MAX_Q per call.  Same outputs. */
+#define EN_KNN_EXACT_MAX_Q 64
+size_t en_ws_bytes_knn_exact(int64_t Q, int64_t n_bank, int d, int k);
+int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                      int k, const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids,
+                      void* ws, size_t ws_bytes, void* stream);
 /* Small-batch variant for the reference's actual call pattern (one query per predict(), models.py:122,135):
  * a CUDA-core fp32 streaming scan bounded by HBM bandwidth; Q <= EN_KNN_STREAM_MAX_Q.  Same outputs.
  * bank_norms (n_bank squared row norms from en_bank_prepare) may be NULL: the scan then evaluates
@@ -174,8 +195,8 @@ int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank,
 #define EN_KNN_STREAM_MAX_Q 8
 size_t en_ws_bytes_knn_stream(int64_t Q, int64_t n_bank, int d, int k);
 int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank, const float* bank_norms,
-                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, void* ws, size_t ws_bytes,
-                       void* stream);
+                       int64_t n_bank, int64_t id_offset, int k, double* d2, int64_t* ids, int32_t* uncertified,
+                       void* ws, size_t ws_bytes, void* stream);
 /* Merge P per-shard lists (P, Q, k) (as gathered by an NCCL all-gather) into the global top-k by (d2, id). */
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
                  int64_t* ids, void* stream);

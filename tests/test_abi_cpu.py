@@ -49,7 +49,13 @@ def test_argument_errors_are_reported_without_a_gpu(lib_built):
     assert rc == -1
     assert lib.en_ws_bytes_batch_hard(4096, 512) > 2 * 4096 * 512 * 4
     assert lib.en_ws_bytes_knn(100, 1000, 64, 40) == 0  # k above EN_KNN_MAX_K
-    assert lib.en_bank_dpad(100) == 128
+    assert lib.en_bank_dpad(100, _lib.EN_PREC_TF32X3) == 128
+    assert lib.en_bank_dpad(100, _lib.EN_PREC_BF16X3) == 128 and lib.en_bank_dpad(33, _lib.EN_PREC_BF16X3) == 64
+    assert lib.en_bank_plane_bytes(10, 100, _lib.EN_PREC_BF16X3) == 10 * 128 * 2
+    assert lib.en_ws_bytes_knn_exact(65, 1000, 64, 5) == 0  # Q above EN_KNN_EXACT_MAX_Q
+    rc2 = lib.en_knn_exact_topk(ctypes.c_void_p(256), 65, 64, ctypes.c_void_p(256), 1000, 0, 5, None, None,
+                                ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 1 << 20, None)
+    assert rc2 == -1 and b"at most 64" in lib.en_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc, "en_l2_normalize_fwd")
 

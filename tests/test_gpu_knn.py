@@ -32,17 +32,19 @@ def test_knn_matches_sklearn_golden(golden):
     np.testing.assert_allclose(d1, golden["knn_dist"][:3], rtol=1e-5)
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
 @pytest.mark.parametrize("N,d,Q,k", [(1000, 64, 200, 5), (5000, 512, 300, 5), (777, 100, 129, 1), (3000, 256, 130, 10),
                                      (130, 32, 17, 29), (4, 8, 9, 5)])
-def test_knn_vs_oracle(N, d, Q, k):
+def test_knn_vs_oracle(N, d, Q, k, precision):
     from embeddingnet_b200.models import BankKNNClassifier
 
     bank, labels = synth.make_numpy(N, d, n_classes=max(2, N // 20), noise=0.5, relu=True)
     bank = unit_rows(bank)
     q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=max(2, N // 20), noise=0.6, relu=True)
     q = unit_rows(q)
-    clf = BankKNNClassifier(n_neighbors=min(k, 5)).fit(bank, labels)
+    clf = BankKNNClassifier(n_neighbors=min(k, 5), precision=precision).fit(bank, labels)
     dist, idx = clf.kneighbors(q, n_neighbors=k)
+    assert clf.last_uncertified <= max(1, Q // 20)  # the certificate covers (nearly) every query on tie-free data
     rd, ri = O.knn_exact(bank, q, k)
     kk = ri.shape[1]
     np.testing.assert_array_equal(idx[:, :kk], ri)
@@ -51,7 +53,8 @@ def test_knn_vs_oracle(N, d, Q, k):
         assert np.all(idx[:, kk:] == -1)
 
 
-def test_knn_ties_resolve_to_lowest_id():
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
+def test_knn_ties_resolve_to_lowest_id(precision):
     from embeddingnet_b200.models import BankKNNClassifier
 
     bank, labels = synth.make_numpy(2000, 64, n_classes=50, noise=0.5)
@@ -59,13 +62,83 @@ def test_knn_ties_resolve_to_lowest_id():
         bank[dup] = bank[5]
     q = np.concatenate([bank[[5, 300]], bank[[5]] + np.float32(1e-3)]).astype(np.float32)
     q = np.tile(q, (40, 1))  # > 8 queries -> tensor-core path
-    clf = BankKNNClassifier(n_neighbors=5).fit(bank, labels)
+    clf = BankKNNClassifier(n_neighbors=5, precision=precision).fit(bank, labels)
     _, idx = clf.kneighbors(q, n_neighbors=5)
     _, ri = O.knn_exact(bank, q, 5)
     np.testing.assert_array_equal(idx, ri)
     assert idx[0].tolist() == [5, 10, 700, 1500, 1999]
     _, idx_s = clf.kneighbors(q[:3], n_neighbors=5)  # streaming path
     np.testing.assert_array_equal(idx_s, ri[:3])
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
+def test_certificate_flags_near_ties_and_exact_path_resolves_them(precision):
+    """Twenty bank rows that differ from one another by ~1e-7 relative: far inside the scan's rounding error, so the
+    tensor-core pass cannot order them and its k + 3 candidates need not contain the true top-5.  The certificate
+    must refuse those queries (uncertified > 0) and the float64 brute force must return the oracle's ids."""
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    rng = np.random.RandomState(7)
+    bank, labels = synth.make_numpy(3000, 128, n_classes=30, noise=0.5)
+    base = bank[17].copy()
+    rows = rng.choice(np.arange(100, 3000), size=20, replace=False)
+    for r in rows:
+        bank[r] = base + (rng.randn(128) * 2e-7 * np.abs(base)).astype(np.float32)
+    q = np.tile(base[None, :], (24, 1)).astype(np.float32)
+    q += (rng.randn(24, 128) * 1e-3).astype(np.float32)
+    other, _ = synth.make_numpy(40, 128, seed_noise=synth.SEED_QUERY, n_classes=30, noise=0.5)
+    q = np.concatenate([q, other]).astype(np.float32)
+    _, ri = O.knn_exact(bank, q, 5)
+    clf = BankKNNClassifier(n_neighbors=5, precision=precision).fit(bank, labels)
+    _, idx = clf.kneighbors(q)
+    assert clf.last_uncertified >= 20  # the near-tie queries; the unrelated ones are certified
+    assert clf.last_uncertified <= 30
+    np.testing.assert_array_equal(idx, ri)
+    _, idx_s = clf.kneighbors(q[:8])  # streaming path: fp32 arithmetic, same certificate logic
+    np.testing.assert_array_equal(idx_s, ri[:8])
+    # with certification off the call still runs (no host read) and the far-from-tie queries are right
+    raw = BankKNNClassifier(n_neighbors=5, precision=precision, certify=False).fit(bank, labels)
+    _, idx_r = raw.kneighbors(q)
+    far = 24 + np.flatnonzero(np.arange(40) % 30 != 17)  # class 17 holds the near-duplicates
+    np.testing.assert_array_equal(idx_r[far], ri[far])
+
+
+@pytest.mark.parametrize("N,d,Q,k,excl", [(2000, 64, 7, 5, False), (1500, 100, 64, 3, True), (300, 512, 33, 29, False),
+                                          (3, 16, 5, 5, False)])
+def test_exact_brute_force_kernel(N, d, Q, k, excl):
+    """en_knn_exact_topk (the path behind the certificate) against the float64 oracle, incl. duplicated rows."""
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr
+
+    lib = _lib.load()
+    bank, labels = synth.make_numpy(N, d, n_classes=max(2, N // 50), noise=0.5)
+    if N > 100:
+        bank[N - 1] = bank[3]
+        bank[N // 2] = bank[3]
+    q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=max(2, N // 50), noise=0.5)
+    q[0] = bank[min(3, N - 1)]
+    anchors = np.arange(Q) % N
+    if excl:
+        q = bank[anchors].copy()
+    dev = torch.device("cuda")
+    tb, tq = torch.tensor(bank, device=dev), torch.tensor(q, device=dev)
+    tl = torch.tensor(labels.astype(np.int32), device=dev)
+    tql = torch.tensor(labels[anchors].astype(np.int32), device=dev) if excl else None
+    d2 = torch.empty((Q, k), dtype=torch.float64, device=dev)
+    ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    ws = torch.empty(lib.en_ws_bytes_knn_exact(Q, N, d, k), dtype=torch.uint8, device=dev)
+    _lib.call("en_knn_exact_topk", ptr(tq), Q, d, ptr(tb), N, 1000, k, ptr(tql), ptr(tl) if excl else None,
+              ptr(d2), ptr(ids), ptr(ws), ws.numel(), stream_ptr())
+    got = ids.cpu().numpy()
+    if excl:
+        rd, ri = O.mine_bank_hardest(bank, labels, anchors, k=k)
+    else:
+        rd, ri = O.knn_exact(bank, q, k)
+    kk = ri.shape[1]
+    np.testing.assert_array_equal(got[:, :kk], ri + 1000)
+    np.testing.assert_allclose(np.sqrt(d2.cpu().numpy()[:, :kk]), rd, rtol=1e-6, atol=1e-7)
+    if kk < k:
+        assert np.all(got[:, kk:] == -1)
 
 
 def test_predict_vote_and_accuracy():

@@ -77,8 +77,9 @@ static uint64_t splitmix(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_sms, bool pair = false) {
-  int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
+static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_sms, bool pair = false,
+                    int bf16 = 0) {
+  int dpad = tc::dpad_for(d, bf16);
   std::vector<float> ha(M * d), hb(N * d);
   for (int64_t i = 0; i < M * d; ++i) ha[i] = (float)((double)(splitmix(i + 17) >> 40) / 8388608.0 - 1.0);
   for (int64_t i = 0; i < N * d; ++i) hb[i] = (float)((double)(splitmix(i + 9999991) >> 40) / 8388608.0 - 1.0);
@@ -98,16 +99,26 @@ static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_
   CK(cudaMemcpy(a, ha.data(), M * d * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b, hb.data(), N * d * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(out, 0xFF, M * N * 4));
-  CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
-  CK(tc::launch_split(b, N, d, d, dpad, bhi, blo, nb, 0));
   CUtensorMap tah, tal, tbh, tbl;
   const int bbox = pair ? tc::BN / 2 : tc::BN;
-  if (tc::make_plane_tmap(&tah, ahi, M, dpad) || tc::make_plane_tmap(&tal, alo, M, dpad) ||
-      tc::make_plane_tmap(&tbh, bhi, N, dpad, bbox) || tc::make_plane_tmap(&tbl, blo, N, dpad, bbox)) {
-    printf("tensor map encode failed\n");
-    return 1;
+  if (bf16) {  // planes allocated at fp32 size: more than enough for bf16
+    CK(tc::launch_split_bf16(a, M, d, d, dpad, ahi, alo, na, 0));
+    CK(tc::launch_split_bf16(b, N, d, d, dpad, bhi, blo, nb, 0));
+    if (tc::make_plane_tmap_bf16(&tah, ahi, M, dpad) || tc::make_plane_tmap_bf16(&tal, alo, M, dpad) ||
+        tc::make_plane_tmap_bf16(&tbh, bhi, N, dpad) || tc::make_plane_tmap_bf16(&tbl, blo, N, dpad)) {
+      printf("tensor map encode failed\n");
+      return 1;
+    }
+  } else {
+    CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
+    CK(tc::launch_split(b, N, d, d, dpad, bhi, blo, nb, 0));
+    if (tc::make_plane_tmap(&tah, ahi, M, dpad) || tc::make_plane_tmap(&tal, alo, M, dpad) ||
+        tc::make_plane_tmap(&tbh, bhi, N, dpad, bbox) || tc::make_plane_tmap(&tbl, blo, N, dpad, bbox)) {
+      printf("tensor map encode failed\n");
+      return 1;
+    }
   }
-  tc::Shape sh = tc::make_shape(M, N, d, 1 << 30, passes);
+  tc::Shape sh = tc::make_shape(M, N, d, 1 << 30, passes, bf16);
   EpStore::Params ep{out, N, N};
   if (pair) CK(tc::pair::launch<EpStore>(tah, tal, tbh, tbl, sh, ep, num_sms, 0));
   else CK(tc::launch<EpStore>(tah, tal, tbh, tbl, sh, ep, num_sms, 0));
@@ -134,18 +145,19 @@ static int run_case(int64_t M, int64_t N, int d, int passes, bool same, int num_
   }
   // scale: |a||b| ~ d/3 for uniform(-1,1)
   double scale = d / 3.0;
-  double tol = passes == 1 ? 2e-3 : 8e-6;
+  double tol = bf16 ? (passes == 1 ? 2e-2 : 6e-5) : (passes == 1 ? 2e-3 : 8e-6);
   if (max_abs / scale > tol) bad = 1;
-  printf("%s M=%-5lld N=%-5lld d=%-4d passes=%d same=%d: max_abs_err=%.3e (rel to |a||b| %.3e) nan=%lld worst@(%lld,%lld) got=%.7f ref=%.7f  %s\n",
-         pair ? "pair" : "case", (long long)M, (long long)N, d, passes, (int)same, max_abs, max_abs / scale, (long long)nan,
+  printf("%s%s M=%-5lld N=%-5lld d=%-4d passes=%d same=%d: max_abs_err=%.3e (rel to |a||b| %.3e) nan=%lld worst@(%lld,%lld) got=%.7f ref=%.7f  %s\n",
+         pair ? "pair" : "case", bf16 ? "-bf16" : "", (long long)M, (long long)N, d, passes, (int)same, max_abs, max_abs / scale, (long long)nan,
          (long long)(worst / N), (long long)(worst % N), ho[worst], hr[worst], (bad || nan) ? "FAIL" : "ok");
   cudaFree(a); cudaFree(b); cudaFree(ahi); cudaFree(alo); cudaFree(bhi); cudaFree(blo);
   cudaFree(na); cudaFree(nb); cudaFree(out); cudaFree(ref);
   return (bad || nan) ? 1 : 0;
 }
 
-static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int num_sms, bool pair = false) {
-  int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
+static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int num_sms, bool pair = false,
+                      int bf16 = 0) {
+  int dpad = tc::dpad_for(d, bf16);
   float *a, *ahi, *alo, *na, *out;
   CK(cudaMalloc(&a, M * d * 4));
   CK(cudaMalloc(&ahi, M * dpad * 4));
@@ -154,13 +166,21 @@ static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int
   std::vector<float> ha(M * d);
   for (int64_t i = 0; i < M * d; ++i) ha[i] = (float)((double)(splitmix(i + 17) >> 40) / 8388608.0 - 1.0);
   CK(cudaMemcpy(a, ha.data(), M * d * 4, cudaMemcpyHostToDevice));
-  CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
   CUtensorMap tah, tal, tbh, tbl;
-  tc::make_plane_tmap(&tah, ahi, M, dpad);
-  tc::make_plane_tmap(&tal, alo, M, dpad);
-  tc::make_plane_tmap(&tbh, ahi, M, dpad, pair ? tc::BN / 2 : tc::BN);
-  tc::make_plane_tmap(&tbl, alo, M, dpad, pair ? tc::BN / 2 : tc::BN);
-  tc::Shape sh = tc::make_shape(M, N, d, n_splits, passes);
+  if (bf16) {
+    CK(tc::launch_split_bf16(a, M, d, d, dpad, ahi, alo, na, 0));
+    tc::make_plane_tmap_bf16(&tah, ahi, M, dpad);
+    tc::make_plane_tmap_bf16(&tal, alo, M, dpad);
+    tc::make_plane_tmap_bf16(&tbh, ahi, M, dpad);
+    tc::make_plane_tmap_bf16(&tbl, alo, M, dpad);
+  } else {
+    CK(tc::launch_split(a, M, d, d, dpad, ahi, alo, na, 0));
+    tc::make_plane_tmap(&tah, ahi, M, dpad);
+    tc::make_plane_tmap(&tal, alo, M, dpad);
+    tc::make_plane_tmap(&tbh, ahi, M, dpad, pair ? tc::BN / 2 : tc::BN);
+    tc::make_plane_tmap(&tbl, alo, M, dpad, pair ? tc::BN / 2 : tc::BN);
+  }
+  tc::Shape sh = tc::make_shape(M, N, d, n_splits, passes, bf16);
   CK(cudaMalloc(&out, M * sh.n_splits * tc::EPI_H * 4));
   EpRowMax::Params ep{out, sh.n_splits};
   cudaEvent_t e0, e1;
@@ -181,8 +201,8 @@ static void time_case(int64_t M, int64_t N, int d, int passes, int n_splits, int
   cudaEventElapsedTime(&ms, e0, e1);
   double us = ms * 1000.0 / iters;
   double flops = 2.0 * M * N * d;
-  printf("%s M=%lld N=%lld d=%d passes=%d n_splits=%d items=%d: %.2f us/launch  -> %.1f TFLOP/s algorithmic, %.1f TFLOP/s TF32 issued\n",
-         pair ? "time-pair" : "time", (long long)M, (long long)N, d, passes, sh.n_splits, sh.tiles_m * sh.n_splits, us, flops / us * 1e-6,
+  printf("%s%s M=%lld N=%lld d=%d passes=%d n_splits=%d items=%d: %.2f us/launch  -> %.1f TFLOP/s algorithmic, %.1f TFLOP/s issued\n",
+         pair ? "time-pair" : "time", bf16 ? "-bf16" : "", (long long)M, (long long)N, d, passes, sh.n_splits, sh.tiles_m * sh.n_splits, us, flops / us * 1e-6,
          flops * passes / us * 1e-6);
   cudaFree(a); cudaFree(ahi); cudaFree(alo); cudaFree(na); cudaFree(out);
 }
@@ -203,6 +223,13 @@ int main(int argc, char** argv) {
   fails += run_case(1000, 1000, 512, 1, true, sms);
   fails += run_case(1000, 1000, 512, 3, true, sms);
   fails += run_case(2048, 4096, 256, 3, false, sms);
+  // BF16 planes (kind::f16), 1 and 3 passes
+  fails += run_case(128, 128, 64, 1, false, sms, false, 1);
+  fails += run_case(128, 128, 64, 3, false, sms, false, 1);
+  fails += run_case(256, 384, 128, 3, false, sms, false, 1);
+  fails += run_case(300, 200, 100, 3, false, sms, false, 1);
+  fails += run_case(1000, 1000, 512, 3, true, sms, false, 1);
+  fails += run_case(2048, 4096, 256, 3, false, sms, false, 1);
   if (argc > 1) {
     fails += run_case(256, 128, 32, 1, false, sms, true);
     fails += run_case(256, 128, 32, 3, false, sms, true);
@@ -218,6 +245,9 @@ int main(int argc, char** argv) {
     time_case(4096, 4096, 512, 1, 32, sms);
     time_case(16384, 16384, 512, 3, 16, sms);
     time_case(16384, 16384, 512, 1, 16, sms);
+    time_case(4096, 4096, 512, 3, 32, sms, false, 1);
+    time_case(16384, 16384, 512, 3, 16, sms, false, 1);
+    time_case(16384, 16384, 512, 1, 16, sms, false, 1);
     if (argc > 1) {
       time_case(4096, 4096, 512, 3, 32, sms, true);
       time_case(16384, 16384, 512, 3, 16, sms, true);
