@@ -55,27 +55,31 @@ __device__ __noinline__ double exact_d2(const float* __restrict__ e, int d, int6
 // =====================================================================================================
 // Batch-hard
 // =====================================================================================================
-// Candidate record per (anchor row, column tile, column half): the two largest same-label and the two smallest
-// other-label proxies t = |b|^2 - 2 a.b (monotone in the distance for a fixed anchor).
+// Candidate record per (anchor row, other tile T, slot): the two largest same-label and the two smallest
+// other-label proxies t = |b|^2 - 2 a.b (monotone in the distance for a fixed anchor).  Each float carries the
+// candidate's index INSIDE tile T (0..127) in its 7 lowest mantissa bits, so the running top-2 is three FMNMX per
+// element instead of compare + select chains on (value, index) pairs, and a record is 16 bytes.  The truncation
+// (< 2^-16 |t|) is part of the error band the finalize kernel re-evaluates exactly.
 struct BhCand {
   float p1, p2, n1, n2;
-  int p1i, p2i, n1i, n2i;
 };
-
-// branch-free running top-2 (value, index); masked elements carry -kBig / +kBig and never win
-__device__ __forceinline__ void top2_max(float& v1, int& i1, float& v2, int& i2, float t, int c) {
-  const bool g1 = t > v1, g2 = t > v2;
-  v2 = g1 ? v1 : (g2 ? t : v2);
-  i2 = g1 ? i1 : (g2 ? c : i2);
-  v1 = g1 ? t : v1;
-  i1 = g1 ? c : i1;
+constexpr unsigned kKeyMask = 0xFFFFFF80u;
+__device__ __forceinline__ float bh_pack(float t, int in_tile) {
+  return __uint_as_float((__float_as_uint(t) & kKeyMask) | static_cast<unsigned>(in_tile));
 }
-__device__ __forceinline__ void top2_min(float& v1, int& i1, float& v2, int& i2, float t, int c) {
-  const bool g1 = t < v1, g2 = t < v2;
-  v2 = g1 ? v1 : (g2 ? t : v2);
-  i2 = g1 ? i1 : (g2 ? c : i2);
-  v1 = g1 ? t : v1;
-  i1 = g1 ? c : i1;
+__device__ __forceinline__ bool bh_valid(float key) { return fabsf(key) < 1.0e38f; }
+__device__ __forceinline__ int bh_index(float key, int tile) {
+  return bh_valid(key) ? tile * tc::BN + static_cast<int>(__float_as_uint(key) & 0x7Fu) : -1;
+}
+
+// running top-2 of packed keys; masked elements carry -kBig / +kBig and never win
+__device__ __forceinline__ void top2_max(float& v1, float& v2, float k) {
+  v2 = fmaxf(v2, fminf(v1, k));
+  v1 = fmaxf(v1, k);
+}
+__device__ __forceinline__ void top2_min(float& v1, float& v2, float k) {
+  v2 = fminf(v2, fmaxf(v1, k));
+  v1 = fminf(v1, k);
 }
 
 // Symmetric schedule: only tiles (I, J) with J >= I are computed.  A strictly-upper tile serves both the anchors
@@ -95,6 +99,7 @@ struct EpBatchHard {
   };
   struct Row {
     int32_t la;
+    int32_t lmin, lmax;  // label range of the 32 rows this warp serves
     float na;
     int tile_m;
     BhCand c;
@@ -104,16 +109,16 @@ struct EpBatchHard {
   static __device__ void reset(BhCand& c) {
     c.p1 = c.p2 = -kBig;
     c.n1 = c.n2 = kBig;
-    c.p1i = c.p2i = c.n1i = c.n2i = -1;
   }
   static __device__ void store(BhCand* out, const BhCand& c) {
-    reinterpret_cast<float4*>(out)[0] = make_float4(c.p1, c.p2, c.n1, c.n2);
-    reinterpret_cast<int4*>(out)[1] = make_int4(c.p1i, c.p2i, c.n1i, c.n2i);
+    *reinterpret_cast<float4*>(out) = make_float4(c.p1, c.p2, c.n1, c.n2);
   }
   static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int tile_m,
                                     int) {
     r.la = valid ? p.labels[row] : 0;
     r.na = valid ? p.norms[row] : 0.f;
+    r.lmin = __reduce_min_sync(0xffffffffu, valid ? r.la : 0x7fffffff);
+    r.lmax = __reduce_max_sync(0xffffffffu, valid ? r.la : static_cast<int32_t>(0x80000000));
     r.tile_m = tile_m;
     reset(r.c);
   }
@@ -123,12 +128,34 @@ struct EpBatchHard {
     tc::stage_columns(ctx, p.norms, p.labels, col0, p.B);
     const float4* n4 = reinterpret_cast<const float4*>(ctx.wf);
     const int4* l4 = reinterpret_cast<const int4*>(ctx.wi);
-    const int c0 = static_cast<int>(col0);
-    const int64_t row0 = row - ctx.lane;  // first row served by this warp
-    // ---- row view.  Rows and columns are tiled in aligned groups of 32, so the diagonal can only fall into the
-    // chunk whose first column equals this warp's first row.
-    const bool edge = (col0 + 32 > p.B) || (col0 == row0);
-    if (!edge) {
+    const int jt0 = static_cast<int>(col0 % tc::BN);  // first column of the chunk inside its tile
+    const int64_t row0 = row - ctx.lane;              // first row served by this warp
+    // Rows and columns are tiled in aligned groups of 32, so the diagonal can only fall into the chunk whose first
+    // column equals this warp's first row.
+    const bool edge = (col0 + 32 > p.B) || (col0 == row0) || (row0 + 32 > p.B);
+    // No label shared between this warp's rows and the chunk's columns (always true off the diagonal when the
+    // batch is class-major, as P x K batches are): every element is a negative, no label compares needed.
+    const int32_t lcol = ctx.wi[ctx.lane];
+    const int32_t cmin = __reduce_min_sync(0xffffffffu, lcol), cmax = __reduce_max_sync(0xffffffffu, lcol);
+    const bool disjoint = !edge && (cmax < r.lmin || cmin > r.lmax);
+    const int tile_n = static_cast<int>(col0 / tc::BN);
+    const bool col_view = tile_n > r.tile_m;  // strictly-upper tiles also serve the column anchors
+    float* sc = reinterpret_cast<float*>(ctx.smem) + (ctx.quarter + 4 * ctx.half) * 1024;
+    if (col_view) __syncwarp();
+    if (disjoint) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 nb = n4[g];
+        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = g * 4 + u;
+          top2_min(r.c.n1, r.c.n2, bh_pack(fmaf(-2.f, dot[j], nbv[u]), jt0 + j));
+          // column view: transpose through shared memory (skewed: conflict free), already packed with the ROW index
+          if (col_view) sc[ctx.lane * 32 + ((j + ctx.lane) & 31)] = bh_pack(fmaf(-2.f, dot[j], r.na), ctx.erow);
+        }
+      }
+    } else if (!edge) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 nb = n4[g];
@@ -138,10 +165,11 @@ struct EpBatchHard {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = g * 4 + u;
-          const float t = fmaf(-2.f, dot[j], nbv[u]);
+          const float k = bh_pack(fmaf(-2.f, dot[j], nbv[u]), jt0 + j);
           const bool same = lbv[u] == r.la;
-          top2_max(r.c.p1, r.c.p1i, r.c.p2, r.c.p2i, same ? t : -kBig, c0 + j);
-          top2_min(r.c.n1, r.c.n1i, r.c.n2, r.c.n2i, same ? kBig : t, c0 + j);
+          top2_max(r.c.p1, r.c.p2, same ? k : -kBig);
+          top2_min(r.c.n1, r.c.n2, same ? kBig : k);
+          if (col_view) sc[ctx.lane * 32 + ((j + ctx.lane) & 31)] = bh_pack(fmaf(-2.f, dot[j], r.na), ctx.erow);
         }
       }
     } else {
@@ -149,36 +177,34 @@ struct EpBatchHard {
       for (int j = 0; j < 32; ++j) {
         const int64_t c = col0 + j;
         const bool ok = c < p.B && c != row;
-        const float t = fmaf(-2.f, dot[j], ctx.wf[j]);
+        const float k = bh_pack(fmaf(-2.f, dot[j], ctx.wf[j]), jt0 + j);
         const bool same = ctx.wi[j] == r.la;
-        top2_max(r.c.p1, r.c.p1i, r.c.p2, r.c.p2i, (ok && same) ? t : -kBig, c0 + j);
-        top2_min(r.c.n1, r.c.n1i, r.c.n2, r.c.n2i, (ok && !same) ? t : kBig, c0 + j);
+        top2_max(r.c.p1, r.c.p2, (ok && same) ? k : -kBig);
+        top2_min(r.c.n1, r.c.n2, (ok && !same) ? k : kBig);
+        if (col_view) sc[ctx.lane * 32 + ((j + ctx.lane) & 31)] = bh_pack(fmaf(-2.f, dot[j], r.na), ctx.erow);
       }
     }
-    // ---- column view (strictly-upper tiles only): transpose the 32x32 block through shared memory so that
-    // lane c owns column col0 + c and scans this warp's 32 rows.
-    const int tile_n = static_cast<int>(col0 / tc::BN);
-    if (tile_n > r.tile_m) {
-      float* sc = reinterpret_cast<float*>(ctx.smem) + (ctx.quarter + 4 * ctx.half) * 1024;
+    // ---- column view: lane c owns column col0 + c and scans this warp's 32 rows.
+    if (col_view) {
       __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sc[ctx.lane * 32 + ((j + ctx.lane) & 31)] = fmaf(-2.f, dot[j], r.na);
-      __syncwarp();
-      const int32_t lc = ctx.wi[ctx.lane];
-      const bool col_ok = col0 + ctx.lane < p.B;
       BhCand cc;
       reset(cc);
+      if (disjoint) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) top2_min(cc.n1, cc.n2, sc[i * 32 + ((ctx.lane + i) & 31)]);
+      } else {
+        const bool col_ok = col0 + ctx.lane < p.B;
 #pragma unroll 8
-      for (int i = 0; i < 32; ++i) {
-        const float v = sc[i * 32 + ((ctx.lane + i) & 31)];
-        const int32_t li = __shfl_sync(0xffffffffu, r.la, i);
-        const bool ok = col_ok && (row0 + i < p.B);
-        const bool same = li == lc;
-        const int ri = static_cast<int>(row0) + i;
-        top2_max(cc.p1, cc.p1i, cc.p2, cc.p2i, (ok && same) ? v : -kBig, ri);
-        top2_min(cc.n1, cc.n1i, cc.n2, cc.n2i, (ok && !same) ? v : kBig, ri);
+        for (int i = 0; i < 32; ++i) {
+          const float v = sc[i * 32 + ((ctx.lane + i) & 31)];
+          const int32_t li = __shfl_sync(0xffffffffu, r.la, i);
+          const bool ok = col_ok && (row0 + i < p.B);
+          const bool same = li == lcol;
+          top2_max(cc.p1, cc.p2, (ok && same) ? v : -kBig);
+          top2_min(cc.n1, cc.n2, (ok && !same) ? v : kBig);
+        }
       }
-      if (col_ok)
+      if (col0 + ctx.lane < p.B)
         store(p.cand + ((col0 + ctx.lane) * p.tiles_n + r.tile_m) * BH_SLOTS + ctx.quarter, cc);
     }
   }
@@ -246,13 +272,13 @@ __device__ __noinline__ void red_axpy_diff(float* __restrict__ gemb, const float
 // tree (the result does not depend on which block finishes last).  Called by all 256 threads of every block.
 __device__ __forceinline__ void block_mean(double hinge, double* sh, double* __restrict__ partial,
                                            unsigned* __restrict__ counter, float* __restrict__ loss, int64_t B) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   __shared__ bool is_last;
   if (lane == 0) sh[warp] = hinge;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += sh[w];
+    for (int w = 0; w < nwarps; ++w) s += sh[w];
     partial[blockIdx.x] = s;
     __threadfence();
     is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
@@ -268,7 +294,7 @@ __device__ __forceinline__ void block_mean(double hinge, double* sh, double* __r
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += sh[w];
+      for (int w = 0; w < nwarps; ++w) s += sh[w];
       loss[0] = static_cast<float>(s / static_cast<double>(B));
       *counter = 0;  // re-armed for the next call on this workspace
     }
@@ -301,7 +327,7 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
     float bp = -kBig, bn = kBig;
     for (int t = lane; t < n_cand; t += 32) {
       if (!slot_valid(t)) continue;
-      const float4 v = reinterpret_cast<const float4*>(mine + t)[0];
+      const float4 v = *reinterpret_cast<const float4*>(mine + t);
       bp = fmaxf(bp, v.x);  // p1 >= p2
       bn = fminf(bn, v.z);  // n1 <= n2
     }
@@ -317,11 +343,10 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
     for (int t0 = 0; t0 < n_cand; t0 += 32) {
       const int t = t0 + lane;
       float4 v = make_float4(-kBig, -kBig, kBig, kBig);
-      int4 ix = make_int4(-1, -1, -1, -1);
-      if (slot_valid(t)) {
-        v = __ldcg(reinterpret_cast<const float4*>(mine + t));
-        ix = __ldcg(reinterpret_cast<const int4*>(mine + t) + 1);
-      }
+      if (slot_valid(t)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
+      // the index inside the record's tile rides in the low mantissa bits of each proxy
+      const int4 ix = make_int4(bh_index(v.x, t >> 2), bh_index(v.y, t >> 2), bh_index(v.z, t >> 2),
+                                bh_index(v.w, t >> 2));
       // the four norm loads are independent: issue them together, ahead of the dependent ballots
       const float nb0 = ix.x >= 0 ? __ldg(&norms[ix.x]) : 0.f;
       const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
@@ -388,8 +413,9 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
 // registers, the 16 candidate norms, then the anchor / positive / negative rows (kept in registers and reused for
 // the two exact distances AND the gradient).  Anything unusual -- several contenders inside the error band, no
 // negative at all -- takes the generic per-candidate path on the same registers.
+constexpr int FF_WARPS = 4;  // anchors per block: small blocks so that one slow warp holds back few others
 template <bool kGrad, int DV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FF_WARPS * 32, 8)
 batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                 const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B,
                                 int tiles_n, float margin, int squared, int soft, float band_c,
@@ -401,29 +427,20 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
   __shared__ double sh[8];
   constexpr int d = 128 * DV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * FF_WARPS + warp;
   double hinge = 0.0;
   if (row < B) {
     const int n_cand = tiles_n * BH_SLOTS;  // <= 128
     const int my_tile = static_cast<int>(row / tc::BM);
     const BhCand* mine = cand + row * n_cand;
-    // the anchor's own row is needed whatever happens: issue it with the records
-    const float4* arow = reinterpret_cast<const float4*>(emb + row * d) + lane;
-    float4 a[DV];
-#pragma unroll
-    for (int i = 0; i < DV; ++i) a[i] = arow[32 * i];
     const float na = norms[row];
     float4 v[4];
-    int4 ix[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int t = lane + 32 * u;
       v[u] = make_float4(-kBig, -kBig, kBig, kBig);
-      ix[u] = make_int4(-1, -1, -1, -1);
-      if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) {  // slots 2,3: column view, tiles left of the anchor's
+      if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile))  // slots 2,3: column view, tiles left of the anchor's
         v[u] = __ldcg(reinterpret_cast<const float4*>(mine + t));
-        ix[u] = __ldcg(reinterpret_cast<const int4*>(mine + t) + 1);
-      }
     }
     float bp = fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x));  // p1 >= p2, n1 <= n2 inside a record
     float bn = fminf(fminf(v[0].z, v[1].z), fminf(v[2].z, v[3].z));
@@ -432,66 +449,98 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
       bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
       bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
-    float nb[4][4];
+    // Contenders inside the error band of the best proxy.  The band needs the candidate's norm; the proxy itself
+    // bounds it (t = |b|^2 - 2 a.b >= |b|^2 - 2 |a||b|  =>  |b| <= |a| + sqrt(|a|^2 + t)), which saves a dependent
+    // gather of 16 norms per lane at the price of a somewhat wider band (a few more exact evaluations).  The index
+    // inside the record's tile rides in the low mantissa bits.  Each lane queues up to two contenders per kind.
+    int pc = 0, nc = 0, pi0 = -1, pi1 = -1, ni0 = -1, ni1 = -1;
+    const float sa = sqrtf(na);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      nb[u][0] = ix[u].x >= 0 ? __ldg(&norms[ix[u].x]) : 0.f;
-      nb[u][1] = ix[u].y >= 0 ? __ldg(&norms[ix[u].y]) : 0.f;
-      nb[u][2] = ix[u].z >= 0 ? __ldg(&norms[ix[u].z]) : 0.f;
-      nb[u][3] = ix[u].w >= 0 ? __ldg(&norms[ix[u].w]) : 0.f;
-    }
-    // contenders inside the error band of the best proxy
-    int pc = 0, nc = 0, pi = -1, ni = -1;
+      const int tile = (lane + 32 * u) >> 2;
+      const float key[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (ix[u].x >= 0 && v[u].x >= bp - (band_c * (na + nb[u][0]) + 1e-30f)) { ++pc; pi = ix[u].x; }
-      if (ix[u].y >= 0 && v[u].y >= bp - (band_c * (na + nb[u][1]) + 1e-30f)) { ++pc; pi = ix[u].y; }
-      if (ix[u].z >= 0 && v[u].z <= bn + (band_c * (na + nb[u][2]) + 1e-30f)) { ++nc; ni = ix[u].z; }
-      if (ix[u].w >= 0 && v[u].w <= bn + (band_c * (na + nb[u][3]) + 1e-30f)) { ++nc; ni = ix[u].w; }
+      for (int e = 0; e < 4; ++e) {
+        if (!bh_valid(key[e])) continue;
+        const float sb = sa + sqrtf(fmaxf(na + key[e], 0.f)) * 1.0001f;
+        const float band = band_c * (na + sb * sb) + 1e-30f;
+        if (e < 2) {
+          if (key[e] >= bp - band) { pi1 = pi0; pi0 = bh_index(key[e], tile); ++pc; }
+        } else {
+          if (key[e] <= bn + band) { ni1 = ni0; ni0 = bh_index(key[e], tile); ++nc; }
+        }
+      }
     }
-    const int tp = __reduce_add_sync(0xffffffffu, pc), tn = __reduce_add_sync(0xffffffffu, nc);
     BhPick pos{-1.0, -1}, neg{1e300, -1};
-    float4 pr[DV], nr[DV];
-    bool rows_cached = false;
-    if (tp <= 1 && tn == 1) {
-      // the usual case: one candidate each (tp == 0: the anchor is alone in its class)
-      const int p_idx = tp ? __shfl_sync(0xffffffffu, pi, __ffs(__ballot_sync(0xffffffffu, pc > 0)) - 1) : -1;
-      const int n_idx = __shfl_sync(0xffffffffu, ni, __ffs(__ballot_sync(0xffffffffu, nc > 0)) - 1);
-      const float4* prow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(p_idx >= 0 ? p_idx : row) * d) + lane;
-      const float4* nrow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(n_idx) * d) + lane;
+    float4 a[DV], pr[DV], nr[DV];
+    int rounds = 0;
+    const bool overflow = __any_sync(0xffffffffu, pc > 2 || nc > 2);
+    const bool no_neg = !__any_sync(0xffffffffu, nc > 0);
+    if (!overflow && !no_neg) {
+      // Each round re-evaluates one positive and one negative contender exactly, all row loads of the round in one
+      // batch.  The usual case is a single round (one contender each; none for an anchor alone in its class).
+      const float4* arow = reinterpret_cast<const float4*>(emb + row * d) + lane;
 #pragma unroll
-      for (int i = 0; i < DV; ++i) pr[i] = prow[32 * i];
+      for (int i = 0; i < DV; ++i) a[i] = arow[32 * i];
+#pragma unroll 1
+      for (;;) {
+        const unsigned pm = __ballot_sync(0xffffffffu, pc > 0), nm = __ballot_sync(0xffffffffu, nc > 0);
+        if ((pm | nm) == 0) break;
+        int p_idx = -1, n_idx = -1;
+        if (pm) {
+          const int src = __ffs(pm) - 1;
+          p_idx = __shfl_sync(0xffffffffu, pi0, src);
+          if (lane == src) { pi0 = pi1; --pc; }
+        }
+        if (nm) {
+          const int src = __ffs(nm) - 1;
+          n_idx = __shfl_sync(0xffffffffu, ni0, src);
+          if (lane == src) { ni0 = ni1; --nc; }
+        }
+        const float4* prow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(p_idx >= 0 ? p_idx : row) * d) + lane;
+        const float4* nrow = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(n_idx >= 0 ? n_idx : row) * d) + lane;
 #pragma unroll
-      for (int i = 0; i < DV; ++i) nr[i] = nrow[32 * i];
-      double dp = 0.0, dn = 0.0;
+        for (int i = 0; i < DV; ++i) pr[i] = prow[32 * i];
 #pragma unroll
-      for (int i = 0; i < DV; ++i) {
-        // same element order as exact_d2(): c = lane * 4 + 128 * i + {0, 1, 2, 3}
-        double t;
-        t = static_cast<double>(a[i].x) - static_cast<double>(pr[i].x); dp = fma(t, t, dp);
-        t = static_cast<double>(a[i].y) - static_cast<double>(pr[i].y); dp = fma(t, t, dp);
-        t = static_cast<double>(a[i].z) - static_cast<double>(pr[i].z); dp = fma(t, t, dp);
-        t = static_cast<double>(a[i].w) - static_cast<double>(pr[i].w); dp = fma(t, t, dp);
-        t = static_cast<double>(a[i].x) - static_cast<double>(nr[i].x); dn = fma(t, t, dn);
-        t = static_cast<double>(a[i].y) - static_cast<double>(nr[i].y); dn = fma(t, t, dn);
-        t = static_cast<double>(a[i].z) - static_cast<double>(nr[i].z); dn = fma(t, t, dn);
-        t = static_cast<double>(a[i].w) - static_cast<double>(nr[i].w); dn = fma(t, t, dn);
+        for (int i = 0; i < DV; ++i) nr[i] = nrow[32 * i];
+        double dp = 0.0, dn = 0.0;
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+          // same element order as exact_d2(): c = lane * 4 + 128 * i + {0, 1, 2, 3}
+          double t;
+          t = static_cast<double>(a[i].x) - static_cast<double>(pr[i].x); dp = fma(t, t, dp);
+          t = static_cast<double>(a[i].y) - static_cast<double>(pr[i].y); dp = fma(t, t, dp);
+          t = static_cast<double>(a[i].z) - static_cast<double>(pr[i].z); dp = fma(t, t, dp);
+          t = static_cast<double>(a[i].w) - static_cast<double>(pr[i].w); dp = fma(t, t, dp);
+          t = static_cast<double>(a[i].x) - static_cast<double>(nr[i].x); dn = fma(t, t, dn);
+          t = static_cast<double>(a[i].y) - static_cast<double>(nr[i].y); dn = fma(t, t, dn);
+          t = static_cast<double>(a[i].z) - static_cast<double>(nr[i].z); dn = fma(t, t, dn);
+          t = static_cast<double>(a[i].w) - static_cast<double>(nr[i].w); dn = fma(t, t, dn);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dp += __shfl_xor_sync(0xffffffffu, dp, o);
+          dn += __shfl_xor_sync(0xffffffffu, dn, o);
+        }
+        if (p_idx >= 0 && (pos.idx < 0 || dp > pos.d2 || (dp == pos.d2 && p_idx < pos.idx))) pos = BhPick{dp, p_idx};
+        if (n_idx >= 0 && (neg.idx < 0 || dn < neg.d2 || (dn == neg.d2 && n_idx < neg.idx))) neg = BhPick{dn, n_idx};
+        ++rounds;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dp += __shfl_xor_sync(0xffffffffu, dp, o);
-        dn += __shfl_xor_sync(0xffffffffu, dn, o);
-      }
-      if (p_idx >= 0) pos = BhPick{dp, p_idx};
-      neg = BhPick{dn, n_idx};
-      rows_cached = true;
     } else {
+      // three contenders queued on one lane, or no negative at all: per-candidate path with exact norms
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
-        bh_consider<true>(pos, emb, d, na, nb[u][0], row, bp, v[u].x, ix[u].x, lane, band_c);
-        bh_consider<true>(pos, emb, d, na, nb[u][1], row, bp, v[u].y, ix[u].y, lane, band_c);
-        bh_consider<false>(neg, emb, d, na, nb[u][2], row, bn, v[u].z, ix[u].z, lane, band_c);
-        bh_consider<false>(neg, emb, d, na, nb[u][3], row, bn, v[u].w, ix[u].w, lane, band_c);
+        const int tile = (lane + 32 * u) >> 2;
+        const int4 ix = make_int4(bh_index(v[u].x, tile), bh_index(v[u].y, tile), bh_index(v[u].z, tile),
+                                  bh_index(v[u].w, tile));
+        const float nb0 = ix.x >= 0 ? __ldg(&norms[ix.x]) : 0.f;
+        const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
+        const float nb2 = ix.z >= 0 ? __ldg(&norms[ix.z]) : 0.f;
+        const float nb3 = ix.w >= 0 ? __ldg(&norms[ix.w]) : 0.f;
+        bh_consider<true>(pos, emb, d, na, nb0, row, bp, v[u].x, ix.x, lane, band_c);
+        bh_consider<true>(pos, emb, d, na, nb1, row, bp, v[u].y, ix.y, lane, band_c);
+        bh_consider<false>(neg, emb, d, na, nb2, row, bn, v[u].z, ix.z, lane, band_c);
+        bh_consider<false>(neg, emb, d, na, nb3, row, bn, v[u].w, ix.w, lane, band_c);
       }
       if (neg.idx < 0) {  // no other-label row at all: Moindrot's degenerate row maximum (see the generic kernel)
         BhPick rmx{-1.0, -1};
@@ -503,6 +552,8 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
         neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
       }
     }
+    // a single round leaves the winners' rows in registers for the gradient
+    const bool rows_cached = rounds == 1;
     const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
     const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
     const double z = hp - hn;
@@ -1074,7 +1125,7 @@ size_t en_ws_bytes_batch_hard(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles_n = static_cast<size_t>((B + tc::BN - 1) / tc::BN);
   return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * BH_SLOTS * sizeof(BhCand)) +
-         align_up(static_cast<size_t>((B + 7) / 8) * sizeof(double)) + align_up(sizeof(unsigned));
+         align_up(static_cast<size_t>((B + FF_WARPS - 1) / FF_WARPS) * sizeof(double)) + align_up(sizeof(unsigned));
 }
 
 static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
@@ -1094,7 +1145,7 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   const int tiles_n = static_cast<int>((B + tc::BN - 1) / tc::BN);
   BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * BH_SLOTS);
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
-  double* partial = w.take<double>(blocks);
+  double* partial = w.take<double>((B + FF_WARPS - 1) / FF_WARPS);
   unsigned* counter = w.take<unsigned>(1);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "%s: workspace too small or misaligned", who);
   // the operand split also zeroes the gradient buffer and the finalize counter (no memset nodes in the step)
@@ -1102,7 +1153,9 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   // |dot~ - dot| <= c |a||b| with c = 3 * 2^-16 (dropped lo*lo and residual products of the BF16 split) +
   // 2^-22 (d/16 + 1) (accumulator truncation): 5.4e-5 at d = 512 (measured maximum: 4e-6).  Proxy = |b|^2 - 2 dot,
   // |a||b| <= (|a|^2 + |b|^2) / 2, best and contender both off by it: band = 2 c (|a|^2 + |b|^2).
-  const float band_c = 2.0f * (3.0f / 65536.0f + (o.dpad / 16 + 1) / 4194304.0f);
+  // The epilogue also truncates 7 mantissa bits of each proxy (index packing): < 2^-16 |t|, |t| <= 2 (|a|^2 +
+  // |b|^2), on both sides: + 2^-14.
+  const float band_c = 2.0f * (3.0f / 65536.0f + (o.dpad / 16 + 1) / 4194304.0f) + 1.0f / 16384.0f;
   tc::Shape sh = tc::make_shape_symmetric(B, d, 3, 1);  // upper-triangular tiles, one per work item; BF16 planes
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
   prof_begin(st);
@@ -1111,11 +1164,11 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   ++launch_counter();
   const bool fast = d % 128 == 0 && d <= 512 && tiles_n * BH_SLOTS <= 128 &&
                     (reinterpret_cast<uintptr_t>(emb) & 15) == 0;
-#define EN_BH_FAST(G, DV)                                                                                          \
-  batch_hard_finalize_fast_kernel<G, DV><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, tiles_n, margin,   \
-                                                                 squared, soft, band_c, hp_idx, hn_idx, hp, hn,    \
-                                                                 coef, partial, counter, loss, G ? gloss : nullptr, \
-                                                                 G ? gemb : nullptr)
+  const unsigned fblocks = static_cast<unsigned>((B + FF_WARPS - 1) / FF_WARPS);
+#define EN_BH_FAST(G, DV)                                                                                       \
+  batch_hard_finalize_fast_kernel<G, DV><<<fblocks, FF_WARPS * 32, 0, st>>>(                                      \
+      emb, labels, o.norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial, \
+      counter, loss, G ? gloss : nullptr, G ? gemb : nullptr)
   if (fast && gemb) {
     if (d == 128) EN_BH_FAST(true, 1);
     else if (d == 256) EN_BH_FAST(true, 2);
