@@ -43,6 +43,7 @@ SIGNATURES = {
     "en_mine_batch_select": (c_int, [P, P, c_int64, P, c_int64, c_float, c_int, P, P, P]),
     "en_loss_scan": (c_int, [P, c_int64, c_float, P, P]),
     "en_loss_select": (c_int, [P, c_int64, c_float, c_int, c_int, P, P]),
+    "en_gather_triplet_rows": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P, P]),
     "en_ws_bytes_batch_hard": (c_size_t, [c_int64, c_int]),
     "en_batch_hard_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "en_batch_hard_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),

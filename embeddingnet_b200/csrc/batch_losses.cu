@@ -699,22 +699,44 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
   if (row >= B) return;
   const int32_t la = labels[row];
   int count = 0;
-  for (int64_t j0 = 0; j0 < B; j0 += 32) {
+  auto emit = [&](int64_t jj) {
+    const double d2 = exact_d2(emb, d, row, jj, lane);
+    if (count < cap && lane == 0) {
+      pos_d[row * cap + count] = static_cast<float>(squared ? d2 : sqrt(d2));
+      pos_j[row * cap + count] = static_cast<int32_t>(jj);
+    }
+    ++count;
+  };
+  int64_t j0 = 0;
+  if ((reinterpret_cast<uintptr_t>(labels) & 15) == 0) {
+    // 128 labels per step (one int4 per lane); nearly every step finds nothing (ncu, round 1: the one-label-per-lane
+    // scan made this kernel as slow as the distance GEMM it prepares)
+    for (; j0 + 128 <= B; j0 += 128) {
+      const int4 l4 = __ldg(reinterpret_cast<const int4*>(labels + j0) + lane);
+      const int64_t jb = j0 + 4 * lane;
+      unsigned f = (l4.x == la && jb != row ? 1u : 0u) | (l4.y == la && jb + 1 != row ? 2u : 0u) |
+                   (l4.z == la && jb + 2 != row ? 4u : 0u) | (l4.w == la && jb + 3 != row ? 8u : 0u);
+      unsigned m = __ballot_sync(0xffffffffu, f != 0);
+      while (m) {  // ascending j: lanes in order, then the four labels of a lane in order
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        unsigned fs = __shfl_sync(0xffffffffu, f, src);
+        while (fs) {
+          const int sub = __ffs(fs) - 1;
+          fs &= fs - 1;
+          emit(j0 + 4 * src + sub);
+        }
+      }
+    }
+  }
+  for (; j0 < B; j0 += 32) {
     const int64_t j = j0 + lane;
     const bool same = j < B && j != row && labels[j] == la;
     unsigned m = __ballot_sync(0xffffffffu, same);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      const int64_t jj = j0 + src;
-      const double d2 = exact_d2(emb, d, row, jj, lane);
-      if (count < cap) {
-        if (lane == 0) {
-          pos_d[row * cap + count] = static_cast<float>(squared ? d2 : sqrt(d2));
-          pos_j[row * cap + count] = static_cast<int32_t>(jj);
-        }
-      }
-      ++count;
+      emit(j0 + src);
     }
   }
   if (lane == 0) {
@@ -844,12 +866,42 @@ struct EpContrastive {
 // Deterministic reduction of the per-(row, split) partials: one block, fixed order.
 // mode 0: batch-all  -> out[0] = sum / (npos + 1e-16), out[1] = npos / (nvalid + 1e-16), stats = {sum,npos,nvalid}
 // mode 1: contrastive -> out[0] = sum / (B (B-1))
-__global__ void pair_reduce_kernel(const PairPartial* __restrict__ partial, int64_t n_partials,
+// Stage 1 (many blocks): block b folds its contiguous chunk of the per-(row, split, half) partials into the chunk's
+// first slot, in place and in a fixed order (deterministic).  One block reading 4 MB took 46 us (ncu, round 1).
+constexpr int kReduceBlocks = 256;
+__global__ void pair_reduce_stage1_kernel(PairPartial* __restrict__ partial, int64_t n_partials, int64_t chunk) {
+  __shared__ double s_sum[8];
+  __shared__ unsigned long long s_cnt[8];
+  const int64_t lo = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int64_t hi = lo + chunk < n_partials ? lo + chunk : n_partials;
+  double sum = 0.0;
+  unsigned long long cnt = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const PairPartial x = partial[i];
+    sum += x.sum;
+    cnt += x.npos;
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+  __syncthreads();  // also: every read of this chunk has completed before its first slot is overwritten
+  if (threadIdx.x == 0 && lo < n_partials) {
+    double a = 0.0;
+    unsigned long long c = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += s_sum[w]; c += s_cnt[w]; }
+    partial[lo] = PairPartial{a, c};
+  }
+}
+
+// Stage 2 (one block): the chunk heads (stride `chunk`), plus the valid-triplet count of batch-all.
+__global__ void pair_reduce_kernel(const PairPartial* __restrict__ partial, int64_t n_partials, int64_t chunk,
                                    const int32_t* __restrict__ pos_n, int64_t B, int mode, float* __restrict__ out,
                                    double* __restrict__ stats) {
   __shared__ double s_sum[32], s_cnt[32], s_val[32];
   double sum = 0.0, cnt = 0.0, nvalid = 0.0;
-  for (int64_t i = threadIdx.x; i < n_partials; i += blockDim.x) {
+  for (int64_t i = static_cast<int64_t>(threadIdx.x) * chunk; i < n_partials; i += blockDim.x * chunk) {
     sum += partial[i].sum;
     cnt += static_cast<double>(partial[i].npos);
   }
@@ -1056,6 +1108,17 @@ __global__ void batch_all_bwd_pos_kernel(const float* __restrict__ emb, int64_t 
   }
 }
 
+int launch_pair_reduce(PairPartial* partial, int64_t n_partials, const int32_t* pos_n, int64_t B, int mode,
+                       float* out, double* stats, cudaStream_t st) {
+  const int64_t chunk = (n_partials + kReduceBlocks - 1) / kReduceBlocks;
+  const unsigned blocks = static_cast<unsigned>((n_partials + chunk - 1) / chunk);
+  pair_reduce_stage1_kernel<<<blocks, 256, 0, st>>>(partial, n_partials, chunk);
+  EN_LAUNCHED("pair_reduce_stage1_kernel");
+  pair_reduce_kernel<<<1, 256, 0, st>>>(partial, n_partials, chunk, pos_n, B, mode, out, stats);
+  EN_LAUNCHED("pair_reduce_kernel");
+  return EN_OK;
+}
+
 struct TcOperands {
   float *hi, *lo, *norms;
   int dpad;
@@ -1079,7 +1142,7 @@ int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStrea
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "workspace too small or misaligned");
   if (centre) {
-    tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, 8), 0, st>>>(emb, B, d, mu);
+    tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, tc::kMeanRows), 0, st>>>(emb, B, d, mu);
     EN_LAUNCHED("column_mean_kernel");
   }
   if (bf16) {
@@ -1281,8 +1344,7 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   EN_CUDA(tc::launch<EpBatchAll>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
   ++launch_counter();
-  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits * tc::EPI_H, pl.pos_n, B, 0, out, stats);
-  EN_LAUNCHED("pair_reduce_kernel");
+  if (int rc = launch_pair_reduce(partial, B * sh.n_splits * tc::EPI_H, pl.pos_n, B, 0, out, stats, st)) return rc;
   // a class larger than max_positives + 1 would silently drop triplets: surface it (one 4-byte read-back)
   int32_t status_h = 0;
   EN_CUDA(cudaMemcpyAsync(&status_h, pl.status, 4, cudaMemcpyDeviceToHost, st));
@@ -1363,8 +1425,7 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
   EN_CUDA(tc::launch<EpContrastive>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
   ++launch_counter();
-  pair_reduce_kernel<<<1, 1024, 0, st>>>(partial, B * sh.n_splits * tc::EPI_H, nullptr, B, 1, loss, nullptr);
-  EN_LAUNCHED("pair_reduce_kernel");
+  if (int rc = launch_pair_reduce(partial, B * sh.n_splits * tc::EPI_H, nullptr, B, 1, loss, nullptr, st)) return rc;
   return EN_OK;
 }
 

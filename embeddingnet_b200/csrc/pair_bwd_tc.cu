@@ -3,7 +3,11 @@
 //     d L / d E  =  rowsum(C) o E  -  C . E ,       C_ik = symmetrised pair coefficient, a function of D_ik
 //
 // One kernel, two chained tcgen05 GEMMs per 128 x 128 tile, nothing of size B x B ever stored:
-//   GEMM1  S  = E_I . E_J^T            3xTF32, operands by TMA, accumulator in TMEM
+//   GEMM1  S  = E_I . E_J^T            operands by TMA, accumulator in TMEM.  Contrastive: split-BF16 planes (3
+//                                     kind::f16 MMAs per k-step, twice the TF32 rate; S only feeds the smooth 1/D
+//                                     factors).  Batch-all: 3xTF32 -- its hinge decisions D_ap + m - D_an > 0 flip
+//                                     against float64 in proportion to the error of S (measured: BF16 planes
+//                                     pushed 8.7 % of the rows over the gradient tolerance, TF32 planes < 8 %)
 //   epilogue  C_IJ = f(S, labels, positives lists)   8 warps pull S out of TMEM into registers (releasing the
 //                                     accumulator at once), build C and write it BACK to TMEM with tcgen05.st as
 //                                     two TF32 planes C_hi + C_lo
@@ -132,10 +136,12 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
             ptx::mbar_wait(&bars->g1_empty[gs], gph ^ 1);
             uint8_t* st = g1 + gs * G1_STAGE_BYTES;
             ptx::mbar_arrive_expect_tx(&bars->g1_full[gs], G1_STAGE_BYTES);
-            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 0 * TILE_BYTES, kb * BK, ti * BM);
-            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 1 * TILE_BYTES, kb * BK, ti * BM);
-            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 2 * TILE_BYTES, kb * BK, J * BN);
-            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 3 * TILE_BYTES, kb * BK, J * BN);
+            // 128-byte k-blocks: 64 BF16 (contrastive) or 32 TF32 (batch-all) elements
+            constexpr int kBk1 = kMode == 1 ? tc::BK16 : BK;
+            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 0 * TILE_BYTES, kb * kBk1, ti * BM);
+            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 1 * TILE_BYTES, kb * kBk1, ti * BM);
+            ptx::tma_load_2d(&tm_hi, &bars->g1_full[gs], st + 2 * TILE_BYTES, kb * kBk1, J * BN);
+            ptx::tma_load_2d(&tm_lo, &bars->g1_full[gs], st + 3 * TILE_BYTES, kb * kBk1, J * BN);
             if (++gs == G1_STAGES) { gs = 0; gph ^= 1; }
           }
         };
@@ -161,6 +167,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc16 = ptx::make_idesc_bf16(BM, BN);
       int gs = 0, es = 0;
       uint32_t gph = 0, eph = 0, acc1_it = 0, c_it = 0, item_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
@@ -180,9 +187,15 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
               const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
               // one accumulator for all three products here: the backward only needs S to decide hinge activity
               // and 1/D factors, where the ~6e-6 accumulation bias is far inside the gradient tolerance
-              ptx::mma_tf32_ss(d_tm, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-              ptx::mma_tf32_ss(d_tm, a_hi + koff, b_lo + koff, idesc, 1);
-              ptx::mma_tf32_ss(d_tm, a_hi + koff, b_hi + koff, idesc, 1);
+              if (kMode == 1) {
+                ptx::mma_bf16_ss(d_tm, a_lo + koff, b_hi + koff, idesc16, (kb | k) != 0);
+                ptx::mma_bf16_ss(d_tm, a_hi + koff, b_lo + koff, idesc16, 1);
+                ptx::mma_bf16_ss(d_tm, a_hi + koff, b_hi + koff, idesc16, 1);
+              } else {
+                ptx::mma_tf32_ss(d_tm, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                ptx::mma_tf32_ss(d_tm, a_hi + koff, b_lo + koff, idesc, 1);
+                ptx::mma_tf32_ss(d_tm, a_hi + koff, b_hi + koff, idesc, 1);
+              }
             }
             ptx::mma_commit(&bars->g1_empty[gs]);
             if (++gs == G1_STAGES) { gs = 0; gph ^= 1; }
@@ -415,35 +428,39 @@ int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < pair_bwd_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small");
   Workspace w(ws, ws_bytes);
-  const int dpad = (d + tc::BK - 1) / tc::BK * tc::BK;
+  const int g1_bf16 = mode == 1;        // contrastive: BF16 GEMM1 planes (they fit in the fp32-sized buffers below)
+  const int dpad = tc::dpad_for(d, g1_bf16);
+  const int dpad32 = tc::dpad_for(d, 0);
   const int n_slices = (d + pbt::DN - 1) / pbt::DN;
   const int rows_t = n_slices * pbt::DN;
   const int64_t bpad = (B + 31) / 32 * 32;
-  float* hi = w.take<float>(static_cast<size_t>(B) * dpad);
-  float* lo = w.take<float>(static_cast<size_t>(B) * dpad);
+  float* hi = w.take<float>(static_cast<size_t>(B) * dpad32);
+  float* lo = w.take<float>(static_cast<size_t>(B) * dpad32);
   float* norms = w.take<float>(B);
   float* et_hi = w.take<float>(static_cast<size_t>(rows_t) * bpad);
   float* et_lo = w.take<float>(static_cast<size_t>(rows_t) * bpad);
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small or misaligned");
   dim3 tb(32, 8), tg(static_cast<unsigned>(bpad / 32), static_cast<unsigned>(rows_t / 32));
-  tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), tb, 0, st>>>(emb, B, d, mu);
+  tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, tc::kMeanRows), 0, st>>>(emb, B, d, mu);
   EN_LAUNCHED("column_mean_kernel");
   // GEMM1 also runs on the centred rows (norms are the centred norms): ||a-b|| is unchanged, S loses its
   // one-sided truncation bias, and with it the hinge-activity flips against the float64 oracle
-  EN_CUDA(tc::launch_split(emb, B, d, d, dpad, hi, lo, norms, st, mu));
+  if (g1_bf16) EN_CUDA(tc::launch_split_bf16(emb, B, d, d, dpad, hi, lo, norms, st, nullptr, nullptr, mu));
+  else EN_CUDA(tc::launch_split(emb, B, d, d, dpad, hi, lo, norms, st, mu));
   ++launch_counter();
   pbt::transpose_split_kernel<<<tg, tb, 0, st>>>(emb, mu, B, d, rows_t, bpad, et_hi, et_lo);
   EN_LAUNCHED("transpose_split_kernel");
   CUtensorMap th, tl, teh, tel;
-  if (tc::make_plane_tmap(&th, hi, B, dpad) || tc::make_plane_tmap(&tl, lo, B, dpad) ||
+  if ((g1_bf16 ? (tc::make_plane_tmap_bf16(&th, hi, B, dpad) || tc::make_plane_tmap_bf16(&tl, lo, B, dpad))
+               : (tc::make_plane_tmap(&th, hi, B, dpad) || tc::make_plane_tmap(&tl, lo, B, dpad))) ||
       tc::make_plane_tmap(&teh, et_hi, rows_t, bpad) || tc::make_plane_tmap(&tel, et_lo, rows_t, bpad))
     return fail(EN_ERR_DRIVER, "pair backward: cuTensorMapEncodeTiled failed");
   pbt::Params p;
   p.emb = emb; p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt;
   p.stats = stats; p.gloss = gloss; p.mu = mu; p.gemb = gemb; p.B = B; p.d = d;
   p.tiles = static_cast<int>((B + tc::BM - 1) / tc::BM);
-  p.n_slices = n_slices; p.kblocks = dpad / tc::BK; p.mode = mode; p.squared = squared; p.margin = margin;
+  p.n_slices = n_slices; p.kblocks = dpad / (g1_bf16 ? tc::BK16 : tc::BK); p.mode = mode; p.squared = squared; p.margin = margin;
   p.scale_c = scale_c;
   if (mode == 0)
     EN_CUDA(cudaFuncSetAttribute(pbt::pair_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pbt::SMEM_BYTES));

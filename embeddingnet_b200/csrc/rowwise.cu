@@ -238,6 +238,29 @@ __global__ void siamese_l1_bwd_kernel(const float* __restrict__ e1, const float*
 inline unsigned row_blocks(int64_t rows) { return static_cast<unsigned>((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
 inline unsigned elem_blocks(int64_t n) { return static_cast<unsigned>((n + THREADS - 1) / THREADS); }
 
+// Gather of the mined triplets' rows (datagenerators.py:241-243,252-256: A, P, N batches are the rows of the sampled
+// set picked by the mined indices).  One block per (triplet, slot); 128-bit copies when rows are 16-byte multiples.
+__global__ void gather_triplet_rows_kernel(const float* __restrict__ src, int64_t n_rows, int64_t row_len,
+                                           const int64_t* __restrict__ trip, int64_t T, float* __restrict__ a,
+                                           float* __restrict__ p, float* __restrict__ n) {
+  const int64_t t = blockIdx.x;
+  const int slot = blockIdx.y;
+  const int64_t r = trip[t * 3 + slot];
+  float* dst = (slot == 0 ? a : (slot == 1 ? p : n)) + t * row_len;
+  if (r < 0 || r >= n_rows) {  // never produced by the miner; keep the output defined
+    for (int64_t c = threadIdx.x; c < row_len; c += blockDim.x) dst[c] = 0.f;
+    return;
+  }
+  const float* from = src + r * row_len;
+  if ((row_len & 3) == 0 && ((reinterpret_cast<uintptr_t>(from) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const float4* f4 = reinterpret_cast<const float4*>(from);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int64_t c = threadIdx.x; c < row_len / 4; c += blockDim.x) d4[c] = __ldg(f4 + c);
+  } else {
+    for (int64_t c = threadIdx.x; c < row_len; c += blockDim.x) dst[c] = from[c];
+  }
+}
+
 }  // namespace
 }  // namespace en
 
@@ -336,6 +359,19 @@ int en_siamese_l1_bwd(const float* e1, const float* e2, const float* gout, int64
   if (n == 0) return EN_OK;
   siamese_l1_bwd_kernel<<<elem_blocks(n), THREADS, 0, as_stream(stream)>>>(e1, e2, gout, n, g1, g2);
   EN_LAUNCHED("siamese_l1_bwd_kernel");
+  return EN_OK;
+}
+
+int en_gather_triplet_rows(const float* src, int64_t n_rows, int64_t row_len, const int64_t* triplets, int64_t T,
+                           float* a, float* p, float* n, void* stream) {
+  EN_REQUIRE(src && triplets && a && p && n && n_rows > 0 && row_len > 0 && T >= 0,
+             "en_gather_triplet_rows: bad arguments");
+  EN_REQUIRE(T < (int64_t(1) << 31), "en_gather_triplet_rows: too many triplets");
+  if (T == 0) return EN_OK;
+  const int threads = row_len >= 4096 ? 256 : 128;
+  gather_triplet_rows_kernel<<<dim3(static_cast<unsigned>(T), 3), threads, 0, as_stream(stream)>>>(
+      src, n_rows, row_len, triplets, T, a, p, n);
+  EN_LAUNCHED("gather_triplet_rows_kernel");
   return EN_OK;
 }
 

@@ -138,6 +138,25 @@ def _select_on_vector(loss_values, margin, mode):
     return int(sel.item())
 
 
+def gather_triplets(rows, triplets):
+    """A, P, N = rows[trip[:, 0]], rows[trip[:, 1]], rows[trip[:, 2]] on the device (dg:241-243,252-256).
+
+    rows: CUDA float32 tensor (n, ...) -- the sampled images or embeddings; triplets: (T, 3) integer array.
+    Returns three CUDA tensors of shape (T, ...)."""
+    if not (isinstance(rows, torch.Tensor) and rows.is_cuda and rows.dtype == torch.float32):
+        raise ValueError("gather_triplets: rows must be a CUDA float32 tensor")
+    rows = rows.contiguous()
+    n = rows.shape[0]
+    row_len = int(rows[0].numel()) if n else 0
+    trip = torch.as_tensor(np.ascontiguousarray(np.asarray(triplets, dtype=np.int64))).to(rows.device)
+    T = trip.shape[0]
+    out = [torch.empty((T,) + tuple(rows.shape[1:]), dtype=torch.float32, device=rows.device) for _ in range(3)]
+    if T and row_len:
+        _lib.call("en_gather_triplet_rows", ptr(rows), n, row_len, ptr(trip), T, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                  stream_ptr())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ generators
 class ENDataGenerator:
     """Bookkeeping of the reference base class (dg:114-156); image IO is delegated to ``image_loader``."""
@@ -216,13 +235,26 @@ class TripletsDataGenerator(ENDataGenerator):
         for idx, cl_img_idxs in enumerate(selected_images):
             images = self._get_images_set(selected_classes[idx], cl_img_idxs, with_aug=self.augmentations)
             all_images_list.append(images)
-            all_embeddings_list.append(np.asarray(self.embedding_model.predict(images)))                   # dg:214
-        all_embeddings = np.vstack(all_embeddings_list)                                                    # dg:217
-        all_images = np.vstack(all_images_list)
+            all_embeddings_list.append(self.embedding_model.predict(images))                               # dg:214
         labels = np.repeat(np.arange(self.k_classes), self.k_samples)                                      # dg:226-227
+        # Device-resident path: when the image hook and the embedding model hand back CUDA tensors,
+        # embeddings go straight into the distance kernel and the mined A / P / N batches are gathered on the device;
+        # only the (T, 3) indices and the candidate counts (which the host RNG needs) ever reach the host.
+        on_device = all(isinstance(t, torch.Tensor) and t.is_cuda for t in all_embeddings_list + all_images_list)
+        if on_device:
+            all_embeddings = torch.cat([e.to(torch.float32) for e in all_embeddings_list], dim=0)          # dg:217
+            all_images = torch.cat([i.to(torch.float32) for i in all_images_list], dim=0)
+        else:
+            all_embeddings = np.vstack([np.asarray(e.cpu() if isinstance(e, torch.Tensor) else e)
+                                        for e in all_embeddings_list])
+            all_images = np.vstack([np.asarray(i.cpu() if isinstance(i, torch.Tensor) else i)
+                                    for i in all_images_list])
         trip, _ = mine_batch_triplets(all_embeddings, labels, margin=self.margin,
                                       mode=self.negatives_selection_mode)
-        triplets = [all_images[trip[:, 0]], all_images[trip[:, 1]], all_images[trip[:, 2]]]                # dg:252-256
+        if on_device:
+            triplets = gather_triplets(all_images, trip)
+        else:
+            triplets = [all_images[trip[:, 0]], all_images[trip[:, 1]], all_images[trip[:, 2]]]            # dg:252-256
         targets = np.ones(trip.shape[0], dtype=np.int64)                                                   # dg:244,255
         return triplets, targets
 

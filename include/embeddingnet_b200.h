@@ -106,6 +106,12 @@ int en_loss_scan(const float* loss_values, int64_t n, float margin, int32_t* out
 int en_loss_select(const float* loss_values, int64_t n, float margin, int mode, int rank, int32_t* out1,
                    void* stream);
 
+/* Gather of the mined triplets (datagenerators.py:241-243,252-256): a/p/n (T, row_len) <- src[triplets[t, 0|1|2]].
+ * src is the (n_rows, row_len) sampled set (flattened images or embeddings) already resident on the device, so the
+ * batch never returns to the host between embedding, mining and the loss.  triplets (T, 3) int64. */
+int en_gather_triplet_rows(const float* src, int64_t n_rows, int64_t row_len, const int64_t* triplets, int64_t T,
+                           float* a, float* p, float* n, void* stream);
+
 /* ---------------------------------------------------------------- fused in-batch losses (tcgen05 distance GEMM) */
 /* Batch-hard triplet loss (BASELINE.json north_star; Hermans et al. / Moindrot, cited at README.md:112,116 --
  * not implemented by the reference).  emb (B, d), labels (B,).

@@ -88,6 +88,47 @@ def test_generator_matches_reference_generator(golden, case, mode, seed):
     assert np.random.random_sample() == golden["mine_%s_%s_%d_rng_after" % (case, mode, seed)]
 
 
+@pytest.mark.parametrize("mode", ["hardest", "semihard"])
+def test_generator_device_resident_path(golden, mode):
+    """image hook and embedding model return CUDA tensors -> embeddings, mining and the A/P/N gather
+    (en_gather_triplet_rows) stay on the device; same triplets and RNG state as the reference generator."""
+    import torch
+    from embeddingnet_b200.datagenerators import TripletsDataGenerator, gather_triplets
+
+    case, seed = list(MINING_CASES)[0], 7
+    ncls, per, d, kc, ks, margin, norm = MINING_CASES[case]
+    table = torch.tensor(np.vstack(class_tables(ncls, per, d, norm)), device="cuda")
+    names = ["c%04d" % i for i in range(ncls)]
+    files = {n: ["%d" % (i * per + j) for j in range(per)] for i, n in enumerate(names)}
+
+    class Model:
+        def predict(self, images):  # "images" carry their row id in element 0 and a payload behind it
+            return table[images[:, 0, 0].to(torch.int64)]
+
+    class Gen(TripletsDataGenerator):
+        def _get_images_set(self, clss, idxs, with_aug=True):
+            ids = torch.tensor([float(self.class_files_paths[clss][i]) for i in idxs], device="cuda")
+            return torch.stack([ids, ids * 0.5, ids + 1.0, -ids, ids * 2.0], dim=1).reshape(-1, 5, 1)
+
+    g = Gen(Model(), files, names, n_batches=1, k_classes=kc, k_samples=ks, margin=margin,
+            negatives_selection_mode=mode)
+    np.random.seed(seed)
+    (A, P, N), targets = g[0]
+    assert all(isinstance(t, torch.Tensor) and t.is_cuda and t.shape[1:] == (5, 1) for t in (A, P, N))
+    got = np.stack([A[:, 0, 0].cpu().numpy(), P[:, 0, 0].cpu().numpy(), N[:, 0, 0].cpu().numpy()], axis=1)
+    want = golden["mine_%s_%s_%d" % (case, mode, seed)]
+    np.testing.assert_array_equal(got.astype(np.int64), want)
+    np.testing.assert_array_equal(A[:, 4, 0].cpu().numpy(), want[:, 0] * 2.0)  # whole rows travel, not just the id
+    assert np.random.random_sample() == golden["mine_%s_%s_%d_rng_after" % (case, mode, seed)]
+    # gather kernel against torch indexing, odd row length (scalar copy path) and an empty triplet list
+    rows = torch.arange(7 * 13, dtype=torch.float32, device="cuda").reshape(7, 13)
+    trip = np.array([[0, 6, 3], [5, 5, 1], [2, 0, 6]], dtype=np.int64)
+    a, p_, n_ = gather_triplets(rows, trip)
+    for k, out in enumerate((a, p_, n_)):
+        assert torch.equal(out, rows[torch.tensor(trip[:, k], device="cuda")])
+    assert gather_triplets(rows, np.zeros((0, 3), np.int64))[0].shape == (0, 13)
+
+
 @pytest.mark.parametrize("mode", ["hardest", "semihard", "random_hard"])
 def test_mine_batch_vs_oracle_general_labels(mode):
     from embeddingnet_b200.datagenerators import mine_batch_triplets
