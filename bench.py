@@ -530,13 +530,17 @@ def main():
             s1.record()
             barrier()
             call_ms = max_over_ranks(s0.elapsed_time(s1) / 5)
+            on_stream = qn <= clf.stream_max_q
             stream[qn] = {
-                "what": "%d query(ies) per call, CUDA-core fp32 streaming scan of the bank shard + exact re-rank" % qn,
+                "what": ("%d query(ies) per call, CUDA-core fp32 streaming scan of the bank shard + exact re-rank" if
+                         on_stream else "%d query(ies) per call, tensor-core scan of the shard's BF16 planes (same "
+                         "bytes as the fp32 rows) + exact re-rank") % qn,
                 "queries_per_sec": qn / (call_ms * 1e-3), "ms_per_call": call_ms,
                 "roofline": {"bound": "hbm", "achieved": stream_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": stream_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "traffic": ncu_traffic("knn_stream_q%d_dram_bytes_per_launch" % qn),
-                             "kernel": "knn_stream_kernel<8,4,%d,true>" % qn, "kernel_ms": k_ms,
+                             "kernel": ("knn_stream_kernel<8,4,%d,true>" % qn) if on_stream else
+                             "dist_gemm_kernel<EpTopK<8>> (one query tile)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": stream_bytes}}
         # C4: offline hard-negative mining over a bank = label-excluded nearest neighbours (1M x 256, 64k anchors)
         mining = None

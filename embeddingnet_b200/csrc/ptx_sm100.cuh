@@ -144,6 +144,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[3
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// same, 8 consecutive columns
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const float (&v)[8]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem: 128 lanes x K 32-bit columns] * B[smem desc]: the A operand comes straight from tensor

@@ -53,6 +53,8 @@ class BankKNNClassifier:
         self.precision = precision
         self.certify = bool(certify)
         self.last_uncertified = 0
+        # queries per call up to which the CUDA-core streaming scan is used instead of the tensor-core scan
+        self.stream_max_q = 4  # measured on B200 (tools/time_knn_smallq.py): Q >= 5 is faster on the tensor path
         self._fitted = False
 
     # -- sharding helpers
@@ -133,7 +135,7 @@ class BankKNNClassifier:
                 ql = exclude_labels.to(dev, torch.int32).contiguous()
                 bl = self._labels[self._offset:self._offset + n]
             flags = torch.empty(Q, dtype=torch.int32, device=dev) if self.certify else None
-            if Q <= _lib.EN_KNN_STREAM_MAX_Q and ql is None:
+            if Q <= min(self.stream_max_q, _lib.EN_KNN_STREAM_MAX_Q) and ql is None:
                 # the reference's own call pattern: one image per predict() -> HBM-bound streaming scan
                 ws = workspace(lib.en_ws_bytes_knn_stream(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._norms), n, self._offset, k,
