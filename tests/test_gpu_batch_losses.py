@@ -178,6 +178,44 @@ def test_batch_hard_edge_cases():
     assert abs(loss.item() - 0.5) < 1e-7
 
 
+def test_batch_hard_near_tie_contenders_take_the_exact_rounds():
+    """Several candidates inside the scan's error band of the best one: the fast finalize kernel must re-evaluate
+    them all exactly (one round per contender) and, when three of them queue up on one lane of the warp, fall back
+    to the per-candidate path -- the selected indices stay the float64 oracle's (lowest index on exact ties)."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr, workspace
+
+    rng = np.random.RandomState(3)
+    x, lab = make_batch(512, 8, 128, True, False)          # B = 4096, d = 128: fast finalize path, 32 row tiles
+    B, d = x.shape
+    # (a) four near-copies of row 5 in other classes, tiles 1, 2, 3, 5 -> four contenders, one per lane
+    for r in (128 + 9, 256 + 70, 384 + 1, 640 + 33):
+        x[r] = x[5] + (rng.randn(d) * 3e-7 * np.abs(x[5])).astype(np.float32)
+    # (b) near-copies of row 2000 in tiles 0, 8, 16, 24 (first column half): records 0, 32, 64, 96 = one lane, 4 deep
+    for r in (3, 1024 + 3, 2048 + 3, 3072 + 3):
+        x[r] = x[2000] + (rng.randn(d) * 3e-7 * np.abs(x[2000])).astype(np.float32)
+    # (c) an exact duplicate pair inside one class: every other anchor sees two identical candidates (exact tie)
+    x[801] = x[800]
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    e = torch.tensor(x, device="cuda")
+    l = torch.tensor(lab, device="cuda", dtype=torch.int32)
+    lib = _lib.load()
+    ws = workspace(lib.en_ws_bytes_batch_hard(B, d), e.device, "t")
+    loss = torch.empty((), device="cuda")
+    si = torch.empty((2, B), dtype=torch.int32, device="cuda")
+    sf = torch.empty((3, B), dtype=torch.float32, device="cuda")
+    g = torch.empty_like(e)
+    _lib.call("en_batch_hard_fwd_bwd", ptr(e), ptr(l), B, d, ctypes.c_float(0.5), 0, 0, ptr(loss), ptr(si[0]),
+              ptr(si[1]), ptr(sf[0]), ptr(sf[1]), ptr(sf[2]), None, ptr(g), ptr(ws), ws.numel(), stream_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(si[0].cpu().numpy(), ref["hp_idx"])
+    np.testing.assert_array_equal(si[1].cpu().numpy(), ref["hn_idx"])
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    _, gref = O.batch_hard_grad(lab, x, 0.5, False, False)
+    assert rel_err(g.cpu().numpy(), gref) < 1e-4
+
+
 def test_batch_hard_full_size_properties():
     """B = 4096, d = 512 (the headline shape): compare with the float64 oracle on a row subset, plus
     permutation invariance of the loss and equivariance of the gradient."""
