@@ -68,6 +68,10 @@ SIGNATURES = {
     "en_knn_finalize_dist": (c_int, [P, c_int64, P, P]),
     "en_knn_vote": (c_int, [P, c_int64, c_int, P, c_int64, P, P]),
     "en_knn_accuracy": (c_int, [P, P, P, c_int64, c_int, P, c_int64, P, P]),
+    "en_dense_plane_bytes": (c_size_t, [c_int, c_int]),
+    "en_dense_prepare": (c_int, [P, c_int, c_int, P, P, P]),
+    "en_ws_bytes_dense": (c_size_t, [c_int64, c_int]),
+    "en_dense_relu_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P, c_size_t, P]),
     "en_synth_fill": (c_int, [P, c_int64, c_int, c_int64, c_uint64, c_uint64, c_int64, c_int64, c_float, c_int, P, P]),
 }
 

@@ -1,0 +1,69 @@
+"""Drop-in for the *head* of ``embedding_net/backbones.py`` (RocketFlash/EmbeddingNet).
+
+The reference ends every backbone with ``Dense(encodings_len // 2, relu) -> Dense(encodings_len, relu) ->
+Lambda(K.l2_normalize(axis=1))`` (/root/reference/embedding_net/backbones.py:114-119; the simple backbones end the same
+way, :36-38 and :75-77).  The convolutional trunk is cuDNN's job and out of scope; this module is the step between the
+pooled trunk features and the distance / mining / kNN path: each Dense is one tcgen05 GEMM whose epilogue applies
+bias + ReLU and, for the last layer, the row normalisation (``csrc/head.cu``), so embeddings are born normalised on
+the device and can go straight into ``TripletsDataGenerator`` / ``BankKNNClassifier`` without touching the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import as_cuda_f32, ptr, require_cuda, stream_ptr, workspace
+
+
+class DenseReLU:
+    """``Dense(units, activation="relu")`` with an optional fused ``K.l2_normalize``.
+
+    kernel: (n_in, units) -- the Keras layout; bias: (units,) or None."""
+
+    def __init__(self, kernel, bias=None, normalize=False, device=None):
+        dev = device or require_cuda()
+        lib = _lib.load()
+        k = as_cuda_f32(kernel, dev)
+        if k.dim() != 2:
+            raise ValueError("DenseReLU: kernel must be (n_in, units)")
+        self.n_in, self.units = int(k.shape[0]), int(k.shape[1])
+        self.normalize = bool(normalize)
+        self.device = dev
+        self.bias = as_cuda_f32(bias, dev).reshape(-1) if bias is not None else None
+        if self.bias is not None and self.bias.numel() != self.units:
+            raise ValueError("DenseReLU: bias must have %d entries" % self.units)
+        nbytes = lib.en_dense_plane_bytes(self.n_in, self.units)
+        self._hi = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        self._lo = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        _lib.call("en_dense_prepare", ptr(k), self.n_in, self.units, ptr(self._hi), ptr(self._lo), stream_ptr())
+
+    def __call__(self, x):
+        lib = _lib.load()
+        xt = as_cuda_f32(x, self.device)
+        if xt.dim() != 2 or xt.shape[1] != self.n_in:
+            raise ValueError("DenseReLU: expected (B, %d) input, got %s" % (self.n_in, tuple(xt.shape)))
+        B = xt.shape[0]
+        out = torch.empty((B, self.units), dtype=torch.float32, device=self.device)
+        if B == 0:
+            return out
+        ws = workspace(lib.en_ws_bytes_dense(B, self.n_in), self.device, "dense")
+        _lib.call("en_dense_relu_fwd", ptr(xt), B, self.n_in, ptr(self._hi), ptr(self._lo), ptr(self.bias), self.units,
+                  int(self.normalize), ptr(out), ptr(ws), ws.numel(), stream_ptr())
+        return out
+
+
+class EmbeddingHead:
+    """``Dense(d // 2, relu) -> Dense(d, relu) [-> l2_normalize]`` on pooled trunk features (backbones.py:114-119).
+
+    ``predict(features)`` mirrors ``base_model.predict``: NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out
+    (which keeps ``TripletsDataGenerator``'s device-resident path on the device)."""
+
+    def __init__(self, kernel1, bias1, kernel2, bias2, embeddings_normalization=True, device=None):
+        self.fc1 = DenseReLU(kernel1, bias1, normalize=False, device=device)
+        self.fc2 = DenseReLU(kernel2, bias2, normalize=embeddings_normalization, device=device)
+
+    def predict(self, features):
+        on_device = isinstance(features, torch.Tensor) and features.is_cuda
+        y = self.fc2(self.fc1(features))
+        return y if on_device else y.cpu().numpy()

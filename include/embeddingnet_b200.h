@@ -217,6 +217,20 @@ int en_knn_vote(const int64_t* ids, int64_t Q, int k, const int32_t* labels, int
 int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* query_labels, int64_t Q, int k_ids,
                     const int32_t* labels, int64_t n_total, int64_t* counts, void* stream);
 
+/* ---------------------------------------------------------------- embedding head */
+/* Dense(n_out, activation="relu") [+ K.l2_normalize(axis=1)]: the last layers of every backbone the reference builds
+ * (backbones.py:114-119, :36-38, :75-77) -- the producer of the embeddings this library consumes.  One tcgen05
+ * 3xTF32 GEMM with bias + ReLU + row normalisation in its epilogue.
+ * en_dense_prepare: w is the Keras kernel, (n_in, n_out) row-major; w_hi / w_lo receive its transposed TF32 planes,
+ * en_dense_plane_bytes() each (once per set of weights).
+ * en_dense_relu_fwd: x (B, n_in) -> out (B, n_out) = relu(x . w + bias), each row scaled by
+ * rsqrt(max(sum y^2, 1e-12)) when normalize != 0.  bias may be NULL. */
+size_t en_dense_plane_bytes(int n_in, int n_out);
+int en_dense_prepare(const float* w, int n_in, int n_out, float* w_hi, float* w_lo, void* stream);
+size_t en_ws_bytes_dense(int64_t B, int n_in);
+int en_dense_relu_fwd(const float* x, int64_t B, int n_in, const float* w_hi, const float* w_lo, const float* bias,
+                      int n_out, int normalize, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- synthetic data (bench / tests) */
 /* x[r, c] = u(r, c) in [-1, 1) from a splitmix64 counter hash; optional class structure:
  * x = relu?(centre[label(r)] + noise * u) with label(r) = (r + row_offset) / rows_per_class (class-major) when

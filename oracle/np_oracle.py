@@ -114,6 +114,18 @@ def l2_normalize(x):
     return (x64 / np.sqrt(np.maximum(ss, 1e-12))).astype(F32)
 
 
+def dense_relu(x, kernel, bias=None, normalize=False):
+    """embedding_net/backbones.py:114-119: Dense(units, activation="relu") (+ K.l2_normalize) in float64."""
+    y = np.asarray(x, np.float64) @ np.asarray(kernel, np.float64)
+    if bias is not None:
+        y = y + np.asarray(bias, np.float64)[None, :]
+    y = np.maximum(y, 0.0)
+    if normalize:
+        ss = np.sum(y * y, axis=1, keepdims=True)
+        y = y / np.sqrt(np.maximum(ss, 1e-12))
+    return y.astype(F32)
+
+
 def l2_normalize_grad(x, upstream):
     x = np.asarray(x, np.float64)
     g = np.asarray(upstream, np.float64)

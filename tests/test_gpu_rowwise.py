@@ -95,3 +95,47 @@ def test_synth_device_matches_numpy():
         np.testing.assert_array_equal(xd.cpu().numpy(), x)
         if kw:
             np.testing.assert_array_equal(ld.cpu().numpy(), l)
+
+
+@pytest.mark.parametrize("B,n_in,units", [(128, 512, 256), (300, 100, 130), (5, 33, 7), (1000, 256, 512)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_dense_relu_head(B, n_in, units, normalize):
+    """Dense(relu) [+ l2_normalize] head (backbones.py:114-119) vs the float64 oracle; ragged sizes, zero rows."""
+    from embeddingnet_b200.backbones import DenseReLU
+
+    x, _ = synth.make_numpy(B, n_in, seed_noise=11)
+    w, _ = synth.make_numpy(n_in, units, seed_noise=12)
+    w = (w / np.sqrt(n_in)).astype(np.float32)
+    b, _ = synth.make_numpy(1, units, seed_noise=13)
+    b = (0.1 * b[0]).astype(np.float32)
+    if B > 4:
+        x[3] = -np.abs(x[3]) * 100.0  # drives the whole row through the ReLU to (almost surely) zero
+    layer = DenseReLU(w, b, normalize=normalize)
+    got = layer(x).cpu().numpy()
+    want = O.dense_relu(x, w, b, normalize)
+    scale = np.abs(want).max() + 1e-30
+    assert np.abs(got - want).max() <= 1e-5 * scale
+    if normalize:
+        nz = np.linalg.norm(want, axis=1) > 0
+        np.testing.assert_allclose(np.linalg.norm(got[nz], axis=1), 1.0, rtol=1e-5)
+    assert not np.isnan(got).any()
+
+
+def test_embedding_head_feeds_the_bank_path_on_device():
+    """EmbeddingHead.predict keeps CUDA tensors on the device and matches the two-layer oracle."""
+    import torch
+    from embeddingnet_b200.backbones import EmbeddingHead
+
+    f, _ = synth.make_numpy(257, 96, seed_noise=21, relu=True)
+    k1, _ = synth.make_numpy(96, 64, seed_noise=22)
+    k2, _ = synth.make_numpy(64, 128, seed_noise=23)
+    k1, k2 = (k1 / 10).astype(np.float32), (k2 / 8).astype(np.float32)
+    b1 = np.full(64, 0.05, np.float32)
+    b2 = np.full(128, -0.02, np.float32)
+    head = EmbeddingHead(k1, b1, k2, b2, embeddings_normalization=True)
+    want = O.dense_relu(O.dense_relu(f, k1, b1), k2, b2, normalize=True)
+    got = head.predict(f)
+    assert isinstance(got, np.ndarray) and np.abs(got - want).max() <= 2e-5
+    got_d = head.predict(torch.tensor(f, device="cuda"))
+    assert isinstance(got_d, torch.Tensor) and got_d.is_cuda
+    assert np.abs(got_d.cpu().numpy() - want).max() <= 2e-5
