@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libembeddingnet_b200.so")
 EN_MODE_SEMIHARD, EN_MODE_HARDEST, EN_MODE_RANDOM_HARD = 0, 1, 2
 EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q = 3, 29, 8, 64
 EN_PREC_TF32X3, EN_PREC_BF16X3 = 0, 1
+EN_MINE_MAX_SLOTS = 8
 
 P = c_void_p  # every device pointer / stream crosses the boundary as an opaque address
 
@@ -68,6 +69,11 @@ SIGNATURES = {
     "en_knn_finalize_dist": (c_int, [P, c_int64, P, P]),
     "en_knn_vote": (c_int, [P, c_int64, c_int, P, c_int64, P, P]),
     "en_knn_accuracy": (c_int, [P, P, P, c_int64, c_int, P, c_int64, P, P]),
+    "en_pair_dist_exact": (c_int, [P, P, c_int64, c_int, P, P]),
+    "en_ws_bytes_mine_bank": (c_size_t, [c_int64, c_int]),
+    "en_mine_bank_count": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P, P, P, c_int64, c_int, P, P, c_size_t, P]),
+    "en_mine_bank_select": (c_int, [P, P, P, c_int64, c_int, c_float, c_int, P, P, P, P, P, P, c_int64, c_int64, c_int,
+                                    P, P, c_size_t, P]),
     "en_dense_plane_bytes": (c_size_t, [c_int, c_int]),
     "en_dense_prepare": (c_int, [P, c_int, c_int, P, P, P]),
     "en_ws_bytes_dense": (c_size_t, [c_int64, c_int]),

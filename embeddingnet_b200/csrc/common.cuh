@@ -71,6 +71,21 @@ void prof_end(cudaStream_t st);
 int device_sm_count();  // SM count of the current device (cached per device), <0 on error
 int check_sm100();      // 0 when the current device is compute capability 10.x
 
+// Rigorous bound c with |dot~ - dot| <= c |q| |b| for the scan arithmetic (x1.5 safety):
+//   operand split: the dropped products lo*lo, r*b, q*r with |x - hi| <= u |x|, |x - hi - lo| <= u^2 |x|
+//                  (u = 2^-11 TF32 round-to-nearest, 2^-8 BF16)                      -> 3 u^2 (1 + u)
+//   accumulation : the tensor core truncates when it adds into the fp32 accumulator, <= 2^-22 of the partial sum
+//                  per MMA (measured bias on B200: ~2^-24 per link), d / K_mma links     -> 2^-22 (links + 1)
+//   fp32 stream  : d/32 sequential FMAs per lane + 5 shuffle adds, 2^-24 each.
+inline double cert_bound(int precision, int d) {
+  const double p22 = 1.0 / 4194304.0;
+  double c;
+  if (precision == EN_PREC_BF16X3) c = 3.0 / 65536.0 * (1.0 + 1.0 / 256.0) + p22 * ((d + 15) / 16 + 1);
+  else if (precision == EN_PREC_TF32X3) c = 3.0 * p22 * (1.0 + 1.0 / 2048.0) + p22 * ((d + 7) / 8 + 1);
+  else c = p22 / 4.0 * ((d + 31) / 32 + 8);
+  return 1.5 * c;
+}
+
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -200,6 +200,99 @@ class BankKNNClassifier:
             return dist_f.cpu().numpy(), ids.cpu().numpy()
         return ids.cpu().numpy()
 
+    # -- offline hard-negative mining over the bank with the generator's strategies (dg:188-199; BASELINE config 4)
+    def mine_negatives(self, anchors, anchor_labels, positives=None, pos_dist=None, margin=0.5, mode="semihard"):
+        """For every anchor a and each of its (up to 8) positives p: one negative bank row chosen by ``mode``
+        ('hardest' | 'random_hard' | 'semihard', datagenerators.py:188-199) among ALL bank rows of another class.
+
+        anchors (A, d); anchor_labels (A,) class ids in the numbering of ``fit_shard`` / ``classes_``; either
+        ``positives`` (A, S, d) embeddings or ``pos_dist`` (A, S) distances d_ap (negative = unused slot).
+        Returns (A, S) int64 global bank ids, -1 where the strategy finds no candidate (the reference's None).
+        The random strategies consume the global legacy NumPy RNG exactly as the reference does: one
+        ``randint(len(candidates))`` per pair with candidates, pairs in (anchor, slot) order.  With a process group,
+        every rank must call this with the same arguments and the same RNG state."""
+        from .datagenerators import MODES
+
+        if mode not in MODES:
+            raise KeyError(mode)
+        if not self._fitted:
+            raise RuntimeError("BankKNNClassifier: call fit() first")
+        lib = _lib.load()
+        dev = self.device
+        a = as_cuda_f32(anchors, dev)
+        A, d = a.shape
+        if d != self._d:
+            raise ValueError("anchor dimension %d != bank dimension %d" % (d, self._d))
+        al = (anchor_labels if isinstance(anchor_labels, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(anchor_labels, dtype=np.int32)))).to(dev, torch.int32).contiguous()
+        MS = _lib.EN_MINE_MAX_SLOTS
+        if pos_dist is None:
+            p = as_cuda_f32(positives, dev)
+            if p.dim() != 3 or p.shape[0] != A or p.shape[2] != d:
+                raise ValueError("positives must be (A, S, d)")
+            S = p.shape[1]
+            rep = a.unsqueeze(1).expand(A, S, d).contiguous()
+            pd = torch.empty((A, S), dtype=torch.float32, device=dev)
+            _lib.call("en_pair_dist_exact", ptr(rep), ptr(p.contiguous()), A * S, d, ptr(pd), stream_ptr())
+        else:
+            pd = as_cuda_f32(pos_dist, dev)
+            S = pd.shape[1]
+        if S > MS:
+            raise ValueError("at most %d positives per anchor (got %d)" % (MS, S))
+        pos_d = torch.full((A, MS), -1.0, dtype=torch.float32, device=dev)
+        pos_d[:, :S] = pd
+        n = self._bank.shape[0]
+        bl = self._labels[self._offset:self._offset + n].contiguous()
+        world, rank = self._world()
+        if mode == "hardest":
+            # nearest row of another class; a candidate only if its loss is positive (dg:189-190)
+            d2, ids = self._search(a, 1, exclude_labels=al)
+            dist = torch.sqrt(d2[:, 0].to(torch.float32))
+            loss = (pos_d - dist[:, None]) + float(margin)
+            out = torch.where((loss > 0) & (pos_d >= 0) & (ids[:, :1] >= 0), ids[:, :1].expand(A, MS),
+                              torch.full_like(ids[:, :1].expand(A, MS), -1))
+            return out[:, :S].cpu().numpy()
+        ws = workspace(lib.en_ws_bytes_mine_bank(A, d), dev, "mine_bank")
+        counts = torch.zeros((A, MS, 2), dtype=torch.int32, device=dev)
+        if n > 0:
+            _lib.call("en_mine_bank_count", ptr(a), ptr(al), ptr(pos_d), A, d, ctypes.c_float(margin), ptr(self._bank),
+                      ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl), n, self._prec, ptr(counts), ptr(ws),
+                      ws.numel(), stream_ptr())
+        col = 0 if mode == "random_hard" else 1
+        mine = counts[:, :, col].contiguous()
+        if world > 1:
+            import torch.distributed as dist_
+
+            allc = torch.empty((world, A, MS), dtype=torch.int32, device=dev)
+            dist_.all_gather_into_tensor(allc, mine, group=self.process_group)   # (pairs, P) counts, SURVEY 8(e)
+        else:
+            allc = mine.unsqueeze(0)
+        allc_h = allc.cpu().numpy().astype(np.int64)
+        total = allc_h.sum(axis=0)
+        local_rank = np.full((A, MS), -1, dtype=np.int32)
+        for i in range(A):                       # reference pair order => same RNG stream on every rank
+            for s in range(S):
+                c = int(total[i, s])
+                if c > 0:
+                    r = int(np.random.randint(0, c))
+                    for q in range(world):       # shards hold ascending id ranges: the owner is found by prefix
+                        if r < allc_h[q, i, s]:
+                            if q == rank:
+                                local_rank[i, s] = r
+                            break
+                        r -= int(allc_h[q, i, s])
+        sel = torch.full((A, MS), -1, dtype=torch.int64, device=dev)
+        if n > 0:
+            rk = torch.from_numpy(local_rank).to(dev)
+            _lib.call("en_mine_bank_select", ptr(a), ptr(al), ptr(pos_d), A, d, ctypes.c_float(margin), MODES[mode],
+                      ptr(rk), ptr(self._bank), ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl), n,
+                      self._offset, self._prec, ptr(sel), ptr(ws), ws.numel(), stream_ptr())
+        if world > 1:
+            import torch.distributed as dist_
+
+            dist_.all_reduce(sel, op=dist_.ReduceOp.MAX, group=self.process_group)  # one owner per pair, others -1
+        return sel[:, :S].cpu().numpy()
+
     def predict_device(self, X):
         """(Q,) int32 class ids on the device."""
         k = self.n_neighbors

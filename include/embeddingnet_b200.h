@@ -217,6 +217,33 @@ int en_knn_vote(const int64_t* ids, int64_t Q, int k, const int32_t* labels, int
 int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* query_labels, int64_t Q, int k_ids,
                     const int32_t* labels, int64_t n_total, int64_t* counts, void* stream);
 
+/* ---------------------------------------------------------------- bank-scale mining with the generator's strategies */
+/* datagenerators.py:188-199 over an encoding bank (BASELINE config 4).  For anchor a and its
+ * positive slot s with distance pos_d[a, s] (< 0 = unused slot; at most EN_MINE_MAX_SLOTS per anchor):
+ *   loss_n = (pos_d[a, s] - d(a, n)) + margin over bank rows n with bank_labels[n] != anchor_labels[a]   (dg:235)
+ *   random_hard candidates: loss_n > 0;  semihard candidates: 0 < loss_n < margin                        (dg:193,197)
+ * d(a, n) = sqrtf((float) sum_f64 (a - n)^2); elements whose scan value lies within the scan's error bound of a
+ * predicate boundary are re-evaluated exactly on the spot, so counts and selected ids are those of the float64
+ * definition for either operand format.
+ * en_mine_bank_count : counts (A, EN_MINE_MAX_SLOTS, 2) int32 = [random_hard, semihard] candidates in THIS shard.
+ * en_mine_bank_select: rank (A, EN_MINE_MAX_SLOTS) int32 = 0-based rank among this shard's candidates of `mode` in
+ *   ascending row id (< 0: nothing to select here) -> selected (A, EN_MINE_MAX_SLOTS) int64 global id or -1.
+ * The host draws the rank from the legacy NumPy RNG (np.random.choice(c) == c[randint(len(c))], dg:194,199); with a
+ * sharded bank the per-shard counts are all-gathered and the owning shard resolves the rank.
+ * en_pair_dist_exact: dist[i] = d(a_i, b_i) with the definition above (the d_ap inputs).
+ * The hardest strategy is the label-excluded nearest neighbour: en_knn_shard_topk with query_labels. */
+#define EN_MINE_MAX_SLOTS 8
+int en_pair_dist_exact(const float* a, const float* b, int64_t n, int d, float* dist, void* stream);
+size_t en_ws_bytes_mine_bank(int64_t A, int d);
+int en_mine_bank_count(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
+                       float margin, const float* bank, const void* bank_hi, const void* bank_lo,
+                       const float* bank_norms, const int32_t* bank_labels, int64_t n_bank, int precision,
+                       int32_t* counts, void* ws, size_t ws_bytes, void* stream);
+int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
+                        float margin, int mode, const int32_t* rank, const float* bank, const void* bank_hi,
+                        const void* bank_lo, const float* bank_norms, const int32_t* bank_labels, int64_t n_bank,
+                        int64_t id_offset, int precision, int64_t* selected, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- embedding head */
 /* Dense(n_out, activation="relu") [+ K.l2_normalize(axis=1)]: the last layers of every backbone the reference builds
  * (backbones.py:114-119, :36-38, :75-77) -- the producer of the embeddings this library consumes.  One tcgen05

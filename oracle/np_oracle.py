@@ -538,6 +538,42 @@ def mine_bank_hardest(bank, labels, anchors_idx, k=1):
     return np.sqrt(dist).astype(F32), ids
 
 
+def mine_bank_modes(bank, labels, anchors, anchor_labels, pos_d, margin, mode):
+    """datagenerators.py:188-199 over a whole bank: for each (anchor, positive slot) the candidates among bank rows of
+    another class, loss = (d_ap - d_an) + margin in float32 (dg:235), d = sqrtf(float32(float64 sum (a-n)^2));
+    np.random.choice(candidates) == candidates[randint(len)] in (anchor, slot) order; -1 where there is none.
+    Returns (ids (A, S) int64, counts (A, S, 2) [random_hard, semihard])."""
+    bank64 = np.asarray(bank, np.float64)
+    labels = np.asarray(labels)
+    anchors = np.asarray(anchors, F32)
+    pos_d = np.asarray(pos_d, F32)
+    A, S = pos_d.shape
+    ids = np.full((A, S), -1, np.int64)
+    counts = np.zeros((A, S, 2), np.int64)
+    m = F32(margin)
+    for i in range(A):
+        diff = bank64 - anchors[i].astype(np.float64)
+        dn = np.sqrt(np.einsum("ij,ij->i", diff, diff).astype(F32))            # float32 sqrt of the float32 value
+        neg = np.where(labels != anchor_labels[i])[0]
+        for s in range(S):
+            if pos_d[i, s] < 0:
+                continue
+            loss = (pos_d[i, s] - dn[neg]) + m                                    # float32, left to right
+            hard = neg[loss > 0]
+            semi = neg[(loss > 0) & (loss < m)]
+            counts[i, s] = (len(hard), len(semi))
+            if mode == "hardest":
+                if len(neg):
+                    j = int(np.argmax(loss))
+                    if loss[j] > 0:
+                        ids[i, s] = neg[j]
+                continue
+            cand = hard if mode == "random_hard" else semi
+            if len(cand):
+                ids[i, s] = cand[np.random.randint(0, len(cand))]
+    return ids, counts
+
+
 # ------------------------------------------------------------------------------------------------ CPU baselines (bench.py)
 def batch_hard_loss_grad_cpu(labels, emb, margin=0.5):
     """The headline step on the host, built from the reference's own distance call

@@ -33,6 +33,22 @@ def main():
         rd, ri = O.knn_exact(bank, q, 5)
         ok = np.array_equal(i, ri) and np.allclose(d, rd, rtol=1e-5) and np.array_equal(i8, ri[:4])
         ok = ok and np.array_equal(pred, O.knn_vote(labels[ri])) and i[0, 0] == 11 and i[0, 1] == 4000
+    # bank-scale semihard mining over the sharded bank: per-shard counts are all-gathered, the host draws the rank
+    # (same RNG state on every rank), the owning shard resolves it
+    rng = np.random.RandomState(3)
+    a_idx = rng.choice(len(bank), size=40, replace=False)
+    lab_ids = np.unique(labels, return_inverse=True)[1].astype(np.int32)
+    pos = np.stack([bank[rng.choice(np.flatnonzero((lab_ids == lab_ids[r]) & (np.arange(len(bank)) != r)), 2,
+                                    replace=False)] for r in a_idx])
+    pos_d = np.sqrt(((bank[a_idx][:, None, :].astype(np.float64) - pos.astype(np.float64)) ** 2).sum(-1)
+                    .astype(np.float32))
+    for mode in ("semihard", "random_hard", "hardest"):
+        np.random.seed(21)
+        got = clf.mine_negatives(bank[a_idx], lab_ids[a_idx], positives=pos, margin=0.5, mode=mode)
+        if rank == 0:
+            np.random.seed(21)
+            want, _ = O.mine_bank_modes(bank, lab_ids, bank[a_idx], lab_ids[a_idx], pos_d, 0.5, mode)
+            ok = ok and np.array_equal(got, want)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     # all ranks must hold the identical merged result
