@@ -554,8 +554,10 @@ def main():
             clf4 = BankKNNClassifier(n_neighbors=1, process_group=group, device=dev)
             clf4.fit_shard(bank4, ids4, lo4, n4, classes=np.arange(10_000))
             a_idx = torch.arange(0, n4, n4 // 65536, device=dev)[:65536]
-            anchors, _ = synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev) if world > 1 else (bank4, None)
-            anchors = anchors[a_idx].contiguous()
+            full4, _ = synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev) if world > 1 else (bank4, None)
+            anchors = full4[a_idx].contiguous()
+            positives = full4[(a_idx + 10_000) % n4].unsqueeze(1).contiguous()  # label = id % 10000: same class
+            del full4
             a_lab = ids4[a_idx].contiguous()
             for _ in range(2):
                 clf4.kneighbors_device(anchors, n_neighbors=1, exclude_labels=a_lab)
@@ -568,6 +570,18 @@ def main():
             m_ms = max_over_ranks(m0.elapsed_time(m1))
             mining = {"workload": "C4: hardest negative of 65536 anchors over a 1M x 256 bank (label-excluded 1-NN), "
                                   "%d GPU(s)" % world, "ms": m_ms, "anchors_per_sec": 65536 / (m_ms * 1e-3)}
+            # the generator's default strategy at bank scale: count pass + host rank draw + select pass
+            np.random.seed(0)
+            clf4.mine_negatives(anchors[:4096], a_lab[:4096], positives=positives[:4096], margin=MARGIN, mode="semihard")
+            barrier()
+            t0 = time.perf_counter()
+            sel = clf4.mine_negatives(anchors, a_lab, positives=positives, margin=MARGIN, mode="semihard")
+            torch.cuda.synchronize()
+            s_dt = max_over_ranks(time.perf_counter() - t0)
+            mining["semihard"] = {
+                "workload": "C4: semihard negative (datagenerators.py:196-199 over the whole bank) for 65536 "
+                            "(anchor, positive) pairs, 1M x 256 bank, %d GPU(s); two scans + host RNG draws" % world,
+                "ms": s_dt * 1e3, "pairs_per_sec": 65536 / s_dt, "pairs_with_a_candidate": int((sel >= 0).sum())}
         knn = {
             "metric": "knn_queries_per_sec_10M_bank", "value": knn_value, "unit": "queries/s", "n_gpus": world,
             "steps": kk, "warmup": kw, "ms_per_step": knn_ms / kk, "scaling": "strong",
