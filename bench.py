@@ -551,10 +551,12 @@ def main():
             lo4, hi4 = BankKNNClassifier.shard_bounds(n4, world, rank)
             bank4, _ = synth.make_device(hi4 - lo4, 256, row_offset=lo4, n_classes=10_000, noise=0.5, device=dev)
             ids4 = (torch.arange(n4, dtype=torch.int64, device=dev) % 10_000).to(torch.int32)
+            bank4 = lac.l2_normalize(bank4).detach().contiguous()  # embeddings_normalization=True, the reference default
             clf4 = BankKNNClassifier(n_neighbors=1, process_group=group, device=dev)
             clf4.fit_shard(bank4, ids4, lo4, n4, classes=np.arange(10_000))
             a_idx = torch.arange(0, n4, n4 // 65536, device=dev)[:65536]
-            full4, _ = synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev) if world > 1 else (bank4, None)
+            full4 = lac.l2_normalize(synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev)[0]).detach() \
+                if world > 1 else bank4
             anchors = full4[a_idx].contiguous()
             positives = full4[(a_idx + 10_000) % n4].unsqueeze(1).contiguous()  # label = id % 10000: same class
             del full4

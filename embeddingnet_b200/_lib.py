@@ -71,8 +71,8 @@ SIGNATURES = {
     "en_knn_accuracy": (c_int, [P, P, P, c_int64, c_int, P, c_int64, P, P]),
     "en_pair_dist_exact": (c_int, [P, P, c_int64, c_int, P, P]),
     "en_ws_bytes_mine_bank": (c_size_t, [c_int64, c_int]),
-    "en_mine_bank_count": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P, P, P, c_int64, c_int, P, P, c_size_t, P]),
-    "en_mine_bank_select": (c_int, [P, P, P, c_int64, c_int, c_float, c_int, P, P, P, P, P, P, c_int64, c_int64, c_int,
+    "en_mine_bank_count": (c_int, [P, P, P, c_int64, c_int, c_int, c_float, P, P, P, P, P, c_int64, c_int, P, P, c_size_t, P]),
+    "en_mine_bank_select": (c_int, [P, P, P, c_int64, c_int, c_int, c_float, c_int, P, P, P, P, P, P, c_int64, c_int64, c_int,
                                     P, P, c_size_t, P]),
     "en_dense_plane_bytes": (c_size_t, [c_int, c_int]),
     "en_dense_prepare": (c_int, [P, c_int, c_int, P, P, P]),

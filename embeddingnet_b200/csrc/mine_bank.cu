@@ -53,9 +53,7 @@ __global__ void pair_dist_exact_kernel(const float* __restrict__ a, const float*
   if (lane == 0) out[i] = sqrtf(static_cast<float>(acc));
 }
 
-template <bool kSelect>
-struct EpMine {
-  struct Params {
+struct MineParams {
     const float* anchors;        // (A, d) fp32
     const float* bank;           // (n, d) fp32 (this shard)
     const float* anchor_norms;   // (A,)
@@ -70,23 +68,28 @@ struct EpMine {
     int64_t A, n_bank, id_offset;
     int d, semihard;             // select pass: which predicate
     float margin, c_err;         // c_err: |d2~ - d2| <= c_err (|a|^2 + |b|^2)
-  };
+};
+
+// NS = positive slots actually in use (1, 2, 4 or 8): the per-element work is proportional to it
+template <bool kSelect, int NS>
+struct EpMine {
+  using Params = MineParams;
   struct Row {
-    float dap[MS];
+    float dap[NS];
     float na, dmax;
     int32_t la;
-    int32_t cnt_h[kSelect ? 1 : MS], cnt_s[kSelect ? 1 : MS];
-    unsigned long long mask[kSelect ? MS : 1];
-    int32_t run[kSelect ? MS : 1], tgt[kSelect ? MS : 1];
+    int32_t cnt_h[kSelect ? 1 : NS], cnt_s[kSelect ? 1 : NS];
+    unsigned long long mask[kSelect ? NS : 1];
+    int32_t run[kSelect ? NS : 1], tgt[kSelect ? NS : 1];
   };
-  static constexpr int kSmemBytes = kSelect ? tc::EPI_H * tc::BM * MS * 4 : 0;
+  static constexpr int kSmemBytes = kSelect ? tc::EPI_H * tc::BM * NS * 4 : 0;
 
   static __device__ void item_begin(const Params& p, Row& r, const tc::Ctx&, int64_t row, bool valid, int, int) {
     r.na = valid ? p.anchor_norms[row] : 0.f;
     r.la = valid ? p.anchor_labels[row] : 0;
     r.dmax = 0.f;
 #pragma unroll
-    for (int s = 0; s < MS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       const float v = valid ? p.pos_d[row * MS + s] : -1.f;
       r.dap[s] = v >= 0.f ? v : -INFINITY;  // unused slot: loss = -inf, no predicate holds
       r.dmax = fmaxf(r.dmax, v);
@@ -119,10 +122,13 @@ struct EpMine {
       const float dn = d2 * rs;
       // |d~ - d| <= e2 / d~ (+ the approximate sqrt and the float32 roundings of the loss); tiny distances: always exact
       const float eb = d2 > 4.f * e2 ? fmaf(e2, rs, 6e-7f * (dn + r.dmax)) : INFINITY;
+      // beyond every slot's d_ap + margin by more than the error bound: no predicate can hold (nor be uncertain) --
+      // the common case for a bank, and the reason this epilogue keeps up with the tensor pipe
+      if (!(dn <= r.dmax + eb)) continue;
       unsigned hard = 0, semi = 0;
       bool unc = false;
 #pragma unroll
-      for (int s = 0; s < MS; ++s) {
+      for (int s = 0; s < NS; ++s) {
         const float l = (r.dap[s] - dn) + p.margin;
         hard |= (l > 0.f ? 1u : 0u) << s;
         semi |= ((l > 0.f && l < p.margin) ? 1u : 0u) << s;
@@ -132,7 +138,7 @@ struct EpMine {
         const float de = exact_dist(p.anchors + row * p.d, p.bank + (col0 + j) * p.d, p.d);
         hard = semi = 0;
 #pragma unroll
-        for (int s = 0; s < MS; ++s) {
+        for (int s = 0; s < NS; ++s) {
           const float l = mining_loss(r.dap[s], de, p.margin);
           hard |= (l > 0.f ? 1u : 0u) << s;
           semi |= ((l > 0.f && l < p.margin) ? 1u : 0u) << s;
@@ -142,10 +148,10 @@ struct EpMine {
       if (kSelect) {
         const unsigned pick = p.semihard ? semi : hard;
 #pragma unroll
-        for (int s = 0; s < MS; ++s) r.mask[s] |= static_cast<unsigned long long>((pick >> s) & 1u) << (bit0 + j);
+        for (int s = 0; s < NS; ++s) r.mask[s] |= static_cast<unsigned long long>((pick >> s) & 1u) << (bit0 + j);
       } else {
 #pragma unroll
-        for (int s = 0; s < MS; ++s) {
+        for (int s = 0; s < NS; ++s) {
           r.cnt_h[s] += (hard >> s) & 1u;
           r.cnt_s[s] += (semi >> s) & 1u;
         }
@@ -159,11 +165,11 @@ struct EpMine {
     if (!kSelect) return;
     int32_t* sm = reinterpret_cast<int32_t*>(ctx.smem);
 #pragma unroll
-    for (int s = 0; s < MS; ++s) sm[(ctx.half * tc::BM + ctx.erow) * MS + s] = __popcll(r.mask[s]);
+    for (int s = 0; s < NS; ++s) sm[(ctx.half * tc::BM + ctx.erow) * NS + s] = __popcll(r.mask[s]);
     ptx::named_bar_sync(2, tc::EPI_WARPS * 32);
 #pragma unroll
-    for (int s = 0; s < MS; ++s) {
-      const int c0 = sm[ctx.erow * MS + s], c1 = sm[(tc::BM + ctx.erow) * MS + s];
+    for (int s = 0; s < NS; ++s) {
+      const int c0 = sm[ctx.erow * NS + s], c1 = sm[(tc::BM + ctx.erow) * NS + s];
       const int before = r.run[s] + (ctx.half ? c0 : 0);
       const int own = ctx.half ? c1 : c0;
       const int want = r.tgt[s] - before;
@@ -185,10 +191,10 @@ struct EpMine {
     if (kSelect) {
       if (ctx.half == 0)
 #pragma unroll
-        for (int s = 0; s < MS; ++s) p.running[row * MS + s] = r.run[s];
+        for (int s = 0; s < NS; ++s) p.running[row * MS + s] = r.run[s];
     } else {
 #pragma unroll
-      for (int s = 0; s < MS; ++s) {
+      for (int s = 0; s < NS; ++s) {
         if (r.cnt_h[s]) atomicAdd(&p.counts[(row * MS + s) * 2 + 0], r.cnt_h[s]);
         if (r.cnt_s[s]) atomicAdd(&p.counts[(row * MS + s) * 2 + 1], r.cnt_s[s]);
       }
@@ -229,8 +235,8 @@ int mine_prepare(const float* anchors, int64_t A, int d, const void* bank_hi, co
   return EN_OK;
 }
 
-template <bool kSelect>
-int mine_scan(const MineOperands& o, typename EpMine<kSelect>::Params ep, int64_t A, int64_t n_bank, int d,
+template <bool kSelect, int NS>
+int mine_scan(const MineOperands& o, const MineParams& ep, int64_t A, int64_t n_bank, int d,
               cudaStream_t st) {
   const int sms = device_sm_count();
   const int tiles_total = static_cast<int>((n_bank + tc::BN - 1) / tc::BN);
@@ -248,7 +254,7 @@ int mine_scan(const MineOperands& o, typename EpMine<kSelect>::Params ep, int64_
     const int tiles_here = tiles_total - base < chunk_tiles ? tiles_total - base : chunk_tiles;
     tc::Shape sh = tc::make_shape(A, static_cast<int64_t>(tiles_here) * tc::BN, d, splits, 3, o.bf16);
     sh.nt_base = base;
-    EN_CUDA(tc::launch<EpMine<kSelect>>(o.ah, o.al, o.bh, o.bl, sh, ep, sms, st));
+    EN_CUDA((tc::launch<EpMine<kSelect, NS>>(o.ah, o.al, o.bh, o.bl, sh, ep, sms, st)));
     ++launch_counter();
   }
   prof_end(st);
@@ -277,13 +283,14 @@ size_t en_ws_bytes_mine_bank(int64_t A, int d) {
 }
 
 int en_mine_bank_count(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
-                       float margin, const float* bank, const void* bank_hi, const void* bank_lo,
+                       int n_slots, float margin, const float* bank, const void* bank_hi, const void* bank_lo,
                        const float* bank_norms, const int32_t* bank_labels, int64_t n_bank, int precision,
                        int32_t* counts, void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(anchors && anchor_labels && pos_d && bank && bank_hi && bank_lo && bank_norms && bank_labels && counts &&
                  A > 0 && d > 0 && n_bank > 0,
              "en_mine_bank_count: bad arguments");
   EN_REQUIRE(precision == EN_PREC_TF32X3 || precision == EN_PREC_BF16X3, "en_mine_bank_count: unknown precision");
+  EN_REQUIRE(n_slots >= 1 && n_slots <= MS, "en_mine_bank_count: n_slots must be in [1, %d]", MS);
   EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_mine_bank_count: shard too large");
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < en_ws_bytes_mine_bank(A, d)) return fail(EN_ERR_WORKSPACE, "en_mine_bank_count: workspace too small");
@@ -292,14 +299,17 @@ int en_mine_bank_count(const float* anchors, const int32_t* anchor_labels, const
   MineOperands o;
   if (int rc = mine_prepare(anchors, A, d, bank_hi, bank_lo, n_bank, precision, w, st, o, "en_mine_bank_count")) return rc;
   EN_CUDA(cudaMemsetAsync(counts, 0, static_cast<size_t>(A) * MS * 2 * sizeof(int32_t), st));
-  EpMine<false>::Params ep{anchors, bank, o.an, bank_norms, anchor_labels, bank_labels, pos_d, counts, nullptr, nullptr,
-                           nullptr, A, n_bank, 0, d, 0, margin,
-                           static_cast<float>(cert_bound(precision, o.dpad) + 3e-7)};
-  return mine_scan<false>(o, ep, A, n_bank, d, st);
+  MineParams ep{anchors, bank, o.an, bank_norms, anchor_labels, bank_labels, pos_d, counts, nullptr,
+                              nullptr, nullptr, A, n_bank, 0, d, 0, margin,
+                              static_cast<float>(cert_bound(precision, o.dpad) + 3e-7)};
+  if (n_slots <= 1) return mine_scan<false, 1>(o, ep, A, n_bank, d, st);
+  if (n_slots <= 2) return mine_scan<false, 2>(o, ep, A, n_bank, d, st);
+  if (n_slots <= 4) return mine_scan<false, 4>(o, ep, A, n_bank, d, st);
+  return mine_scan<false, 8>(o, ep, A, n_bank, d, st);
 }
 
 int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
-                        float margin, int mode, const int32_t* rank, const float* bank, const void* bank_hi,
+                        int n_slots, float margin, int mode, const int32_t* rank, const float* bank, const void* bank_hi,
                         const void* bank_lo, const float* bank_norms, const int32_t* bank_labels, int64_t n_bank,
                         int64_t id_offset, int precision, int64_t* selected, void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(anchors && anchor_labels && pos_d && rank && bank && bank_hi && bank_lo && bank_norms && bank_labels &&
@@ -308,6 +318,7 @@ int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, cons
   EN_REQUIRE(mode == EN_MODE_SEMIHARD || mode == EN_MODE_RANDOM_HARD,
              "en_mine_bank_select: mode must be EN_MODE_SEMIHARD or EN_MODE_RANDOM_HARD (got %d)", mode);
   EN_REQUIRE(precision == EN_PREC_TF32X3 || precision == EN_PREC_BF16X3, "en_mine_bank_select: unknown precision");
+  EN_REQUIRE(n_slots >= 1 && n_slots <= MS, "en_mine_bank_select: n_slots must be in [1, %d]", MS);
   EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_mine_bank_select: shard too large");
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < en_ws_bytes_mine_bank(A, d)) return fail(EN_ERR_WORKSPACE, "en_mine_bank_select: workspace too small");
@@ -319,10 +330,13 @@ int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, cons
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_mine_bank_select: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(running, 0, static_cast<size_t>(A) * MS * sizeof(int32_t), st));
   EN_CUDA(cudaMemsetAsync(selected, 0xFF, static_cast<size_t>(A) * MS * sizeof(int64_t), st));  // -1
-  EpMine<true>::Params ep{anchors, bank, o.an, bank_norms, anchor_labels, bank_labels, pos_d, nullptr, rank, running,
-                          selected, A, n_bank, id_offset, d, mode == EN_MODE_SEMIHARD ? 1 : 0, margin,
-                          static_cast<float>(cert_bound(precision, o.dpad) + 3e-7)};
-  return mine_scan<true>(o, ep, A, n_bank, d, st);
+  MineParams ep{anchors, bank, o.an, bank_norms, anchor_labels, bank_labels, pos_d, nullptr, rank, running,
+                             selected, A, n_bank, id_offset, d, mode == EN_MODE_SEMIHARD ? 1 : 0, margin,
+                             static_cast<float>(cert_bound(precision, o.dpad) + 3e-7)};
+  if (n_slots <= 1) return mine_scan<true, 1>(o, ep, A, n_bank, d, st);
+  if (n_slots <= 2) return mine_scan<true, 2>(o, ep, A, n_bank, d, st);
+  if (n_slots <= 4) return mine_scan<true, 4>(o, ep, A, n_bank, d, st);
+  return mine_scan<true, 8>(o, ep, A, n_bank, d, st);
 }
 
 }  // extern "C"

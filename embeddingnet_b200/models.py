@@ -255,7 +255,7 @@ class BankKNNClassifier:
         ws = workspace(lib.en_ws_bytes_mine_bank(A, d), dev, "mine_bank")
         counts = torch.zeros((A, MS, 2), dtype=torch.int32, device=dev)
         if n > 0:
-            _lib.call("en_mine_bank_count", ptr(a), ptr(al), ptr(pos_d), A, d, ctypes.c_float(margin), ptr(self._bank),
+            _lib.call("en_mine_bank_count", ptr(a), ptr(al), ptr(pos_d), A, d, S, ctypes.c_float(margin), ptr(self._bank),
                       ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl), n, self._prec, ptr(counts), ptr(ws),
                       ws.numel(), stream_ptr())
         col = 0 if mode == "random_hard" else 1
@@ -270,21 +270,20 @@ class BankKNNClassifier:
         allc_h = allc.cpu().numpy().astype(np.int64)
         total = allc_h.sum(axis=0)
         local_rank = np.full((A, MS), -1, dtype=np.int32)
-        for i in range(A):                       # reference pair order => same RNG stream on every rank
-            for s in range(S):
-                c = int(total[i, s])
-                if c > 0:
-                    r = int(np.random.randint(0, c))
-                    for q in range(world):       # shards hold ascending id ranges: the owner is found by prefix
-                        if r < allc_h[q, i, s]:
-                            if q == rank:
-                                local_rank[i, s] = r
-                            break
-                        r -= int(allc_h[q, i, s])
+        # pairs with candidates in the reference's (anchor, slot) order => same RNG stream on every rank
+        ii, ss = np.nonzero(total[:, :S] > 0)
+        for i, s in zip(ii.tolist(), ss.tolist()):
+            r = int(np.random.randint(0, int(total[i, s])))
+            for q in range(world):               # shards hold ascending id ranges: the owner is found by prefix
+                if r < allc_h[q, i, s]:
+                    if q == rank:
+                        local_rank[i, s] = r
+                    break
+                r -= int(allc_h[q, i, s])
         sel = torch.full((A, MS), -1, dtype=torch.int64, device=dev)
         if n > 0:
             rk = torch.from_numpy(local_rank).to(dev)
-            _lib.call("en_mine_bank_select", ptr(a), ptr(al), ptr(pos_d), A, d, ctypes.c_float(margin), MODES[mode],
+            _lib.call("en_mine_bank_select", ptr(a), ptr(al), ptr(pos_d), A, d, S, ctypes.c_float(margin), MODES[mode],
                       ptr(rk), ptr(self._bank), ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl), n,
                       self._offset, self._prec, ptr(sel), ptr(ws), ws.numel(), stream_ptr())
         if world > 1:

@@ -228,6 +228,7 @@ int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* quer
  * en_mine_bank_count : counts (A, EN_MINE_MAX_SLOTS, 2) int32 = [random_hard, semihard] candidates in THIS shard.
  * en_mine_bank_select: rank (A, EN_MINE_MAX_SLOTS) int32 = 0-based rank among this shard's candidates of `mode` in
  *   ascending row id (< 0: nothing to select here) -> selected (A, EN_MINE_MAX_SLOTS) int64 global id or -1.
+ * n_slots = number of leading slots in use (1..EN_MINE_MAX_SLOTS; the arrays keep the EN_MINE_MAX_SLOTS stride).
  * The host draws the rank from the legacy NumPy RNG (np.random.choice(c) == c[randint(len(c))], dg:194,199); with a
  * sharded bank the per-shard counts are all-gathered and the owning shard resolves the rank.
  * en_pair_dist_exact: dist[i] = d(a_i, b_i) with the definition above (the d_ap inputs).
@@ -236,11 +237,11 @@ int en_knn_accuracy(const int64_t* ids, const int32_t* pred, const int32_t* quer
 int en_pair_dist_exact(const float* a, const float* b, int64_t n, int d, float* dist, void* stream);
 size_t en_ws_bytes_mine_bank(int64_t A, int d);
 int en_mine_bank_count(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
-                       float margin, const float* bank, const void* bank_hi, const void* bank_lo,
+                       int n_slots, float margin, const float* bank, const void* bank_hi, const void* bank_lo,
                        const float* bank_norms, const int32_t* bank_labels, int64_t n_bank, int precision,
                        int32_t* counts, void* ws, size_t ws_bytes, void* stream);
 int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, const float* pos_d, int64_t A, int d,
-                        float margin, int mode, const int32_t* rank, const float* bank, const void* bank_hi,
+                        int n_slots, float margin, int mode, const int32_t* rank, const float* bank, const void* bank_hi,
                         const void* bank_lo, const float* bank_norms, const int32_t* bank_labels, int64_t n_bank,
                         int64_t id_offset, int precision, int64_t* selected, void* ws, size_t ws_bytes, void* stream);
 

@@ -307,7 +307,7 @@ def test_bank_mining_counts_and_sharding_invariance():
         counts = torch.zeros((A, MS, 2), dtype=torch.int32, device=dev)
         ws = torch.empty(lib.en_ws_bytes_mine_bank(A, d), dtype=torch.uint8, device=dev)
         bl = c._labels[lo:hi].contiguous()
-        _lib.call("en_mine_bank_count", ptr(ta), ptr(tl), ptr(pd), A, d, ctypes.c_float(0.8), ptr(c._bank), ptr(c._hi),
+        _lib.call("en_mine_bank_count", ptr(ta), ptr(tl), ptr(pd), A, d, 2, ctypes.c_float(0.8), ptr(c._bank), ptr(c._hi),
                   ptr(c._lo), ptr(c._norms), ptr(bl), hi - lo, c._prec, ptr(counts), ptr(ws), ws.numel(), stream_ptr())
         parts.append((c, counts, ws, bl, lo, hi))
     total = sum(p[1].cpu().numpy().astype(np.int64) for p in parts)
@@ -323,7 +323,7 @@ def test_bank_mining_counts_and_sharding_invariance():
             mine = counts.cpu().numpy()[:, :, col]
             local = np.where((local >= 0) & (local < mine), local, -1).astype(np.int32)
             out = torch.full((A, MS), -1, dtype=torch.int64, device=dev)
-            _lib.call("en_mine_bank_select", ptr(ta), ptr(tl), ptr(pd), A, d, ctypes.c_float(0.8),
+            _lib.call("en_mine_bank_select", ptr(ta), ptr(tl), ptr(pd), A, d, 2, ctypes.c_float(0.8),
                       _lib.EN_MODE_RANDOM_HARD if mode == "random_hard" else _lib.EN_MODE_SEMIHARD,
                       ptr(torch.tensor(local, device=dev)), ptr(c._bank), ptr(c._hi), ptr(c._lo), ptr(c._norms), ptr(bl),
                       hi - lo, lo, c._prec, ptr(out), ptr(ws), ws.numel(), stream_ptr())
