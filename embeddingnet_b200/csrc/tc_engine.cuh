@@ -458,6 +458,30 @@ static __global__ void split_planes_bf16_kernel(const float* __restrict__ x, int
   uint32_t* hr = reinterpret_cast<uint32_t*>(hi + row * dpad);  // dpad is even (multiple of 64): 2 bf16 per store
   uint32_t* lr = reinterpret_cast<uint32_t*>(lo + row * dpad);
   double acc = 0.0;
+  if ((d & 3) == 0 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // four elements per lane and trip: one 128-bit load, two 64-bit stores (the 2-element form below was latency
+    // bound: 7.4 us for 4096 x 512 where the DRAM read takes 1.3 us)
+    uint2* h2 = reinterpret_cast<uint2*>(hr);
+    uint2* l2 = reinterpret_cast<uint2*>(lr);
+#pragma unroll 4
+    for (int c = 4 * lane; c < dpad; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        v = *reinterpret_cast<const float4*>(xr + c);
+        if (mu != nullptr) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mu + c));
+          v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+        }
+      }
+      const uint32_t h0 = to_bf16_bits(v.x), h1 = to_bf16_bits(v.y), h2b = to_bf16_bits(v.z), h3 = to_bf16_bits(v.w);
+      const uint32_t r0 = to_bf16_bits(v.x - __uint_as_float(h0 << 16)), r1 = to_bf16_bits(v.y - __uint_as_float(h1 << 16)),
+                     r2 = to_bf16_bits(v.z - __uint_as_float(h2b << 16)), r3 = to_bf16_bits(v.w - __uint_as_float(h3 << 16));
+      h2[c >> 2] = make_uint2(h0 | (h1 << 16), h2b | (h3 << 16));
+      l2[c >> 2] = make_uint2(r0 | (r1 << 16), r2 | (r3 << 16));
+      acc += (static_cast<double>(v.x) * static_cast<double>(v.x) + static_cast<double>(v.y) * static_cast<double>(v.y)) +
+             (static_cast<double>(v.z) * static_cast<double>(v.z) + static_cast<double>(v.w) * static_cast<double>(v.w));
+    }
+  } else
   for (int c = 2 * lane; c < dpad; c += 64) {
     float v0 = c < d ? xr[c] : 0.0f;
     float v1 = c + 1 < d ? xr[c + 1] : 0.0f;
