@@ -37,6 +37,20 @@ if what == "pairbwd":
             e = x.clone().requires_grad_(True)
             fn(labels, e).backward()
     torch.cuda.synchronize()
+if what == "mining":
+    # C4-shaped bank mining at reduced size: hardest (label-excluded 1-NN) and semihard (count + select passes)
+    n, A = 200_000, 16384
+    bank, _ = synth.make_device(n, 256, n_classes=2000, noise=0.5, device=dev)
+    bank = lac.l2_normalize(bank).detach().contiguous()
+    ids = (torch.arange(n, device=dev) % 2000).to(torch.int32)
+    clf = BankKNNClassifier(1, device=dev).fit_shard(bank, ids, 0, n, classes=np.arange(2000))
+    a_idx = torch.arange(0, n, n // A, device=dev)[:A]
+    anchors, a_lab = bank[a_idx].contiguous(), ids[a_idx].contiguous()
+    pos = bank[(a_idx + 2000) % n].unsqueeze(1).contiguous()
+    np.random.seed(0)
+    for mode in ("hardest", "semihard"):
+        clf.mine_negatives(anchors, a_lab, positives=pos, margin=0.5, mode=mode)
+    torch.cuda.synchronize()
 if what in ("all", "knn"):
     n, Q = 400_000, 8192
     bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
