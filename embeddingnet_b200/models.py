@@ -28,6 +28,29 @@ from . import _lib
 from ._runtime import as_cuda_f32, ptr, require_cuda, stream_ptr, workspace
 
 
+def draw_candidate_ranks(shard_counts, n_slots, my_rank):
+    """Host half of the sharded mining protocol.  shard_counts (P, A, slots): candidates of every
+    (anchor, slot) pair in each shard.  For every pair with candidates, in the reference's (anchor, slot) order, draw
+    ``np.random.randint(total)`` -- the stream ``np.random.choice(candidates)`` consumes (dg:194,199) -- and hand the
+    draw to the shard that owns that position of the ascending-id candidate list (prefix over the shard ranges).
+    Returns (A, slots) int32: the rank inside ``my_rank``'s own candidates, -1 where another shard (or none) owns it.
+    Every rank calls this with the same counts and the same RNG state, so all agree without further communication."""
+    counts = np.asarray(shard_counts).astype(np.int64)
+    world, A, slots = counts.shape
+    total = counts.sum(axis=0)
+    local = np.full((A, slots), -1, dtype=np.int32)
+    ii, ss = np.nonzero(total[:, :n_slots] > 0)
+    for i, s in zip(ii.tolist(), ss.tolist()):
+        r = int(np.random.randint(0, int(total[i, s])))
+        for q in range(world):
+            if r < counts[q, i, s]:
+                if q == my_rank:
+                    local[i, s] = r
+                break
+            r -= int(counts[q, i, s])
+    return local
+
+
 class BankKNNClassifier:
     """``sklearn.neighbors.KNeighborsClassifier``-shaped brute-force classifier over an encoding bank on B200.
 
@@ -267,19 +290,7 @@ class BankKNNClassifier:
             dist_.all_gather_into_tensor(allc, mine, group=self.process_group)   # (pairs, P) counts, SURVEY 8(e)
         else:
             allc = mine.unsqueeze(0)
-        allc_h = allc.cpu().numpy().astype(np.int64)
-        total = allc_h.sum(axis=0)
-        local_rank = np.full((A, MS), -1, dtype=np.int32)
-        # pairs with candidates in the reference's (anchor, slot) order => same RNG stream on every rank
-        ii, ss = np.nonzero(total[:, :S] > 0)
-        for i, s in zip(ii.tolist(), ss.tolist()):
-            r = int(np.random.randint(0, int(total[i, s])))
-            for q in range(world):               # shards hold ascending id ranges: the owner is found by prefix
-                if r < allc_h[q, i, s]:
-                    if q == rank:
-                        local_rank[i, s] = r
-                    break
-                r -= int(allc_h[q, i, s])
+        local_rank = draw_candidate_ranks(allc.cpu().numpy(), S, rank)
         sel = torch.full((A, MS), -1, dtype=torch.int64, device=dev)
         if n > 0:
             rk = torch.from_numpy(local_rank).to(dev)

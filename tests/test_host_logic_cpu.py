@@ -116,6 +116,73 @@ def test_two_rank_gloo_gather_merge_matches_single_rank():
     assert want[0, 0] == 20 and want[0, 1] == 150
 
 
+def _shard_candidates(bank, labels, anchors, a_lab, pos_d, margin, mode, lo, hi):
+    """Per-shard candidate id lists of every (anchor, slot) pair: stands in for en_mine_bank_count / _select."""
+    out = {}
+    b64 = bank.astype(np.float64)
+    for i in range(len(anchors)):
+        dn = np.sqrt(((b64[lo:hi] - anchors[i].astype(np.float64)) ** 2).sum(1).astype(np.float32))
+        neg = np.flatnonzero(labels[lo:hi] != a_lab[i])
+        for s in range(pos_d.shape[1]):
+            loss = (np.float32(pos_d[i, s]) - dn[neg]) + np.float32(margin)
+            ok = (loss > 0) if mode == "random_hard" else ((loss > 0) & (loss < np.float32(margin)))
+            out[(i, s)] = lo + neg[ok]
+    return out
+
+
+def _gloo_mining_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from embeddingnet_b200.models import BankKNNClassifier, draw_candidate_ranks
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    bank, labels = synth.make_numpy(301, 12, n_classes=9, noise=0.6)
+    anchors, a_lab = bank[[3, 77, 200, 250]].copy(), labels[[3, 77, 200, 250]]
+    pos_d = np.array([[2.0, 2.4], [1.9, 2.2], [2.5, 2.1], [2.3, 2.0]], np.float32)
+    lo, hi = BankKNNClassifier.shard_bounds(len(bank), world, rank)
+    cands = _shard_candidates(bank, labels, anchors, a_lab, pos_d, 0.5, "semihard", lo, hi)
+    mine = torch.tensor([[len(cands[(i, s)]) for s in range(2)] for i in range(4)], dtype=torch.int32)
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)                                    # (pairs, P) counts, SURVEY 8(e) row 2
+    np.random.seed(77)                                             # same RNG state on every rank
+    local = draw_candidate_ranks(torch.stack(allc).numpy(), 2, rank)
+    sel = torch.full((4, 2), -1, dtype=torch.int64)
+    for i in range(4):
+        for s in range(2):
+            if local[i, s] >= 0:
+                sel[i, s] = int(cands[(i, s)][local[i, s]])        # the owner shard resolves its rank
+    dist.all_reduce(sel, op=dist.ReduceOp.MAX)
+    q.put((rank, sel.numpy(), np.random.random_sample()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bank_mining_protocol_matches_single_rank():
+    """Sharded semihard mining: per-shard counts -> all-gather -> identical rank draws -> owner resolves ->
+    all-reduce(max) gives, on every rank, exactly what the unsharded oracle draws from the same RNG state."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_gloo_mining_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {r: (sel, rnd) for r, sel, rnd in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bank, labels = synth.make_numpy(301, 12, n_classes=9, noise=0.6)
+    anchors, a_lab = bank[[3, 77, 200, 250]].copy(), labels[[3, 77, 200, 250]]
+    pos_d = np.array([[2.0, 2.4], [1.9, 2.2], [2.5, 2.1], [2.3, 2.0]], np.float32)
+    np.random.seed(77)
+    want, counts = O.mine_bank_modes(bank, labels, anchors, a_lab, pos_d, 0.5, "semihard")
+    rnd = np.random.random_sample()
+    assert (want >= 0).sum() >= 4 and counts[:, :, 1].max() > 3  # not vacuous
+    for r in range(2):
+        np.testing.assert_array_equal(results[r][0], want)
+        assert results[r][1] == rnd
+
+
 def test_product_path_never_imports_oracle():
     """The package must not depend on oracle/ (the judge checks exactly this)."""
     import re
