@@ -1165,7 +1165,7 @@ int prepare_operands(const float* emb, int64_t B, int d, Workspace& w, cudaStrea
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "workspace too small or misaligned");
   if (centre) {
-    tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, tc::kMeanRows), 0, st>>>(emb, B, d, mu);
+    tc::launch_column_mean(emb, B, d, mu, st);
     EN_LAUNCHED("column_mean_kernel");
   }
   if (bf16) {

@@ -542,7 +542,7 @@ int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d
   float* mu = w.take<float>(d);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "pair backward: workspace too small or misaligned");
   dim3 tb(32, 8), tg(static_cast<unsigned>(bpad / 32), static_cast<unsigned>(rows_t / 32));
-  tc::column_mean_kernel<<<static_cast<unsigned>((d + 31) / 32), dim3(32, tc::kMeanRows), 0, st>>>(emb, B, d, mu);
+  tc::launch_column_mean(emb, B, d, mu, st);
   EN_LAUNCHED("column_mean_kernel");
   // GEMM1 also runs on the centred rows (norms are the centred norms): ||a-b|| is unchanged, S loses its
   // one-sided truncation bias, and with it the hinge-activity flips against the float64 oracle

@@ -501,15 +501,16 @@ static __global__ void split_planes_bf16_kernel(const float* __restrict__ x, int
   if (lane == 0 && norms) norms[row] = static_cast<float>(acc);
 }
 
-// Column means of x (B x d), float64 accumulation in a fixed order (deterministic): one block of (32, 8) threads per
-// 32 columns.  Used to centre the operands (see split_planes_kernel).
-constexpr int kMeanRows = 32;  // row groups per block (blockDim.y)
+// Column means of x (B x d), float64 accumulation in a fixed order (deterministic).  Used to centre the operands
+// (see split_planes_kernel).
+constexpr int kMeanCols = 8;     // columns per block: 8 floats = one 32-byte sector per row
+constexpr int kMeanRows = 128;   // row groups per block (blockDim.y)
 static __global__ void column_mean_kernel(const float* __restrict__ e, int64_t B, int d, float* __restrict__ mu) {
-  // one block of (32, kMeanRows) threads per 32 columns; each thread keeps four independent partial sums over its
-  // rows so that the loads overlap (the 8-group, one-accumulator version took 58 us at 4096 x 512: latency bound),
-  // then the row groups are reduced through shared memory in a fixed order (deterministic)
-  __shared__ double part[kMeanRows][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  // one block of (kMeanCols, kMeanRows) threads per 8 columns (64 blocks at d = 512: the 32-column version kept only
+  // 16 SMs busy and took 23 us at 4096 x 512); each thread keeps four independent partial sums over its rows so that
+  // the loads overlap, then the row groups are reduced through shared memory in a fixed order (deterministic)
+  __shared__ double part[kMeanRows][kMeanCols + 1];
+  const int c = blockIdx.x * kMeanCols + threadIdx.x;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (c < d) {
     int64_t r = threadIdx.y;
@@ -525,11 +526,15 @@ static __global__ void column_mean_kernel(const float* __restrict__ e, int64_t B
   }
   part[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (threadIdx.y == 0 && c < d) {
-    double s = 0.0;
-    for (int g = 0; g < kMeanRows; ++g) s += part[g][threadIdx.x];
-    mu[c] = static_cast<float>(s / static_cast<double>(B));
+  // fixed-shape tree over the row groups
+  for (int h = kMeanRows / 2; h > 0; h >>= 1) {
+    if (static_cast<int>(threadIdx.y) < h) part[threadIdx.y][threadIdx.x] += part[threadIdx.y + h][threadIdx.x];
+    __syncthreads();
   }
+  if (threadIdx.y == 0 && c < d) mu[c] = static_cast<float>(part[0][threadIdx.x] / static_cast<double>(B));
+}
+inline void launch_column_mean(const float* e, int64_t B, int d, float* mu, cudaStream_t st) {
+  column_mean_kernel<<<static_cast<unsigned>((d + kMeanCols - 1) / kMeanCols), dim3(kMeanCols, kMeanRows), 0, st>>>(e, B, d, mu);
 }
 
 inline cudaError_t launch_split(const float* x, int64_t rows, int d, int64_t ldx, int dpad, float* hi, float* lo,
