@@ -414,7 +414,10 @@ def main():
     line = {
         "metric": "batch_hard_triplet_loss_grad_embeddings_per_sec", "value": value, "unit": "embeddings/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 in/out; tensor-core selection on split-BF16 planes (3 MMAs per k-step), float64 re-evaluation "
+                 "of every selected distance",
+        "data": "synthetic",
         "config": {"workload": TRIPLET_WORKLOAD, "l2": "256 MiB memset between timed steps (L2 flush)",
                    "timing": "per-step CUDA events around one CUDA-graph replay of fwd+bwd; sum over steps, max over ranks",
                    "parallelism": "replicas only (the in-batch path does not shard)" if world > 1 else "1 GPU",
