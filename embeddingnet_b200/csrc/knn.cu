@@ -922,8 +922,8 @@ int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, i
 }
 
 int en_knn_finalize_dist(const double* d2, int64_t n, float* dist, void* stream) {
-  EN_REQUIRE(d2 && dist && n >= 0, "en_knn_finalize_dist: bad arguments");
-  if (n == 0) return EN_OK;
+  if (n == 0) return EN_OK;  // empty query set: nothing to do (the pointers of empty buffers may be null)
+  EN_REQUIRE(d2 && dist && n > 0, "en_knn_finalize_dist: bad arguments");
   sqrt_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(d2, n, dist);
   EN_LAUNCHED("sqrt_kernel");
   return EN_OK;

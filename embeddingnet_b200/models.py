@@ -243,9 +243,14 @@ class BankKNNClassifier:
         lib = _lib.load()
         dev = self.device
         a = as_cuda_f32(anchors, dev)
+        if a.dim() != 2:
+            raise ValueError("anchors must be (A, d)")
         A, d = a.shape
         if d != self._d:
             raise ValueError("anchor dimension %d != bank dimension %d" % (d, self._d))
+        if A == 0:
+            S0 = np.asarray(pos_dist).shape[1] if pos_dist is not None else np.asarray(positives).shape[1]
+            return np.zeros((0, S0), dtype=np.int64)
         al = (anchor_labels if isinstance(anchor_labels, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(np.asarray(anchor_labels, dtype=np.int32)))).to(dev, torch.int32).contiguous()
         MS = _lib.EN_MINE_MAX_SLOTS
@@ -311,7 +316,9 @@ class BankKNNClassifier:
             q = q.reshape(1, -1)
         _, ids = self._search(q, k)
         pred = torch.empty(q.shape[0], dtype=torch.int32, device=self.device)
-        _lib.call("en_knn_vote", ptr(ids), q.shape[0], k, ptr(self._labels), self._n_total, ptr(pred), stream_ptr())
+        if q.shape[0] > 0:
+            _lib.call("en_knn_vote", ptr(ids), q.shape[0], k, ptr(self._labels), self._n_total, ptr(pred),
+                      stream_ptr())
         return pred, ids
 
     def predict(self, X):

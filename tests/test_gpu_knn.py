@@ -340,3 +340,50 @@ def test_bank_mining_counts_and_sharding_invariance():
                 loss = (np.float32(pos_d[i, s]) - dn[neg]) + np.float32(0.8)
                 cand = neg[loss > 0] if mode == "random_hard" else neg[(loss > 0) & (loss < np.float32(0.8))]
                 assert sel[i, s] == (cand[len(cand) // 2] if len(cand) else -1), (i, s, mode)
+
+
+def test_knn_large_bank_planted_neighbours_and_empty_inputs():
+    """Size-independent properties at a bank too large for the float64 oracle (2M x 128): every query is a bank row
+    plus a small perturbation, so its nearest neighbour is known by construction; the result must not depend on the
+    operand format or on how the bank is cut into shards, and (nearly) every query must carry a certificate."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    dev = torch.device("cuda")
+    n, d, Q, k = 2_000_000, 128, 3000, 5
+    bank, _ = synth.make_device(n, d, n_classes=20_000, noise=0.5, device=dev)
+    lab = (torch.arange(n, device=dev) % 20_000).to(torch.int32)
+    src = torch.arange(0, n, n // Q, device=dev)[:Q]
+    noise, _ = synth.make_device(Q, d, seed_noise=99, device=dev)
+    q = (bank[src] + 0.02 * noise).contiguous()
+    results = {}
+    for prec in ("bf16x3", "tf32x3"):
+        clf = BankKNNClassifier(n_neighbors=k, precision=prec, device=dev).fit_shard(bank, lab, 0, n)
+        dist, ids = clf.kneighbors_device(q)
+        assert clf.last_uncertified <= Q // 100
+        assert torch.equal(ids[:, 0], src)                                   # the planted row
+        assert bool((dist[:, 1:] >= dist[:, :-1]).all())                     # ascending
+        results[prec] = ids.cpu().numpy()
+        if prec == "bf16x3":
+            # three unequal shards through the C-ABI merge
+            parts_d, parts_i = [], []
+            for lo, hi in ((0, 700_001), (700_001, 1_500_000), (1_500_000, n)):
+                c = BankKNNClassifier(n_neighbors=k, device=dev).fit_shard(bank[lo:hi], lab, lo, n)
+                d2, ii = c._search(q, k)
+                parts_d.append(d2)
+                parts_i.append(ii)
+                del c
+            D, I = torch.stack(parts_d).contiguous(), torch.stack(parts_i).contiguous()
+            d2m, idm = torch.empty_like(parts_d[0]), torch.empty_like(parts_i[0])
+            _lib.call("en_knn_merge", ptr(D), ptr(I), 3, Q, k, ptr(d2m), ptr(idm), stream_ptr())
+            np.testing.assert_array_equal(idm.cpu().numpy(), results[prec])
+        # empty inputs
+        dd, ii = clf.kneighbors(np.zeros((0, d), np.float32))
+        assert dd.shape == (0, k) and ii.shape == (0, k)
+        assert clf.predict(np.zeros((0, d), np.float32)).shape == (0,)
+        assert clf.mine_negatives(np.zeros((0, d), np.float32), np.zeros(0, np.int32),
+                                  pos_dist=np.zeros((0, 2), np.float32)).shape == (0, 2)
+        del clf
+    np.testing.assert_array_equal(results["bf16x3"], results["tf32x3"])
