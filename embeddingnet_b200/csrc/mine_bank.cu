@@ -111,6 +111,21 @@ struct EpMine {
     tc::stage_columns(ctx, p.bank_norms, p.bank_labels, col0, p.n_bank);
     const int ncols = static_cast<int>(p.n_bank - col0 < 32 ? p.n_bank - col0 : 32);
     const int bit0 = static_cast<int>(col0 % tc::BN) - ctx.half * tc::COLS_PER_EPI_WARP;  // 0 or 32 inside the half
+    // Chunk-level reject in the proxy domain (two instructions per element): with T = d_max + A, A >= the error
+    // bound of any column of this chunk whose distance exceeds d_max (A uses the chunk's largest norm; e2 / d~ <=
+    // e2 / d_max there), every element with  |a|^2 + t > T^2 (1 + 2e-6)  is beyond every slot's d_ap + margin by
+    // more than its own bound: no predicate holds and none is uncertain.  ncu (round 1): without it the count pass
+    // ran 413 M warp instructions per launch with the tensor pipe 22 % active.
+    {
+      const float nbmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ctx.wf[ctx.lane])));
+      const float A = p.c_err * (r.na + nbmax) / r.dmax + 1e-6f * r.dmax;
+      const float T = r.dmax + A;
+      const float tthr = T * T * 1.000002f - r.na;
+      float tmin = INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tmin = fminf(tmin, fmaf(-2.f, dot[j], ctx.wf[j]));
+      if (tmin > tthr) return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float nb = ctx.wf[j];
