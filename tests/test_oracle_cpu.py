@@ -158,3 +158,53 @@ def test_oracle_matches_reference_live():
         rows = np.concatenate([c * 7 + p for c, p in zip(cls, picks)])
         trip, _ = O.mine_batch_triplets(table[rows], 6, 5, 0.4, mode)
         np.testing.assert_array_equal(rows[trip], np.stack([A.ravel(), P.ravel(), N.ravel()], 1))
+
+
+@pytest.mark.parametrize("mode", ["hardest", "random_hard", "semihard"])
+def test_bank_mining_oracle_is_the_selection_callables_over_the_whole_bank(mode):
+    """O.mine_bank_modes (the oracle of the bank-scale mining kernels) must be nothing but the reference's selection
+    callables (dg:188-199, pinned above by the golden `select_vectors`) applied to loss_values = (d_ap - d_an) + m
+    over all bank rows of another class, pairs in (anchor, slot) order, same RNG stream."""
+    bank, labels = synth.make_numpy(400, 24, n_classes=11, noise=0.7, relu=True)
+    a_idx = np.array([3, 57, 200, 399, 123])
+    anchors, a_lab = bank[a_idx], labels[a_idx]
+    rng = np.random.RandomState(4)
+    pos_d = (1.2 + rng.rand(5, 3)).astype(np.float32)
+    pos_d[2, 1] = -1.0  # unused slot
+    margin = 0.6
+    np.random.seed(9)
+    got, counts = O.mine_bank_modes(bank, labels, anchors, a_lab, pos_d, margin, mode)
+    after = np.random.random_sample()
+    fn = {"hardest": O.hardest_negative, "random_hard": O.random_hard_negative, "semihard": O.semihard_negative}[mode]
+    np.random.seed(9)
+    want = np.full((5, 3), -1, np.int64)
+    b64 = bank.astype(np.float64)
+    for i in range(5):
+        dn = np.sqrt(((b64 - anchors[i].astype(np.float64)) ** 2).sum(1).astype(np.float32))
+        neg = np.flatnonzero(labels != a_lab[i])
+        for s in range(3):
+            if pos_d[i, s] < 0:
+                continue
+            loss_values = pos_d[i, s] - dn[neg] + margin                         # dg:235
+            k = fn(loss_values, margin)
+            if k is not None:
+                want[i, s] = neg[k]                                              # dg:240
+            assert counts[i, s, 0] == int((loss_values > 0).sum())
+            assert counts[i, s, 1] == int(((loss_values > 0) & (loss_values < margin)).sum())
+    np.testing.assert_array_equal(got, want)
+    assert np.random.random_sample() == after
+    assert (got >= 0).sum() >= 5
+
+
+def test_dense_relu_oracle_known_answers():
+    """backbones.py:114-119: Dense(relu) then K.l2_normalize; identity kernel, bias shift, all-negative row -> zeros."""
+    x = np.array([[3.0, -4.0, 0.0], [-1.0, -2.0, -3.0], [0.0, 0.0, 2.0]], np.float32)
+    eye = np.eye(3, dtype=np.float32)
+    np.testing.assert_array_equal(O.dense_relu(x, eye), np.maximum(x, 0))
+    y = O.dense_relu(x, eye, bias=np.array([0.0, 4.0, 0.0], np.float32), normalize=True)
+    np.testing.assert_allclose(y[0], [1.0, 0.0, 0.0], atol=1e-7)                 # relu(3, 0, 0) normalised
+    np.testing.assert_allclose(y[1], [0.0, 1.0, 0.0], atol=1e-7)                 # relu(-1, 2, -3) normalised
+    assert np.all(O.dense_relu(x[1:2], eye, normalize=True) == 0)                # zero row stays zero (eps clamp)
+    w, _ = synth.make_numpy(3, 5, seed_noise=3)
+    np.testing.assert_allclose(O.dense_relu(x, w, normalize=True), O.l2_normalize(np.maximum(x @ w, 0)), rtol=1e-6,
+                               atol=1e-7)
