@@ -1,7 +1,9 @@
 // Tensor-core distance engine for sm_100a: C = A . B^T as a tcgen05/TMEM GEMM fed by TMA, with the FP32
-// inputs split into two TF32 planes (hi, lo) so that hi*hi + hi*lo + lo*hi reproduces the FP32 product to
-// ~2^-21 ("3xTF32").  The 128x128 accumulator tile never leaves the SM: a pluggable epilogue functor consumes it
-// straight out of TMEM (label masks, per-anchor reductions, top-k, ...).
+// inputs split into two planes (hi, lo) so that hi*hi + hi*lo + lo*hi reproduces the FP32 product: TF32 planes
+// ("3xTF32", ~2^-21, kind::tf32) where the value itself is used, BF16 planes ("split-BF16", ~2^-16 worst case,
+// kind::f16 at twice the rate) where the GEMM only selects candidates that are re-evaluated exactly.  The 128x128
+// accumulator tile never leaves the SM: a pluggable epilogue functor consumes it straight out of TMEM (label masks,
+// per-anchor reductions, top-k, candidate counts, ...).
 //
 // Replaces, for the large shapes, the arithmetic the reference delegates to
 //   sklearn.metrics.pairwise_distances      (embedding_net/datagenerators.py:219)
