@@ -3,8 +3,8 @@
 // of EmbeddingNet.predict (embedding_net/models.py:123-124).
 //
 //   stage 1a  en_knn_shard_topk : tcgen05 distance GEMM (queries x bank shard; split-BF16 or 3xTF32 planes) with a
-//                                 per-query running
-//                                 top-(k+slack) kept in registers by the epilogue thread that owns the query row;
+//                                 per-query running top-(k+slack) kept in registers by the epilogue thread that owns
+//                                 the query row;
 //   stage 1b  en_knn_stream_topk: for a handful of queries (the reference's one-image-per-call pattern) a CUDA-core
 //                                 fp32 streaming scan bounded by HBM bandwidth;
 //   stage 2   exact re-rank     : the surviving candidates are re-evaluated as float64 sum (q-b)^2 and ordered by
