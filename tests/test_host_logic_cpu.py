@@ -203,3 +203,34 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.EmbeddingNetB200Error):
         _lib.load()
+
+
+def test_draw_candidate_ranks_assigns_each_draw_to_exactly_one_shard():
+    """Three shards, random counts: for every pair the draw lands in exactly one shard, at the position the
+    concatenated (ascending-id) candidate list has for it; the RNG stream equals one randint per non-empty pair."""
+    from embeddingnet_b200.models import draw_candidate_ranks
+
+    rng = np.random.RandomState(1)
+    counts = rng.randint(0, 4, size=(3, 6, 8))
+    counts[:, 2, :] = 0            # an anchor without any candidate
+    counts[:, :, 5:] = 0           # slots not in use
+    np.random.seed(42)
+    per_rank = [None] * 3
+    for q in range(3):
+        np.random.seed(42)
+        per_rank[q] = draw_candidate_ranks(counts, 5, q)
+        after = np.random.random_sample()
+    total = counts.sum(axis=0)
+    np.random.seed(42)
+    for i in range(6):
+        for s in range(5):
+            owners = [q for q in range(3) if per_rank[q][i, s] >= 0]
+            if total[i, s] == 0:
+                assert owners == []
+                continue
+            r = np.random.randint(0, total[i, s])
+            assert len(owners) == 1
+            q = owners[0]
+            assert counts[:q, i, s].sum() + per_rank[q][i, s] == r and per_rank[q][i, s] < counts[q, i, s]
+    assert np.random.random_sample() == after
+    assert all((p[:, 5:] == -1).all() for p in per_rank)
