@@ -118,7 +118,8 @@ struct EpMine {
     // ran 413 M warp instructions per launch with the tensor pipe 22 % active.
     {
       const float nbmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ctx.wf[ctx.lane])));
-      const float A = p.c_err * (r.na + nbmax) / r.dmax + 1e-6f * r.dmax;
+      // (a non-positive d_max -- only with a non-positive margin and no slot in use -- disables the reject)
+      const float A = r.dmax > 0.f ? p.c_err * (r.na + nbmax) / r.dmax + 1e-6f * r.dmax : INFINITY;
       const float T = r.dmax + A;
       const float tthr = T * T * 1.000002f - r.na;
       float tmin = INFINITY;
