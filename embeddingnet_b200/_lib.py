@@ -38,6 +38,8 @@ SIGNATURES = {
     "en_siamese_l2_bwd": (c_int, [P, P, P, c_int64, c_int, P, P, P]),
     "en_siamese_l1_fwd": (c_int, [P, P, c_int64, P, P]),
     "en_siamese_l1_bwd": (c_int, [P, P, P, c_int64, P, P, P]),
+    "en_query_distances": (c_int, [P, P, c_int64, c_int, P, P]),
+    "en_scale_inplace": (c_int, [P, c_int64, P, P]),
     "en_ws_bytes_pairwise": (c_size_t, [c_int64, c_int, c_int]),
     "en_pairwise_dist": (c_int, [P, c_int64, c_int, c_int, c_int, P, P, c_size_t, P]),
     "en_mine_batch_scan": (c_int, [P, P, c_int64, P, c_int64, c_float, P, P, P, P]),

@@ -68,9 +68,6 @@ __device__ __forceinline__ float bh_pack(float t, int in_tile) {
   return __uint_as_float((__float_as_uint(t) & kKeyMask) | static_cast<unsigned>(in_tile));
 }
 __device__ __forceinline__ bool bh_valid(float key) { return fabsf(key) < 1.0e38f; }
-__device__ __forceinline__ int bh_index(float key, int tile) {
-  return bh_valid(key) ? tile * tc::BN + static_cast<int>(__float_as_uint(key) & 0x7Fu) : -1;
-}
 
 // running top-2 of packed keys; masked elements carry -kBig / +kBig and never win
 __device__ __forceinline__ void top2_max(float& v1, float& v2, float k) {
@@ -223,29 +220,119 @@ struct BhPick {
   int idx;
 };
 
-template <bool kMax>
-__device__ __forceinline__ void bh_consider(BhPick& win, const float* __restrict__ emb, int d, float na, float nb,
-                                            int64_t row, float best, float val, int idx, int lane, float band_c) {
-  // error band of the split-BF16 dot product (band_c, see bh_band()) times |a||b| <= (|a|^2 + |b|^2) / 2; the proxy
-  // error is twice the dot error, and both the best and the contender carry it
-  bool contender = false;
-  if (idx >= 0) {
-    const float band = band_c * (na + nb) + 1e-30f;
-    contender = kMax ? (val >= best - band) : (val <= best + band);
-  }
-  unsigned m = __ballot_sync(0xffffffffu, contender);
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const int ci = __shfl_sync(0xffffffffu, idx, src);
-    const double d2 = exact_d2(emb, d, row, ci, lane);
-    const bool better = kMax ? (d2 > win.d2 || (d2 == win.d2 && ci < win.idx))
-                             : (d2 < win.d2 || (d2 == win.d2 && ci < win.idx));
-    if (win.idx < 0 || better) {
-      win.d2 = d2;
-      win.idx = ci;
+// Contender thresholds.  |dot~ - dot| <= c |a||b|, so a proxy t = |b|^2 - 2 a.b is off by at most c (|a|^2 + |b|^2)
+// (band_c already holds 2c for "best and contender both carry it" plus the index-packing truncation).  The
+// candidate's norm is bounded from the proxy itself (t >= |b|^2 - 2|a||b|  =>  |b| <= |a| + sqrt(|a|^2 + t)), and
+// that bound grows with t, so ONE threshold per side covers the best entry and every contender: positives have
+// t <= bp; negatives have t <= bn + band_n, evaluated at that (slightly inflated) upper end.
+struct BhThr {
+  float p, n;
+};
+__device__ __forceinline__ BhThr bh_thresholds(float na, float bp, float bn, float band_c) {
+  const float sa = sqrtf(na);
+  auto band_at = [&](float t) {
+    const float sb = sa + sqrtf(fmaxf(na + t, 0.f)) * 1.0001f;
+    return band_c * (na + sb * sb) + 1e-30f;
+  };
+  BhThr r;
+  r.p = bp - band_at(bp);
+  r.n = bn + band_at(bn + band_at(bn) * 1.5f) * 1.0001f;
+  return r;
+}
+
+__device__ __forceinline__ void bh_update_max(BhPick& win, double d2, int ci) {
+  if (win.idx < 0 || d2 > win.d2 || (d2 == win.d2 && ci < win.idx)) win = BhPick{d2, ci};
+}
+__device__ __forceinline__ void bh_update_min(BhPick& win, double d2, int ci) {
+  if (win.idx < 0 || d2 < win.d2 || (d2 == win.d2 && ci < win.idx)) win = BhPick{d2, ci};
+}
+
+// Exact re-scan of ONE record slot: every row the slot covers (64 columns of the row view, 32 rows of the column
+// view) with the wanted label relation is re-evaluated in float64.  Used when the slot is SATURATED: its second
+// entry is itself a contender, so the slot may hide further contenders behind its top-2 (three duplicates of the
+// hardest negative in adjacent rows -- the reference's sampler draws with replacement,
+// embedding_net/datagenerators.py:205 -- or three near-ties).  A hidden entry's packed key is never better than the
+// slot's second one, so "second entry outside the band" proves that nothing hidden matters.
+__device__ __noinline__ void bh_rescan_slot(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                            int64_t B, int d, int64_t row, int32_t la, int t, int my_tile,
+                                            bool want_same, int lane, BhPick& win) {
+  const int tile = t >> 2, slot = t & 3;
+  const bool col_view = tile < my_tile;
+  const int len = col_view ? 32 : 64;
+  const int64_t j0 = static_cast<int64_t>(tile) * tc::BN + slot * len;
+  for (int64_t jb = j0; jb < j0 + len; jb += 32) {
+    const int64_t j = jb + lane;
+    const bool ok = j < B && j != row;
+    const bool want = ok && ((__ldg(&labels[ok ? j : 0]) == la) == want_same);
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = static_cast<int>(jb) + src;
+      const double d2 = exact_d2(emb, d, row, ci, lane);
+      if (want_same) bh_update_max(win, d2, ci);
+      else bh_update_min(win, d2, ci);
     }
   }
+}
+
+// General resolver (one warp per anchor): every record entry inside the band is re-evaluated exactly, saturated
+// slots are re-scanned.  Ties resolve to the lowest index because every candidate that can tie is evaluated and the
+// (d2, index) order is applied on the exact values -- the order of the packed keys (which for negative proxies
+// favours the HIGHER in-tile index among equal values) never decides anything.
+__device__ __noinline__ void bh_resolve(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                        const BhCand* __restrict__ mine, int n_cand, int my_tile, int64_t row,
+                                        int64_t B, int d, BhThr thr, int lane, BhPick& pos, BhPick& neg) {
+  const int32_t la = labels[row];
+#pragma unroll 1
+  for (int t0 = 0; t0 < n_cand; t0 += 32) {
+    const int t = t0 + lane;
+    float4 v = make_float4(-kBig, -kBig, kBig, kBig);
+    // slots 2,3 exist only for tiles left of the anchor's own (column view); see EpBatchHard
+    if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
+    const bool cp1 = bh_valid(v.x) && v.x >= thr.p, cp2 = bh_valid(v.y) && v.y >= thr.p;
+    const bool cn1 = bh_valid(v.z) && v.z <= thr.n, cn2 = bh_valid(v.w) && v.w <= thr.n;
+    const int ip = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.x) & 0x7Fu);
+    const int in = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.z) & 0x7Fu);
+    unsigned m = __ballot_sync(0xffffffffu, cp1 && !cp2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = __shfl_sync(0xffffffffu, ip, src);
+      bh_update_max(pos, exact_d2(emb, d, row, ci, lane), ci);
+    }
+    m = __ballot_sync(0xffffffffu, cn1 && !cn2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = __shfl_sync(0xffffffffu, in, src);
+      bh_update_min(neg, exact_d2(emb, d, row, ci, lane), ci);
+    }
+    m = __ballot_sync(0xffffffffu, cp2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, true, lane, pos);
+    }
+    m = __ballot_sync(0xffffffffu, cn2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, false, lane, neg);
+    }
+  }
+}
+
+// No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row maximum; a
+// degenerate batch, handled exactly by a brute-force scan (never on a training path).
+__device__ __noinline__ BhPick bh_row_maximum(const float* __restrict__ emb, int64_t B, int d, int64_t row, int lane) {
+  BhPick rmx{-1.0, -1};
+  for (int64_t j = 0; j < B; ++j) {
+    if (j == row) continue;
+    const double d2 = exact_d2(emb, d, row, j, lane);
+    if (rmx.idx < 0 || d2 > rmx.d2) { rmx.d2 = d2; rmx.idx = static_cast<int>(j); }
+  }
+  return rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -336,38 +423,10 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
       bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
-    // pass 2: exact re-evaluation of everything inside the band (kept compact: each warp runs this code once, so
-    // instruction fetch dominates when it is unrolled)
+    // pass 2: exact re-evaluation of everything inside the band, saturated slots re-scanned
     BhPick pos{-1.0, -1}, neg{1e300, -1};
-#pragma unroll 1
-    for (int t0 = 0; t0 < n_cand; t0 += 32) {
-      const int t = t0 + lane;
-      float4 v = make_float4(-kBig, -kBig, kBig, kBig);
-      if (slot_valid(t)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
-      // the index inside the record's tile rides in the low mantissa bits of each proxy
-      const int4 ix = make_int4(bh_index(v.x, t >> 2), bh_index(v.y, t >> 2), bh_index(v.z, t >> 2),
-                                bh_index(v.w, t >> 2));
-      // the four norm loads are independent: issue them together, ahead of the dependent ballots
-      const float nb0 = ix.x >= 0 ? __ldg(&norms[ix.x]) : 0.f;
-      const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
-      const float nb2 = ix.z >= 0 ? __ldg(&norms[ix.z]) : 0.f;
-      const float nb3 = ix.w >= 0 ? __ldg(&norms[ix.w]) : 0.f;
-      bh_consider<true>(pos, emb, d, na, nb0, row, bp, v.x, ix.x, lane, band_c);
-      bh_consider<true>(pos, emb, d, na, nb1, row, bp, v.y, ix.y, lane, band_c);
-      bh_consider<false>(neg, emb, d, na, nb2, row, bn, v.z, ix.z, lane, band_c);
-      bh_consider<false>(neg, emb, d, na, nb3, row, bn, v.w, ix.w, lane, band_c);
-    }
-    if (neg.idx < 0) {
-      // No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row
-      // maximum; a degenerate batch, handled exactly by a brute-force scan (never on a training path).
-      BhPick rmx{-1.0, -1};
-      for (int64_t j = 0; j < B; ++j) {
-        if (j == row) continue;
-        const double d2 = exact_d2(emb, d, row, j, lane);
-        if (rmx.idx < 0 || d2 > rmx.d2) { rmx.d2 = d2; rmx.idx = static_cast<int>(j); }
-      }
-      neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
-    }
+    bh_resolve(emb, labels, mine, n_cand, my_tile, row, B, d, bh_thresholds(na, bp, bn, band_c), lane, pos, neg);
+    if (neg.idx < 0) neg = bh_row_maximum(emb, B, d, row, lane);
     const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
     const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
     const double z = hp - hn;
@@ -449,22 +508,18 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
       bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
       bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
-    // Contenders inside the error band of the best proxy.  The band needs the candidate's norm; the proxy itself
-    // bounds it (t = |b|^2 - 2 a.b >= |b|^2 - 2 |a||b|  =>  |b| <= |a| + sqrt(|a|^2 + t)), which saves a dependent
-    // gather of 16 norms per lane at the price of a somewhat wider band (a few more exact evaluations).  The index
-    // inside the record's tile rides in the low mantissa bits.  Each lane queues up to two contenders per kind.
-    // The bound grows with the proxy, so one threshold per side covers every contender: positives have t <= bp;
-    // negatives have t <= bn + band_n, evaluated at that (slightly inflated) upper end.  Three square roots per
-    // anchor instead of sixteen IEEE ones per lane (ncu, round 1: the kernel is issue bound, ~1000 instructions
-    // per anchor).
+    // Contenders inside the error band of the best proxy (bh_thresholds(): the band needs the candidate's norm, which
+    // the proxy itself bounds -- no dependent gather of 16 norms per lane, three square roots per anchor instead of
+    // sixteen IEEE ones per lane; ncu, round 1: the kernel is issue bound, ~1000 instructions per anchor).  The index
+    // inside the record's tile rides in the low mantissa bits.  Each lane queues up to two contenders per kind.  A
+    // record whose SECOND entry is a contender marks a saturated slot (it may hide more): general resolver.
     int pc = 0, nc = 0, pi0 = -1, pi1 = -1, ni0 = -1, ni1 = -1;
-    const float sa = sqrtf(na);
-    auto band_at = [&](float t) {
-      const float sb = sa + sqrtf(fmaxf(na + t, 0.f)) * 1.0001f;
-      return band_c * (na + sb * sb) + 1e-30f;
-    };
-    const float thr_p = bp - band_at(bp);
-    const float thr_n = bn + band_at(bn + band_at(bn) * 1.5f) * 1.0001f;
+    const BhThr thr = bh_thresholds(na, bp, bn, band_c);
+    const float thr_p = thr.p, thr_n = thr.n;
+    bool sat = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      sat = sat || (bh_valid(v[u].y) && v[u].y >= thr_p) || (bh_valid(v[u].w) && v[u].w <= thr_n);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int tile = (lane + 32 * u) >> 2;
@@ -489,7 +544,7 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
     BhPick pos{-1.0, -1}, neg{1e300, -1};
     float4 a[DV], pr[DV], nr[DV];
     int rounds = 0;
-    const bool overflow = __any_sync(0xffffffffu, pc > 2 || nc > 2);
+    const bool overflow = __any_sync(0xffffffffu, sat || pc > 2 || nc > 2);
     const bool no_neg = !__any_sync(0xffffffffu, nc > 0);
     if (!overflow && !no_neg) {
       // Each round re-evaluates one positive and one negative contender exactly, all row loads of the round in one
@@ -542,30 +597,9 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
         ++rounds;
       }
     } else {
-      // three contenders queued on one lane, or no negative at all: per-candidate path with exact norms
-#pragma unroll 1
-      for (int u = 0; u < 4; ++u) {
-        const int tile = (lane + 32 * u) >> 2;
-        const int4 ix = make_int4(bh_index(v[u].x, tile), bh_index(v[u].y, tile), bh_index(v[u].z, tile),
-                                  bh_index(v[u].w, tile));
-        const float nb0 = ix.x >= 0 ? __ldg(&norms[ix.x]) : 0.f;
-        const float nb1 = ix.y >= 0 ? __ldg(&norms[ix.y]) : 0.f;
-        const float nb2 = ix.z >= 0 ? __ldg(&norms[ix.z]) : 0.f;
-        const float nb3 = ix.w >= 0 ? __ldg(&norms[ix.w]) : 0.f;
-        bh_consider<true>(pos, emb, d, na, nb0, row, bp, v[u].x, ix.x, lane, band_c);
-        bh_consider<true>(pos, emb, d, na, nb1, row, bp, v[u].y, ix.y, lane, band_c);
-        bh_consider<false>(neg, emb, d, na, nb2, row, bn, v[u].z, ix.z, lane, band_c);
-        bh_consider<false>(neg, emb, d, na, nb3, row, bn, v[u].w, ix.w, lane, band_c);
-      }
-      if (neg.idx < 0) {  // no other-label row at all: Moindrot's degenerate row maximum (see the generic kernel)
-        BhPick rmx{-1.0, -1};
-        for (int64_t j = 0; j < B; ++j) {
-          if (j == row) continue;
-          const double d2 = exact_d2(emb, d, row, j, lane);
-          if (rmx.idx < 0 || d2 > rmx.d2) { rmx.d2 = d2; rmx.idx = static_cast<int>(j); }
-        }
-        neg = rmx.idx >= 0 ? rmx : BhPick{0.0, -1};
-      }
+      // a saturated slot, three contenders queued on one lane, or no negative at all: general resolver
+      bh_resolve(emb, labels, mine, n_cand, my_tile, row, B, d, thr, lane, pos, neg);
+      if (neg.idx < 0) neg = bh_row_maximum(emb, B, d, row, lane);
     }
     // a single round leaves the winners' rows in registers for the gradient
     const bool rows_cached = rounds == 1;

@@ -212,7 +212,7 @@ class _BatchHard(torch.autograd.Function):
             _lib.call("en_batch_hard_fwd_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
                       int(soft), ptr(loss), ptr(saved_i[0]), ptr(saved_i[1]), ptr(saved_f[0]), ptr(saved_f[1]),
                       ptr(saved_f[2]), None, ptr(gemb), ptr(ws), ws.numel(), stream_ptr())
-            ctx.save_for_backward(gemb)
+            ctx.gemb = gemb   # not save_for_backward: backward hands this very buffer to autograd (no copy)
         else:
             _lib.call("en_batch_hard_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
                       int(soft), ptr(loss), ptr(saved_i[0]), ptr(saved_i[1]), ptr(saved_f[0]), ptr(saved_f[1]),
@@ -221,8 +221,15 @@ class _BatchHard(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        (gemb,) = ctx.saved_tensors
-        return gemb * g.to(torch.float32), None, None, None, None
+        gemb = getattr(ctx, "gemb", None)
+        if gemb is None:
+            raise RuntimeError("batch_hard_triplet_loss: backward was already run for this forward (the fused step "
+                               "stores d loss / d emb once and hands the buffer over); call the loss again")
+        ctx.gemb = None
+        g = g.contiguous().to(torch.float32).reshape(1)
+        # upstream gradient applied in place; the kernel returns at once when it is exactly 1 (plain loss.backward())
+        _lib.call("en_scale_inplace", ptr(gemb), gemb.numel(), ptr(g), stream_ptr())
+        return gemb, None, None, None, None
 
 
 def batch_hard_triplet_loss(margin=0.5, squared=False, soft=False):

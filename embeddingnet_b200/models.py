@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import ctypes
 import os
-import pickle
 import random
 
 import numpy as np
@@ -149,6 +148,11 @@ class BankKNNClassifier:
             raise ValueError("query dimension %d != bank dimension %d" % (d, self._d))
         if not (1 <= k <= _lib.EN_KNN_MAX_K):
             raise ValueError("n_neighbors must be in [1, %d]" % _lib.EN_KNN_MAX_K)
+        if k > self._n_total and exclude_labels is None:
+            # scikit-learn's message and behaviour (neighbors/_base.py): never pad with id -1, which Python indexing
+            # (labels[-1], models.py:139) would silently turn into the LAST bank label
+            raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d, "
+                             "n_samples = %d" % (k, self._n_total, Q))
         n = self._bank.shape[0]
         d2 = torch.full((Q, k), float("inf"), dtype=torch.float64, device=dev)
         ids = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
@@ -327,7 +331,10 @@ class BankKNNClassifier:
 
     def score_topk(self, X, y):
         """Batched ``calculate_prediction_accuracy`` (models.py:144-161): one scan, on-device top-1 / top-5 tally."""
-        k = max(self.n_neighbors, 5)
+        if self.n_neighbors > self._n_total:
+            raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d" %
+                             (self.n_neighbors, self._n_total))
+        k = min(max(self.n_neighbors, 5), self._n_total)  # a bank of fewer than 5 rows: top-"5" = all of them
         q = as_cuda_f32(X, self.device)
         Q = q.shape[0]
         _, ids = self._search(q, k)
@@ -411,9 +418,9 @@ class EmbeddingNet:
 
     def save_encodings(self, encoded_training_data, save_folder="./", save_file_name="encodings.pkl"):
         """models.py:86-90 (the fitted GPU classifier is not picklable and is dropped)."""
-        data = {k: v for k, v in encoded_training_data.items() if k != "knn_classifier"}
-        with open(os.path.join(save_folder, save_file_name), "wb") as f:
-            pickle.dump(data, f)
+        from .utils import save_encodings
+
+        save_encodings(encoded_training_data, save_folder, save_file_name)  # keeps {paths, labels, encodings} only
 
     def load_encodings(self, path_to_encodings, fit_knn=True):
         """What tools/test.py:22 calls (absent in the snapshot): ``utils.load_encodings`` + classifier fit."""
@@ -443,23 +450,31 @@ class EmbeddingNet:
         return enc.reshape(1, -1) if enc.ndim == 1 else enc   # np.squeeze quirk for a one-row bank (models.py:82)
 
     def _nn1(self):
-        clf = self.encoded_training_data.get("_nn1")
-        if clf is None:
+        """1-NN searcher over the current bank.  Cached on the object (never inside the user-visible bank dict, which
+        ``save_encodings`` pickles) and rebuilt when 'encodings' / 'labels' are replaced."""
+        data = self.encoded_training_data
+        enc, labels = data["encodings"], data["labels"]
+        key = (id(enc), getattr(enc, "shape", None), id(labels), len(labels))
+        cache = getattr(self, "_nn1_cache", None)
+        if cache is None or cache[0] != key:
             clf = BankKNNClassifier(n_neighbors=1)
-            clf.fit(self._bank_matrix(), self.encoded_training_data["labels"])
-            self.encoded_training_data["_nn1"] = clf
-        return clf
+            clf.fit(self._bank_matrix(), labels)
+            cache = (key, clf, enc, labels)   # holds the arrays: their ids cannot be recycled while cached
+            self._nn1_cache = cache
+        return cache[1]
 
     def calculate_distances(self, encoding):
         """The method ``predict`` calls but the snapshot never defines (models.py:123): Euclidean distance from one
         encoding to every bank row, shape (N,)."""
-        dev = require_cuda()
-        bank = as_cuda_f32(self._bank_matrix(), dev)
-        q = as_cuda_f32(np.asarray(encoding, np.float32).reshape(1, -1), dev).expand(bank.shape[0], -1).contiguous()
-        n, d = bank.shape  # row-wise sqrt(max(sum (a-b)^2, 1e-7)) kernel of the Siamese head
-        dist = torch.empty((n, 1), dtype=torch.float32, device=dev)
-        _lib.call("en_siamese_l2_fwd", ptr(q), ptr(bank), n, d, ptr(dist), stream_ptr())
-        return dist.reshape(-1).cpu().numpy()
+        clf = self._nn1()                      # the fitted device bank: no re-upload, no (N, d) broadcast of the query
+        bank = clf._bank
+        n, d = bank.shape
+        q = as_cuda_f32(np.asarray(encoding, np.float32).reshape(1, -1), bank.device)
+        if q.shape[1] != d:
+            raise ValueError("encoding dimension %d != bank dimension %d" % (q.shape[1], d))
+        dist = torch.empty(n, dtype=torch.float32, device=bank.device)
+        _lib.call("en_query_distances", ptr(bank), ptr(q), n, d, ptr(dist), stream_ptr())  # one pass over the bank
+        return dist.cpu().numpy()
 
     def predict(self, image):
         """models.py:115-126: nearest bank row (np.argmin -> lowest index on ties) -> its label."""

@@ -76,6 +76,16 @@ int en_siamese_l1_fwd(const float* e1, const float* e2, int64_t n, float* out, v
 int en_siamese_l1_bwd(const float* e1, const float* e2, const float* gout, int64_t n, float* g1, float* g2,
                       void* stream);
 
+/* calculate_distances(encoding): the method EmbeddingNet.predict calls at models.py:123 (undefined in the snapshot;
+ * np.argmin over its result at models.py:124): dist[i] = sqrt(sum((bank[i] - query)^2)), one query row against all
+ * n bank rows, no clamp (an exact match reports 0).  Reads the bank once: n * d * 4 bytes. */
+int en_query_distances(const float* bank, const float* query, int64_t n, int d, float* dist, void* stream);
+
+/* x[0..n) *= scale[0] in place (scale is a DEVICE scalar): the upstream gradient of a scalar loss applied to the
+ * d loss / d emb that the fused forward+backward entry points store (Keras multiplies the loss by sample / loss
+ * weights before differentiating, losses_and_accuracies.py callables are used through model.compile, train.py:160). */
+int en_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+
 /* ---------------------------------------------------------------- pairwise distances + in-batch mining */
 /* sklearn.metrics.pairwise_distances(x) as called at datagenerators.py:219, with sklearn's float32 semantics
  * (float64 -2xy+|x|^2+|y|^2, cast f32, clamp >= 0, zero diagonal, sqrt unless `squared`).  out is (n, n).

@@ -216,6 +216,102 @@ def test_batch_hard_near_tie_contenders_take_the_exact_rounds():
     assert rel_err(g.cpu().numpy(), gref) < 1e-4
 
 
+def run_batch_hard(x, lab, margin=0.5, squared=False, soft=False):
+    """en_batch_hard_fwd_bwd through the C ABI -> (loss, hp_idx, hn_idx, hp, hn, grad) as NumPy."""
+    import ctypes
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr, workspace
+
+    B, d = x.shape
+    e = torch.tensor(x, device="cuda")
+    l = torch.tensor(lab, device="cuda", dtype=torch.int32)
+    lib = _lib.load()
+    ws = workspace(lib.en_ws_bytes_batch_hard(B, d), e.device, "t")
+    loss = torch.empty((), device="cuda")
+    si = torch.empty((2, B), dtype=torch.int32, device="cuda")
+    sf = torch.empty((3, B), dtype=torch.float32, device="cuda")
+    g = torch.empty_like(e)
+    _lib.call("en_batch_hard_fwd_bwd", ptr(e), ptr(l), B, d, ctypes.c_float(margin), int(squared), int(soft),
+              ptr(loss), ptr(si[0]), ptr(si[1]), ptr(sf[0]), ptr(sf[1]), ptr(sf[2]), None, ptr(g), ptr(ws),
+              ws.numel(), stream_ptr())
+    torch.cuda.synchronize()
+    return (loss.item(), si[0].cpu().numpy(), si[1].cpu().numpy(), sf[0].cpu().numpy(), sf[1].cpu().numpy(),
+            g.cpu().numpy())
+
+
+@pytest.mark.parametrize("ncls,per,d", [(512, 8, 128),   # B = 4096: fast finalize (DV = 1), 32 row tiles
+                                        (512, 8, 512),   # the headline shape (DV = 4)
+                                        (48, 8, 100)])   # 384 rows, 3 tiles, generic finalize kernel
+@pytest.mark.parametrize("n_dup", [3, 5])
+@pytest.mark.parametrize("kind", ["exact", "near"])
+def test_batch_hard_saturated_slots(ncls, per, d, n_dup, kind):
+    """Three / five copies (exact, or 1e-7 apart) of one row in ADJACENT rows = inside one record slot (one 64-column
+    half of the row view, one 32-row quarter of the column view), placed so that they are the hardest negative and
+    the hardest positive of anchors in earlier tiles (row view), the same tile and later tiles (column view).  The
+    epilogue keeps two entries per slot: the finalize kernel has to notice the saturated slot and re-scan it.  The
+    reference's sampler draws with replacement (embedding_net/datagenerators.py:205) and batches are class-major, so
+    this is what a real batch with a twice-repeated image looks like.  Unit post-ReLU rows: cos > 0.5, i.e. negative
+    proxies, where a packed key grows with a SMALLER in-tile index."""
+    rng = np.random.RandomState(11 + n_dup)
+    x, lab = make_batch(ncls, per, d, True, False)
+    B = len(lab)
+    tiles = (B + 127) // 128
+    tm = tiles // 2
+    last = np.arange((tiles - 1) * 128, B)
+
+    def plant(rows, src):
+        y = x[src] + 0.15 * np.abs(x[src]).mean() * rng.randn(d).astype(np.float32)
+        y = unit_rows(np.maximum(y, 0)[None])[0]
+        for r in rows:
+            x[r] = y if kind == "exact" else y + (rng.randn(d) * 1e-7 * np.abs(y)).astype(np.float32)
+
+    a, b = 5, B - 7                                        # anchors before / after tile tm
+    g1 = np.arange(tm * 128 + 8 + 1, tm * 128 + 8 + 1 + n_dup)    # class rows tm*128+8 .. +15: half 0, quarter 0
+    g2 = np.arange(tm * 128 + 72 + 2, tm * 128 + 72 + 2 + n_dup)  # class rows tm*128+72 .. +79: half 1, quarter 2
+    plant(g1, a)
+    plant(g2, b)
+    # positives across tiles: one row of tile 0 and one of the last tile join the classes of the two groups; pick the
+    # rows least similar to the planted vector so that the copies are their FARTHEST class members
+    far0 = int(np.argmin(x[:128] @ x[g1[0]]))
+    far1 = int(last[np.argmin(x[last] @ x[g1[0]])])
+    lab[far0] = lab[g1[0]]
+    lab[far1] = lab[g1[0]]
+    far2 = int(np.argmin(np.where(np.arange(128) == far0, np.inf, x[:128] @ x[g2[0]])))
+    far3 = int(last[np.argmin(np.where(last == far1, np.inf, x[last] @ x[g2[0]]))])
+    lab[far2] = lab[g2[0]]
+    lab[far3] = lab[g2[0]]
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    planted = np.zeros(B, bool)
+    planted[g1] = planted[g2] = True
+    # the test must bite: copies are hardest negatives / positives for anchors on both sides of tile tm
+    hn_hit = planted[np.maximum(ref["hn_idx"], 0)] & (ref["hn_idx"] >= 0)
+    hp_hit = planted[np.maximum(ref["hp_idx"], 0)] & (ref["hp_idx"] >= 0)
+    rows = np.arange(B)
+    for hit in (hn_hit, hp_hit):
+        assert hit[rows < tm * 128].any() and hit[rows >= (tm + 1) * 128].any(), "planted rows are not selected"
+    loss, hp_idx, hn_idx, hp, hn, g = run_batch_hard(x, lab)
+    np.testing.assert_array_equal(hn_idx, ref["hn_idx"])
+    np.testing.assert_array_equal(hp_idx, ref["hp_idx"])
+    np.testing.assert_allclose(hp, ref["hp"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(hn, ref["hn"], rtol=1e-5, atol=1e-7)
+    assert abs(loss - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    _, gref = O.batch_hard_grad_analytic(lab, x, 0.5, False, False)
+    assert rel_err(g, gref) < 1e-4
+
+
+def test_batch_hard_collapsed_batch():
+    """Every embedding identical (a collapsed model early in training): all candidates tie exactly, every slot is
+    saturated for every anchor; indices are the lowest ones, the loss is the margin."""
+    x, lab = make_batch(32, 8, 128, True, False)
+    x[:] = x[0]
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    loss, hp_idx, hn_idx, hp, hn, g = run_batch_hard(x, lab)
+    np.testing.assert_array_equal(hp_idx, ref["hp_idx"])
+    np.testing.assert_array_equal(hn_idx, ref["hn_idx"])
+    assert abs(loss - 0.5) < 1e-6 and float(ref["loss"]) == 0.5
+    assert np.abs(g).max() == 0.0          # all distances are 0: no direction, zero gradient (sqrt(0) convention)
+
+
 def test_batch_hard_full_size_properties():
     """B = 4096, d = 512 (the headline shape): compare with the float64 oracle on a row subset, plus
     permutation invariance of the loss and equivariance of the gradient."""
@@ -248,6 +344,15 @@ def test_batch_hard_full_size_properties():
     loss2.backward()
     assert abs(loss2.item() - loss.item()) <= 2e-6 * abs(loss.item())
     assert rel_err(e2.grad.cpu().numpy(), e.grad.cpu().numpy()[perm]) < 1e-5
+    # the headline shape against the oracle itself: selected indices bit-exact, gradient 1e-4
+    _, hp_idx, hn_idx, hp, hn, g = run_batch_hard(x, lab)
+    np.testing.assert_array_equal(hp_idx, full["hp_idx"])
+    np.testing.assert_array_equal(hn_idx, full["hn_idx"])
+    np.testing.assert_allclose(hp, full["hp"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(hn, full["hn"], rtol=1e-5, atol=1e-7)
+    _, gref = O.batch_hard_grad_analytic(lab, x, 0.5, False, False)
+    assert rel_err(g, gref) < 1e-4
+    assert rel_err(e.grad.cpu().numpy(), gref) < 1e-4
 
 
 BA_SHAPES = [(32, 8, 128, True, False), (16, 8, 256, True, True), (7, 5, 33, False, True), (37, 9, 100, True, True),

@@ -43,6 +43,11 @@ def test_knn_vs_oracle(N, d, Q, k, precision):
     q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=max(2, N // 20), noise=0.6, relu=True)
     q = unit_rows(q)
     clf = BankKNNClassifier(n_neighbors=min(k, 5), precision=precision).fit(bank, labels)
+    if k > N:
+        # scikit-learn raises here; padding with id -1 would make models.py:139's labels[idx] return the LAST label
+        with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):
+            clf.kneighbors(q, n_neighbors=k)
+        k = N
     dist, idx = clf.kneighbors(q, n_neighbors=k)
     assert clf.last_uncertified <= max(1, Q // 20)  # the certificate covers (nearly) every query on tie-free data
     rd, ri = O.knn_exact(bank, q, k)
@@ -227,6 +232,61 @@ def test_embeddingnet_predict_api(tmp_path):
         _, ri = O.knn_exact(bank, q[i:i + 1], 5)
         assert top5 == [names[j] for j in ri[0]]
         assert pred.shape == (1,) and pred[0] == O.knn_vote(np.array(names)[ri])[0]
+
+
+def test_saved_bank_keeps_the_reference_layout_after_predict(tmp_path):
+    """generate_encodings -> predict -> save_encodings (the order tools/train.py and test.py use): the pickle holds
+    exactly the reference's {paths, labels, encodings} (models.py:80-90), no cached GPU classifier, and loads
+    without this package; the 1-NN cache follows a replaced bank."""
+    import pickle
+    from embeddingnet_b200.models import EmbeddingNet
+
+    bank, labels = synth.make_numpy(300, 32, n_classes=15, noise=0.4)
+    names = ["c%02d" % l for l in labels]
+    net = EmbeddingNet({"model": {}, "encodings": {"knn_k": 5}})
+    net.encoded_training_data = {"paths": ["%d.png" % i for i in range(300)], "labels": names, "encodings": bank}
+    net.fit_knn()
+    q, _ = synth.make_numpy(3, 32, seed_noise=synth.SEED_QUERY, n_classes=15, noise=0.4)
+    assert net.predict_encoding(q[:1]) == O.predict_1nn(bank, names, q[0])
+    net.save_encodings(net.encoded_training_data, str(tmp_path), "enc.pkl")
+    with open(tmp_path / "enc.pkl", "rb") as f:
+        raw = pickle.load(f)
+    assert sorted(raw) == ["encodings", "labels", "paths"]
+    assert isinstance(raw["encodings"], np.ndarray) and raw["encodings"].dtype == np.float32
+    assert sorted(k for k in net.encoded_training_data if not k.startswith("knn")) == ["encodings", "labels", "paths"]
+    # replace the bank in place: predictions must follow it (no stale cache)
+    bank2 = bank[::-1].copy()
+    net.encoded_training_data["encodings"] = bank2
+    net.encoded_training_data["labels"] = names[::-1]
+    for i in range(3):
+        assert net.predict_encoding(q[i:i + 1]) == O.predict_1nn(bank2, names[::-1], q[i])
+    # calculate_distances: plain Euclidean distances over the fitted device bank; an exact match reports 0
+    dists = net.calculate_distances(bank2[17])
+    want = np.sqrt(O.sqdist_exact(bank2[17:18], bank2)[0])
+    assert dists[17] == 0.0 and int(np.argmin(dists)) == 17
+    np.testing.assert_allclose(dists, want, rtol=1e-5, atol=1e-6)
+
+
+def test_calculate_distances_at_bank_scale():
+    """1M x 256 bank (BASELINE config 4's size): one pass over the resident bank, no per-call upload or broadcast."""
+    from embeddingnet_b200.models import EmbeddingNet
+
+    n, d = 1_000_000, 256
+    bank_t, _ = synth.make_device(n, d, n_classes=10_000, noise=0.5)
+    bank = bank_t.cpu().numpy()
+    net = EmbeddingNet({"model": {}, "encodings": {}})
+    net.encoded_training_data = {"paths": [], "labels": list(range(n)), "encodings": bank}
+    q = bank[123_457] + 0.01
+    dists = net.calculate_distances(q)
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    dists = net.calculate_distances(q)
+    assert torch.cuda.memory_allocated() - before < 64 * 1024 * 1024   # nothing bank-sized is allocated per call
+    assert dists.shape == (n,) and int(np.argmin(dists)) == 123_457
+    rows = np.arange(0, n, 9973)
+    want = np.sqrt(O.sqdist_exact(q[None], bank[rows])[0])
+    np.testing.assert_allclose(dists[rows], want, rtol=1e-5)
+    assert net.predict_encoding(q) == 123_457
 
 
 def test_sharded_knn_over_nccl():

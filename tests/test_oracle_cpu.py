@@ -138,6 +138,28 @@ def test_analytic_gradients_match_autograd():
     np.testing.assert_allclose(O.contrastive_allpairs_grad_analytic(lab, x7), g, rtol=1e-5, atol=1e-10)
 
 
+def test_batch_hard_analytic_gradient_matches_autograd():
+    """The closed form used at the headline shape (B = 4096, d = 512) is pinned to the autograd oracle on small
+    batches: duplicated rows (exact ties, zero distances), a single-class batch, squared / soft variants."""
+    from conftest import unit_rows
+
+    x, lab = synth.make_numpy(60, 24, n_classes=10, rows_per_class=6, noise=0.5, relu=True)
+    x = unit_rows(x)
+    x[7] = x[6]
+    x[31] = x[2]
+    for squared in (False, True):
+        for soft in (False, True):
+            l, g = O.batch_hard_grad(lab, x, 0.5, squared, soft)
+            la, ga = O.batch_hard_grad_analytic(lab, x, 0.5, squared, soft)
+            assert abs(l - la) <= 1e-6 * abs(l)
+            np.testing.assert_allclose(ga, g, rtol=1e-5, atol=1e-9)
+    x1, lab1 = synth.make_numpy(6, 5, n_classes=1, rows_per_class=6)
+    l, g = O.batch_hard_grad(lab1, x1, 0.5)
+    la, ga = O.batch_hard_grad_analytic(lab1, x1, 0.5)
+    assert abs(l - la) <= 1e-6 * abs(l)
+    np.testing.assert_allclose(ga, g, rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present (GPU box)")
 def test_oracle_matches_reference_live():
     import torch
