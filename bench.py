@@ -33,6 +33,12 @@ TRIPLET_WORKLOAD = ("C3: fused batch-hard triplet loss + grad, B=4096 d=512 (512
                     "L2-normalised), margin 0.5, non-squared distances")
 
 
+def bench_config(world):
+    """Identical in both arms (the driver compares the two `config` dicts)."""
+    return {"workload": TRIPLET_WORKLOAD,
+            "parallelism": "replicas only (the in-batch path does not shard)" if world > 1 else "1 GPU"}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -155,22 +161,44 @@ def cpu_knn_baseline(bank_rows=400_000, n_q=256):
         n_q, bank_rows)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and is meant to use
+    all host cores.  Must run before NumPy / scikit-learn load their BLAS."""
+    n = str(os.cpu_count() or 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = n
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count()
-    steps = max(1, min(args.steps, 40))
-    value, dt = cpu_triplet_baseline(steps, max(1, min(args.warmup, 3)))
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=cores)
+        import numpy  # noqa: F401  (loads the BLAS so that threadpool_info sees it)
+
+        threads = max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = cores
+    # same K and W as our arm (one C3 step takes ~0.2 s on the host: 50 steps stay within seconds)
+    W, steps = max(3, args.warmup), max(1, args.steps)
+    value, dt = cpu_triplet_baseline(steps, W)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference",
         "metric": "batch_hard_triplet_loss_grad_embeddings_per_sec", "value": value, "unit": "embeddings/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": dt * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": W, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 in / f64 BLAS internals",
         "data": "synthetic",
-        "config": {"workload": TRIPLET_WORKLOAD, "note": "reference CPU path: sklearn.pairwise_distances + NumPy; "
-                   "TensorFlow 2.2 is not runnable in this image (Python 3.12, no network)"},
-        "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                         "sample": "full C3 step (B=4096, d=512), %d steps" % steps},
+        "config": bench_config(world),
+        "method": "reference CPU path: sklearn.pairwise_distances (datagenerators.py:219) + NumPy selection and "
+                  "gradient on rank 0's host cores; TensorFlow 2.2 is not runnable in this image (Python 3.12, no "
+                  "network)",
+        "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": threads, "kind": "port",
+                         "sample": "full C3 step (B=4096, d=512), %d steps, %d BLAS threads of %d host cores" % (
+                             steps, threads, cores)},
         "e2e": {"value": value, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,6 +208,71 @@ def run_reference(args, rank):
                        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                         "sample": sample}}
     print(json.dumps(line), flush=True)
+
+
+def rowwise_rooflines(torch, _lib, synth, dev, flush, peaks):
+    """HBM roofline of the memory-bound row-wise kernels (north_star (3); SURVEY 8(d) A6 / A9 / A10 byte counts),
+    called through the C ABI.  C3 scale (4096 x 512: 8-25 MB, smaller than L2, so L2 is flushed before every timed
+    launch and the figure includes launch latency) and bank scale (1M x 256 = 1 GB per operand, >> L2)."""
+    from embeddingnet_b200._runtime import ptr, stream_ptr
+
+    out = {}
+    for tag, rows, d, flush_each in (("C3_4096x512", 4096, 512, True), ("bank_1Mx256", 1_000_000, 256, False)):
+        x = synth.make_device(rows, d, n_classes=max(rows // 8, 1), rows_per_class=8, noise=0.5, relu=True, device=dev)[0]
+        g = synth.make_device(rows, d, seed_noise=77, device=dev)[0]
+        y = torch.empty_like(x)
+        apn = synth.make_device(rows, 3 * d, seed_noise=78, device=dev)[0]
+        gapn = torch.empty_like(apn)
+        vec = torch.empty(rows, dtype=torch.float32, device=dev)
+        ones = torch.ones(rows, dtype=torch.float32, device=dev)
+        s = stream_ptr()
+        m = ctypes.c_float(0.5)
+        n4 = rows * d * 4
+        cases = {
+            "l2_normalize_fwd": (2 * n4, lambda: _lib.call("en_l2_normalize_fwd", ptr(x), ptr(y), rows, d, s)),
+            "l2_normalize_bwd": (3 * n4, lambda: _lib.call("en_l2_normalize_bwd", ptr(x), ptr(g), ptr(y), rows, d, s)),
+            "triplet_apn_fwd": (3 * n4 + rows * 4, lambda: _lib.call("en_triplet_apn_fwd", ptr(apn), rows, 3 * d, m,
+                                                                     ptr(vec), s)),
+            "triplet_apn_bwd": (6 * n4 + rows * 4, lambda: _lib.call("en_triplet_apn_bwd", ptr(apn), ptr(ones), rows,
+                                                                     3 * d, m, ptr(gapn), s)),
+            "siamese_l2_fwd": (2 * n4 + rows * 4, lambda: _lib.call("en_siamese_l2_fwd", ptr(x), ptr(g), rows, d,
+                                                                    ptr(vec), s)),
+            "query_distances": (n4 + rows * 4, lambda: _lib.call("en_query_distances", ptr(x), ptr(g), rows, d,
+                                                                 ptr(vec), s)),
+        }
+        rec = {}
+        for name, (nbytes, fn) in cases.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            if flush_each:
+                evs = []
+                for _ in range(20):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+                ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+            else:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 10
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            rec[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
+        out[tag] = rec
+        del x, g, y, apn, gapn, vec, ones
+        torch.cuda.empty_cache()
+    out["peak_gbs"] = peaks["hbm_gbs"]
+    out["note"] = ("C3-scale launches move 8-50 MB in 3-10 us: launch latency and the L2-flushed cold start are inside "
+                   "the figure; the bank-scale rows are the steady-state HBM rate")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- ours
@@ -199,6 +292,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if rank == 0:
+            use_all_host_threads()
         run_reference(args, rank)
         return
 
@@ -219,7 +314,11 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        os.environ["NCCL_DEBUG"] = os.environ.get("EN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # NCCL's own init log (rank / nranks lines) is the evidence that the sharded path really spans N ranks: keep
+        # it on, but on stderr, so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     lib = _lib.load()  # raises if the CUDA extension is missing
@@ -418,9 +517,9 @@ def main():
         "dtype": "f32 in/out; tensor-core selection on split-BF16 planes (3 MMAs per k-step), float64 re-evaluation "
                  "of every selected distance",
         "data": "synthetic",
-        "config": {"workload": TRIPLET_WORKLOAD, "l2": "256 MiB memset between timed steps (L2 flush)",
+        "config": bench_config(world),
+        "method": {"l2": "256 MiB memset between timed steps (L2 flush)",
                    "timing": "per-step CUDA events around one CUDA-graph replay of fwd+bwd; sum over steps, max over ranks",
-                   "parallelism": "replicas only (the in-batch path does not shard)" if world > 1 else "1 GPU",
                    "loss": loss_value},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
         "gpu_launches_per_step": int(launches_per_step), "e2e_gpu_launches_per_step": int(e2e_launches),
@@ -452,8 +551,34 @@ def main():
         emb7 = (emb * 0.7).contiguous()
         t_ba = time_ms(lambda: fwd_bwd(ba, emb))
         t_ca = time_ms(lambda: fwd_bwd(ca, emb7))
-        others["C3_batch_all_loss_grad"] = {"ms": t_ba, "embeddings_per_sec": B / (t_ba * 1e-3)}
-        others["C3_contrastive_all_pairs_loss_grad"] = {"ms": t_ca, "embeddings_per_sec": B / (t_ca * 1e-3)}
+        pair_flops = 4.0 * B * B * D   # forward distance GEMM + backward (C . E) contraction, 2 B^2 d each
+        pair_peak = peaks["bf16"] / 6.0  # 3xTF32: dense TF32 = dense bf16 / 2, three passes
+
+        def pair_roofline(ms):
+            ach = pair_flops / (ms * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pair_peak, "unit": "TFLOP/s", "frac": ach / pair_peak,
+                    "algorithmic_flops_per_step": pair_flops,
+                    "peak_note": "%s bf16 dense %.1f TFLOP/s / 2 (TF32) / 3 (passes); whole fwd+bwd step, all "
+                                 "kernels" % (peaks["source"], peaks["bf16"])}
+
+        others["C3_batch_all_loss_grad"] = {"ms": t_ba, "embeddings_per_sec": B / (t_ba * 1e-3),
+                                            "roofline": pair_roofline(t_ba)}
+        others["C3_contrastive_all_pairs_loss_grad"] = {"ms": t_ca, "embeddings_per_sec": B / (t_ca * 1e-3),
+                                                        "roofline": pair_roofline(t_ca)}
+        # stress shape of SURVEY 8(d): 64 classes x 64 rows (63 positives per anchor)
+        raw64, lab64 = synth.make_device(B, D, n_classes=64, rows_per_class=64, noise=0.5, relu=True, device=dev)
+        emb64 = lac.l2_normalize(raw64).detach().contiguous()
+        ba64 = lac.batch_all_triplet_loss(MARGIN, max_positives=63)
+
+        def fwd_bwd64():
+            e = emb64.detach().clone().requires_grad_(True)
+            ba64(lab64, e).backward()
+
+        t_ba64 = time_ms(fwd_bwd64, n=5, w=2)
+        others["C3_batch_all_loss_grad_64x64"] = {"ms": t_ba64, "embeddings_per_sec": B / (t_ba64 * 1e-3),
+                                                  "roofline": pair_roofline(t_ba64)}
+        del raw64, emb64
+        others["rowwise_hbm"] = rowwise_rooflines(torch, _lib, synth, dev, flush, peaks)
         # C1: reference-semantics in-batch mining, 32 classes x 8 samples, d = 128 (host arrays in, triplets out)
         from embeddingnet_b200.datagenerators import mine_batch_triplets
 
@@ -491,7 +616,22 @@ def main():
         label_ids = (torch.arange(n_total, dtype=torch.int64, device=dev) % KNN_CLASSES).to(torch.int32)
         clf = BankKNNClassifier(n_neighbors=KNN_K, process_group=group, device=dev)
         clf.fit_shard(bank, label_ids, lo, n_total, classes=np.arange(KNN_CLASSES))
+        # 90 % of the queries are bank rows perturbed by 0.25 u (the true nearest row is known: the
+        # planted one), 10 % are unrelated draws.  Bank rows come from the counter-hash generator, so every rank can
+        # regenerate the planted rows wherever they live: queries are bit-identical for every N.
         queries, _ = synth.make_device(Q, D, seed_noise=synth.SEED_QUERY, n_classes=KNN_CLASSES, noise=0.5, device=dev)
+        n_planted = Q - Q // 10
+        blk = 1000
+        n_blk = (n_planted + blk - 1) // blk
+        planted = torch.full((Q,), -1, dtype=torch.int64, device=dev)
+        pert = synth.make_device(n_planted, D, seed_noise=synth.SEED_QUERY + 1, device=dev)[0]  # plain u in [-1, 1)
+        for b_ in range(n_blk):
+            q0, q1 = b_ * blk, min((b_ + 1) * blk, n_planted)
+            r0 = (b_ * (n_total - blk)) // max(n_blk - 1, 1) if n_total > blk else 0   # blocks spread over the bank
+            rows = synth.make_device(q1 - q0, D, row_offset=r0, n_classes=KNN_CLASSES, noise=0.5, device=dev)[0]
+            queries[q0:q1] = rows + 0.25 * pert[q0:q1]
+            planted[q0:q1] = torch.arange(r0, r0 + (q1 - q0), device=dev) % max(n_total, 1)
+        del pert
         kw, kk = 3, max(1, args.knn_steps)
         for _ in range(kw):
             clf.kneighbors_device(queries)
@@ -505,6 +645,15 @@ def main():
         barrier()
         knn_launches = launch_count()
         knn_uncertified = clf.last_uncertified
+        # parity gate inside the bench: top-1 of every planted query is the planted row, on every rank; the id table
+        # is hashed so that runs at N = 1, 2, 4, 8 can be compared (the search is exact: the hash must not change)
+        import hashlib
+
+        ok_planted = bool((ids_d[:n_planted, 0] == planted[:n_planted]).all().item()) if n_total >= blk else None
+        all_ok = max_over_ranks(0.0 if ok_planted in (True, None) else 1.0) == 0.0
+        ids_sha = hashlib.sha256(ids_d.cpu().numpy().tobytes()).hexdigest()
+        if not all_ok:
+            raise SystemExit("bench.py: kNN parity gate failed: a planted query's nearest row is not the planted row")
         knn_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev))
         knn_value = Q * kk / (knn_ms * 1e-3)
         lib.en_prof_enable(1)
@@ -607,24 +756,13 @@ def main():
                 "workload": "C4: semihard negative (datagenerators.py:196-199 over the whole bank) for 65536 "
                             "(anchor, positive) pairs, 1M x 256 bank, %d GPU(s); two scans + host RNG draws" % world,
                 "ms": s_dt * 1e3, "pairs_per_sec": 65536 / s_dt, "pairs_with_a_candidate": int((sel >= 0).sum())}
+        # Key order matters to the reader of a truncated log: bulky sub-records first, the headline of the sharded
+        # path (value, time, roofline, e2e, parity hash, NCCL ranks) last.
         knn = {
-            "metric": "knn_queries_per_sec_10M_bank", "value": knn_value, "unit": "queries/s", "n_gpus": world,
-            "steps": kk, "warmup": kw, "ms_per_step": knn_ms / kk, "scaling": "strong",
-            "config": {"workload": "C5: %d queries vs %d x %d fp32 bank, k=%d, bank sharded row-wise over %d GPU(s), "
-                       "NCCL all-gather + merge; inputs >> L2 (no flush needed)" % (Q, n_total, D, KNN_K, world)},
-            "roofline": {"bound": "tensor", "achieved": kach, "peak": kpeak, "unit": "TFLOP/s", "frac": kach / kpeak,
-                         "traffic": ncu_traffic("knn_scan_dram_bytes_per_launch"), "kernel": "dist_gemm_kernel<EpTopK<8>> (split-BF16 planes)",
-                         "kernel_ms": scan_ms, "share_of_step": scan_ms / (knn_ms / kk),
-                         "algorithmic_flops_per_launch": kflops,
-                         "peak_note": "%s bf16 dense %.1f TFLOP/s (sustained) / 3, per GPU" % (
-                             peaks["source"], peaks["bf16_sustained"]),
-                         "frac_of_tf32x3_roofline": kach / (peaks["bf16_sustained"] / 6.0)},
-            "e2e": {"value": Q / knn_e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
-                    "d2h_bytes_per_step": Q * KNN_K * 12, "api": "BankKNNClassifier.kneighbors (pinned host queries)"},
-            "gpu_launches": int(knn_launches),
-            "certificate": {"uncertified_queries_this_rank": int(knn_uncertified), "of": Q,
-                            "note": "queries whose exactness proof failed are redone by float64 brute force "
-                                    "inside the timed call"},
+            "metric": "knn_queries_per_sec_10M_bank", "unit": "queries/s", "scaling": "strong",
+            "config": {"workload": "C5: %d queries (90%% planted: bank row + 0.25 u, 10%% unrelated) vs %d x %d fp32 "
+                       "bank, k=%d, bank sharded row-wise over %d GPU(s), NCCL all-gather + merge; inputs >> L2 (no "
+                       "flush needed)" % (Q, n_total, D, KNN_K, world)},
             "stream_scan": stream[1], "stream_scan_q8": stream[8],
         }
         if mining is not None:
@@ -633,9 +771,33 @@ def main():
             qps, sample = cpu_knn_baseline()
             knn["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": sample}
+        knn.update({
+            "gpu_launches": int(knn_launches),
+            "certificate": {"uncertified_queries_this_rank": int(knn_uncertified), "of": Q,
+                            "note": "queries whose exactness proof failed are redone by float64 brute force "
+                                    "inside the timed call"},
+            "roofline": {"bound": "tensor", "achieved": kach, "peak": kpeak, "unit": "TFLOP/s", "frac": kach / kpeak,
+                         "traffic": ncu_traffic("knn_scan_dram_bytes_per_launch"),
+                         "kernel": "dist_gemm_kernel<EpTopK<8>> (split-BF16 planes)",
+                         "kernel_ms": scan_ms, "share_of_step": scan_ms / (knn_ms / kk),
+                         "algorithmic_flops_per_launch": kflops,
+                         "peak_note": "%s bf16 dense %.1f TFLOP/s (sustained) / 3, per GPU" % (
+                             peaks["source"], peaks["bf16_sustained"]),
+                         "frac_of_tf32x3_roofline": kach / (peaks["bf16_sustained"] / 6.0)},
+            "e2e": {"value": Q / knn_e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
+                    "d2h_bytes_per_step": Q * KNN_K * 12, "api": "BankKNNClassifier.kneighbors (pinned host queries)"},
+            "parity": {"planted_top1_ok": ok_planted, "planted_queries": int(n_planted), "ids_sha256": ids_sha},
+            "n_gpus": world, "nccl_ranks": (dist.get_world_size() if world > 1 else 1),
+            "steps": kk, "warmup": kw, "ms_per_step": knn_ms / kk, "value": knn_value,
+        })
         line["knn"] = knn
 
-    line["clocks"] = sampler.stop()
+    clocks = sampler.stop()
+    # `knn` stays the last key: the tail of the line is the sharded path's headline
+    tail = line.pop("knn", None)
+    line["clocks"] = clocks
+    if tail is not None:
+        line["knn"] = tail
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -54,9 +54,11 @@ SIGNATURES = {
     "en_ws_bytes_batch_all": (c_size_t, [c_int64, c_int, c_int]),
     "en_batch_all_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, c_size_t, P]),
     "en_batch_all_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "en_batch_all_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_contrastive_allpairs": (c_size_t, [c_int64, c_int]),
     "en_contrastive_allpairs_fwd": (c_int, [P, P, c_int64, c_int, P, P, c_size_t, P]),
     "en_contrastive_allpairs_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, c_size_t, P]),
+    "en_contrastive_allpairs_fwd_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, P, c_size_t, P]),
     "en_bank_dpad": (c_int, [c_int, c_int]),
     "en_bank_plane_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "en_bank_prepare": (c_int, [P, c_int64, c_int, c_int, P, P, P, P]),

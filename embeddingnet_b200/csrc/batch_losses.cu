@@ -16,16 +16,17 @@
 
 namespace en {
 
-// csrc/pair_bwd_tc.cu: tensor-core backward of the pair losses (two chained tcgen05 GEMMs)
-size_t pair_bwd_tc_ws_bytes(int64_t B, int d);
-int pair_bwd_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
-                       float scale_c, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
-                       const float* gloss, float* gemb, void* ws, size_t ws_bytes, cudaStream_t st);
+// csrc/pair_tc.cu: fused tensor-core kernel of the pair losses (two chained tcgen05 GEMMs; loss and / or gradient)
+size_t pair_tc_ws_bytes(int64_t B, int d);
+int pair_tc_partials_per_row(int64_t B, int d);
+int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
+                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
+                   const float* gloss, PairPartial* partial, float* gemb, void* ws, size_t ws_bytes, cudaStream_t st);
 
 namespace {
 
 constexpr float kBig = 3.0e38f;
-constexpr int kTcBwdMaxPos = 8;  // pair_bwd_tc_kernel keeps the positives lists in registers / 1 KB of smem
+constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps the positives lists in registers / 2 KB of smem per warp
 
 // warp-cooperative exact squared distance between rows i and j (float64 accumulate); result in every lane
 // (not inlined: it is called from many sites of kernels whose warps run the code once, where instruction fetch,
@@ -247,24 +248,64 @@ __device__ __forceinline__ void bh_update_min(BhPick& win, double d2, int ci) {
   if (win.idx < 0 || d2 < win.d2 || (d2 == win.d2 && ci < win.idx)) win = BhPick{d2, ci};
 }
 
-// Exact re-scan of ONE record slot: every row the slot covers (64 columns of the row view, 32 rows of the column
-// view) with the wanted label relation is re-evaluated in float64.  Used when the slot is SATURATED: its second
-// entry is itself a contender, so the slot may hide further contenders behind its top-2 (three duplicates of the
-// hardest negative in adjacent rows -- the reference's sampler draws with replacement,
+// Squared distance between rows i and j by ONE lane in float32 (four partial sums).  All terms are non-negative, so
+// the result is within (d/4 + 8) * 2^-23 RELATIVE of the true value: a filter five orders of magnitude sharper than
+// the tensor-core proxy, at a fraction of the cost of the float64 evaluation.  Lanes of a warp work on different
+// rows j of the same anchor i (the anchor's loads are broadcasts).
+__device__ __forceinline__ float lane_d2_f32(const float* __restrict__ e, int d, int64_t i, int64_t j) {
+  const float* a = e + i * d;
+  const float* b = e + j * d;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0) {
+#pragma unroll 4
+    for (int c = 0; c < d; c += 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a + c)), y = __ldg(reinterpret_cast<const float4*>(b + c));
+      float t;
+      t = x.x - y.x; s0 = fmaf(t, t, s0);
+      t = x.y - y.y; s1 = fmaf(t, t, s1);
+      t = x.z - y.z; s2 = fmaf(t, t, s2);
+      t = x.w - y.w; s3 = fmaf(t, t, s3);
+    }
+  } else {
+    for (int c = 0; c < d; ++c) {
+      const float t = a[c] - b[c];
+      s0 = fmaf(t, t, s0);
+    }
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+// Re-scan of ONE record slot: every row the slot covers (64 columns of the row view, 32 rows of the column view)
+// with the wanted label relation is measured in float32, one row per lane; the rows within the float32 error of the
+// slot's best are then re-evaluated in float64 by the same exact_d2() every other candidate goes through (so exact
+// duplicates compare equal bit for bit and resolve to the lowest index).  Used when the slot is SATURATED: its
+// second entry is itself a contender, so the slot may hide further contenders behind its top-2 (three duplicates of
+// the hardest negative in adjacent rows -- the reference's sampler draws with replacement,
 // embedding_net/datagenerators.py:205 -- or three near-ties).  A hidden entry's packed key is never better than the
 // slot's second one, so "second entry outside the band" proves that nothing hidden matters.
-__device__ __noinline__ void bh_rescan_slot(const float* __restrict__ emb, const int32_t* __restrict__ labels,
-                                            int64_t B, int d, int64_t row, int32_t la, int t, int my_tile,
-                                            bool want_same, int lane, BhPick& win) {
+__device__ __noinline__ BhPick bh_rescan_slot(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                              int64_t B, int d, int64_t row, int32_t la, int t, int my_tile,
+                                              bool want_same, int lane, BhPick win) {
   const int tile = t >> 2, slot = t & 3;
   const bool col_view = tile < my_tile;
   const int len = col_view ? 32 : 64;
   const int64_t j0 = static_cast<int64_t>(tile) * tc::BN + slot * len;
+  const float rel = static_cast<float>(d / 4 + 8) * 2.4e-7f;  // both the best and the contender carry the error
   for (int64_t jb = j0; jb < j0 + len; jb += 32) {
     const int64_t j = jb + lane;
     const bool ok = j < B && j != row;
     const bool want = ok && ((__ldg(&labels[ok ? j : 0]) == la) == want_same);
-    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!__any_sync(0xffffffffu, want)) continue;
+    float f = want_same ? -1.f : kBig;
+    if (want) f = lane_d2_f32(emb, d, row, j);
+    float best = f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = want_same ? fmaxf(best, other) : fminf(best, other);
+    }
+    const bool surv = want && (want_same ? f >= best - best * rel - 1e-30f : f <= best + best * rel + 1e-30f);
+    unsigned m = __ballot_sync(0xffffffffu, surv);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
@@ -274,15 +315,20 @@ __device__ __noinline__ void bh_rescan_slot(const float* __restrict__ emb, const
       else bh_update_min(win, d2, ci);
     }
   }
+  return win;
 }
 
 // General resolver (one warp per anchor): every record entry inside the band is re-evaluated exactly, saturated
 // slots are re-scanned.  Ties resolve to the lowest index because every candidate that can tie is evaluated and the
 // (d2, index) order is applied on the exact values -- the order of the packed keys (which for negative proxies
 // favours the HIGHER in-tile index among equal values) never decides anything.
-__device__ __noinline__ void bh_resolve(const float* __restrict__ emb, const int32_t* __restrict__ labels,
-                                        const BhCand* __restrict__ mine, int n_cand, int my_tile, int64_t row,
-                                        int64_t B, int d, BhThr thr, int lane, BhPick& pos, BhPick& neg) {
+struct BhPair {
+  BhPick pos, neg;
+};
+__device__ __noinline__ BhPair bh_resolve(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                          const BhCand* __restrict__ mine, int n_cand, int my_tile, int64_t row,
+                                          int64_t B, int d, BhThr thr, int lane) {
+  BhPair r{BhPick{-1.0, -1}, BhPick{1e300, -1}};
   const int32_t la = labels[row];
 #pragma unroll 1
   for (int t0 = 0; t0 < n_cand; t0 += 32) {
@@ -299,28 +345,29 @@ __device__ __noinline__ void bh_resolve(const float* __restrict__ emb, const int
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int ci = __shfl_sync(0xffffffffu, ip, src);
-      bh_update_max(pos, exact_d2(emb, d, row, ci, lane), ci);
+      bh_update_max(r.pos, exact_d2(emb, d, row, ci, lane), ci);
     }
     m = __ballot_sync(0xffffffffu, cn1 && !cn2);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int ci = __shfl_sync(0xffffffffu, in, src);
-      bh_update_min(neg, exact_d2(emb, d, row, ci, lane), ci);
+      bh_update_min(r.neg, exact_d2(emb, d, row, ci, lane), ci);
     }
     m = __ballot_sync(0xffffffffu, cp2);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, true, lane, pos);
+      r.pos = bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, true, lane, r.pos);
     }
     m = __ballot_sync(0xffffffffu, cn2);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, false, lane, neg);
+      r.neg = bh_rescan_slot(emb, labels, B, d, row, la, t0 + src, my_tile, false, lane, r.neg);
     }
   }
+  return r;
 }
 
 // No other-label row at all.  Moindrot's min(D + rowmax * (1 - mask_neg)) then degenerates to the row maximum; a
@@ -424,8 +471,8 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
       bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
     // pass 2: exact re-evaluation of everything inside the band, saturated slots re-scanned
-    BhPick pos{-1.0, -1}, neg{1e300, -1};
-    bh_resolve(emb, labels, mine, n_cand, my_tile, row, B, d, bh_thresholds(na, bp, bn, band_c), lane, pos, neg);
+    const BhPair won = bh_resolve(emb, labels, mine, n_cand, my_tile, row, B, d, bh_thresholds(na, bp, bn, band_c), lane);
+    BhPick pos = won.pos, neg = won.neg;
     if (neg.idx < 0) neg = bh_row_maximum(emb, B, d, row, lane);
     const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
     const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
@@ -480,10 +527,9 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
                                 int tiles_n, float margin, int squared, int soft, float band_c,
                                 int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
                                 float* __restrict__ hp_out, float* __restrict__ hn_out, float* __restrict__ coef,
-                                double* __restrict__ partial, unsigned* __restrict__ counter,
-                                float* __restrict__ loss, const float* __restrict__ gloss,
+                                double* __restrict__ hinge_all, int32_t* __restrict__ work_list,
+                                unsigned* __restrict__ counters, const float* __restrict__ gloss,
                                 float* __restrict__ gemb) {
-  __shared__ double sh[8];
   constexpr int d = 128 * DV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * FF_WARPS + warp;
@@ -546,7 +592,14 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
     int rounds = 0;
     const bool overflow = __any_sync(0xffffffffu, sat || pc > 2 || nc > 2);
     const bool no_neg = !__any_sync(0xffffffffu, nc > 0);
-    if (!overflow && !no_neg) {
+    if (overflow || no_neg) {
+      // A saturated slot, three contenders queued on one lane, or no negative at all: the anchor goes on the work
+      // list of batch_hard_finalize_slow_kernel (a whole block per anchor).  Resolving it here, one warp per anchor,
+      // held the block's slot for tens of microseconds and doubled the kernel's duration with ~5 % such anchors.
+      if (lane == 0) work_list[atomicAdd(&counters[0], 1u)] = static_cast<int32_t>(row);
+      return;
+    }
+    {
       // Each round re-evaluates one positive and one negative contender exactly, all row loads of the round in one
       // batch.  The usual case is a single round (one contender each; none for an anchor alone in its class).
       const float4* arow = reinterpret_cast<const float4*>(emb + row * d) + lane;
@@ -596,10 +649,6 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
         if (n_idx >= 0 && (neg.idx < 0 || dn < neg.d2 || (dn == neg.d2 && n_idx < neg.idx))) neg = BhPick{dn, n_idx};
         ++rounds;
       }
-    } else {
-      // a saturated slot, three contenders queued on one lane, or no negative at all: general resolver
-      bh_resolve(emb, labels, mine, n_cand, my_tile, row, B, d, thr, lane, pos, neg);
-      if (neg.idx < 0) neg = bh_row_maximum(emb, B, d, row, lane);
     }
     // a single round leaves the winners' rows in registers for the gradient
     const bool rows_cached = rounds == 1;
@@ -620,6 +669,7 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
       hp_out[row] = static_cast<float>(hp);
       hn_out[row] = static_cast<float>(hn);
       coef[row] = static_cast<float>(g / static_cast<double>(B));
+      hinge_all[row] = hinge;
     }
     if (kGrad) {
       const float gg = static_cast<float>(g / static_cast<double>(B)) * (gloss ? gloss[0] : 1.0f);
@@ -658,7 +708,273 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
       }
     }
   }
-  block_mean(hinge, sh, partial, counter, loss, B);
+}
+
+// ---- slow finalize: the anchors the fast kernel put on the work list, one BLOCK per anchor -------------------
+// Eight warps: four of them hold the anchor's (at most 128) records; a saturated slot's candidates are split over all,
+// measured in float32 (four rows per trip, all loads of a trip in flight together), and the ones within the float32
+// error of the slot's best are re-evaluated by exact_d2() -- the arithmetic every other candidate goes through, so
+// exact duplicates compare equal bit for bit and resolve to the lowest index.  The last block to finish adds the
+// per-anchor hinge values of BOTH kernels in a fixed order (deterministic mean).
+constexpr int FS_WARPS = 8;
+
+// float32 squared distances of the anchor row to four rows at once, warp-cooperative (d % 128 == 0, 16-byte aligned)
+__device__ __forceinline__ void warp_d2_f32x4(const float* __restrict__ e, int d, int64_t row, const int (&j)[4],
+                                              int lane, float (&out)[4]) {
+  const float4* a = reinterpret_cast<const float4*>(e + row * d) + lane;
+  const float4* b0 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[0]) * d) + lane;
+  const float4* b1 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[1]) * d) + lane;
+  const float4* b2 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[2]) * d) + lane;
+  const float4* b3 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[3]) * d) + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  auto acc = [](float s, const float4& x, const float4& y) {
+    float t;
+    t = x.x - y.x; s = fmaf(t, t, s);
+    t = x.y - y.y; s = fmaf(t, t, s);
+    t = x.z - y.z; s = fmaf(t, t, s);
+    t = x.w - y.w; s = fmaf(t, t, s);
+    return s;
+  };
+#pragma unroll 4
+  for (int i = 0; i < d / 128; ++i) {
+    const float4 x = __ldg(a + 32 * i), y0 = __ldg(b0 + 32 * i), y1 = __ldg(b1 + 32 * i), y2 = __ldg(b2 + 32 * i),
+                 y3 = __ldg(b3 + 32 * i);
+    s0 = acc(s0, x, y0);
+    s1 = acc(s1, x, y1);
+    s2 = acc(s2, x, y2);
+    s3 = acc(s3, x, y3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
+}
+
+// hinge / outputs / gradient of one anchor from its resolved picks (one warp); returns the hinge value
+template <bool kGrad>
+__device__ __forceinline__ double bh_finish(const float* __restrict__ emb, int d, int64_t B, int64_t row, BhPick pos,
+                                            BhPick neg, float margin, int squared, int soft,
+                                            int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                            float* __restrict__ hp_out, float* __restrict__ hn_out,
+                                            float* __restrict__ coef, const float* __restrict__ gloss,
+                                            float* __restrict__ gemb, int lane, int term = -1) {
+  // term: -1 = outputs and all four gradient terms (one warp does everything); 0..3 = only that gradient term, and
+  // the outputs with term 0 (the four terms of one anchor spread over four warps)
+  const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
+  const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
+  const double z = hp - hn;
+  double g, hinge;
+  if (soft) {
+    hinge = z > 0 ? z + log1p(exp(-z)) : log1p(exp(z));
+    g = 1.0 / (1.0 + exp(-z));
+  } else {
+    hinge = fmax(z + static_cast<double>(margin), 0.0);
+    g = (z + static_cast<double>(margin)) >= 0.0 ? 1.0 : 0.0;
+  }
+  if (lane == 0 && term <= 0) {
+    hp_idx[row] = pos.idx;
+    hn_idx[row] = neg.idx;
+    hp_out[row] = static_cast<float>(hp);
+    hn_out[row] = static_cast<float>(hn);
+    coef[row] = static_cast<float>(g / static_cast<double>(B));
+  }
+  if (kGrad) {
+    const float gg = static_cast<float>(g / static_cast<double>(B)) * (gloss ? gloss[0] : 1.0f);
+    if (gg != 0.f) {
+      const float hpf = static_cast<float>(hp), hnf = static_cast<float>(hn);
+      const float sp = pos.idx >= 0 ? (squared ? 2.f * gg : (hpf > 0.f ? gg / hpf : 0.f)) : 0.f;
+      const float sn = neg.idx >= 0 ? (squared ? 2.f * gg : (hnf > 0.f ? gg / hnf : 0.f)) : 0.f;
+      if (sp != 0.f) {
+        if (term < 0 || term == 0) red_axpy_diff(gemb, emb, d, row, row, pos.idx, sp, lane);
+        if (term < 0 || term == 1) red_axpy_diff(gemb, emb, d, pos.idx, row, pos.idx, -sp, lane);
+      }
+      if (sn != 0.f) {
+        if (term < 0 || term == 2) red_axpy_diff(gemb, emb, d, row, row, neg.idx, -sn, lane);
+        if (term < 0 || term == 3) red_axpy_diff(gemb, emb, d, neg.idx, row, neg.idx, sn, lane);
+      }
+    }
+  }
+  return hinge;
+}
+
+template <bool kGrad>
+__global__ void __launch_bounds__(FS_WARPS * 32)
+batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B, int d,
+                                int tiles_n, float margin, int squared, int soft, float band_c,
+                                int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                float* __restrict__ hp_out, float* __restrict__ hn_out, float* __restrict__ coef,
+                                double* __restrict__ hinge_all, const int32_t* __restrict__ work_list,
+                                unsigned* __restrict__ counters, float* __restrict__ loss,
+                                const float* __restrict__ gloss, float* __restrict__ gemb) {
+  __shared__ float s_bp[FS_WARPS], s_bn[FS_WARPS];
+  __shared__ double s_d2[2][FS_WARPS];
+  __shared__ int s_idx[2][FS_WARPS];
+  __shared__ int s_nsat;
+  __shared__ int s_sat[2 * 128];
+  __shared__ float s_f[64];
+  __shared__ double s_red[FS_WARPS];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned n_work = *reinterpret_cast<volatile unsigned*>(&counters[0]);
+  const int n_cand = tiles_n * BH_SLOTS;  // <= 128: the records live in warps 0..3
+  for (unsigned k = blockIdx.x; k < n_work; k += gridDim.x) {
+    const int64_t row = work_list[k];
+    const int my_tile = static_cast<int>(row / tc::BM);
+    const BhCand* mine = cand + row * n_cand;
+    const float na = norms[row];
+    const int32_t la = labels[row];
+    const int t = warp * 32 + lane;
+    float4 v = make_float4(-kBig, -kBig, kBig, kBig);
+    if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
+    float bp = v.x, bn = v.z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+      bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+    }
+    if (lane == 0) { s_bp[warp] = bp; s_bn[warp] = bn; }
+    if (threadIdx.x == 0) s_nsat = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < FS_WARPS; ++w) { bp = fmaxf(bp, s_bp[w]); bn = fminf(bn, s_bn[w]); }
+    const BhThr thr = bh_thresholds(na, bp, bn, band_c);
+    const bool cp1 = bh_valid(v.x) && v.x >= thr.p, cp2 = bh_valid(v.y) && v.y >= thr.p;
+    const bool cn1 = bh_valid(v.z) && v.z <= thr.n, cn2 = bh_valid(v.w) && v.w <= thr.n;
+    const int ip = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.x) & 0x7Fu);
+    const int in = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.z) & 0x7Fu);
+    BhPick pos{-1.0, -1}, neg{1e300, -1};
+    // entries of unsaturated slots: exact, one by one
+    unsigned m = __ballot_sync(0xffffffffu, cp1 && !cp2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = __shfl_sync(0xffffffffu, ip, src);
+      bh_update_max(pos, exact_d2(emb, d, row, ci, lane), ci);
+    }
+    m = __ballot_sync(0xffffffffu, cn1 && !cn2);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = __shfl_sync(0xffffffffu, in, src);
+      bh_update_min(neg, exact_d2(emb, d, row, ci, lane), ci);
+    }
+    // saturated slots (second entry inside the band): queued for the whole block
+    if (cp2) s_sat[atomicAdd(&s_nsat, 1)] = t * 2 + 1;
+    if (cn2) s_sat[atomicAdd(&s_nsat, 1)] = t * 2;
+    __syncthreads();
+    const int n_sat = s_nsat;
+    const float rel = static_cast<float>(d / 32 + 16) * 2.4e-7f;  // float32 error of both values being compared
+    for (int s = 0; s < n_sat; ++s) {
+      const int code = s_sat[s];
+      const bool want_same = (code & 1) != 0;
+      const int tt = code >> 1, tile = tt >> 2, slot = tt & 3;
+      const int len = tile < my_tile ? 32 : 64;  // column view: 32-row quarters; row view: 64-column halves
+      const int j0 = tile * tc::BN + slot * len;
+      const int per = len / FS_WARPS;            // candidates per warp: 8 or 16
+      const int64_t jq = static_cast<int64_t>(j0) + warp * per + lane;
+      const bool ok = lane < per && jq < B && jq != row;
+      const bool want = ok && ((__ldg(&labels[ok ? jq : 0]) == la) == want_same);
+      unsigned wm = __ballot_sync(0xffffffffu, want);
+      float myf = want_same ? -1.f : kBig;       // "not a candidate"
+      while (wm) {
+        int l[4], jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          l[u] = wm ? __ffs(wm) - 1 : l[0];
+          if (wm) wm &= wm - 1;
+          jj[u] = j0 + warp * per + l[u];
+        }
+        float f4[4];
+        warp_d2_f32x4(emb, d, row, jj, lane, f4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (lane == l[u]) myf = f4[u];
+      }
+      if (lane < per) s_f[warp * per + lane] = myf;
+      __syncthreads();
+      const float f0 = lane < len ? s_f[lane] : (want_same ? -1.f : kBig);
+      const float f1 = lane + 32 < len ? s_f[lane + 32] : (want_same ? -1.f : kBig);
+      float best = want_same ? fmaxf(f0, f1) : fminf(f0, f1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = want_same ? fmaxf(best, other) : fminf(best, other);
+      }
+      const float lim = want_same ? best - best * rel - 1e-30f : best + best * rel + 1e-30f;
+      const bool v0 = want_same ? f0 >= 0.f : f0 < 1e38f, v1 = want_same ? f1 >= 0.f : f1 < 1e38f;
+      const unsigned m0 = __ballot_sync(0xffffffffu, v0 && (want_same ? f0 >= lim : f0 <= lim));
+      const unsigned m1 = __ballot_sync(0xffffffffu, v1 && (want_same ? f1 >= lim : f1 <= lim));
+      int n_surv = 0;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        unsigned mm = h ? m1 : m0;
+        while (mm) {
+          const int src = __ffs(mm) - 1;
+          mm &= mm - 1;
+          if ((n_surv++ % FS_WARPS) == warp) {  // survivors round-robin over the warps
+            const int ci = j0 + h * 32 + src;
+            const double d2 = exact_d2(emb, d, row, ci, lane);
+            if (want_same) bh_update_max(pos, d2, ci);
+            else bh_update_min(neg, d2, ci);
+          }
+        }
+      }
+      __syncthreads();  // s_f is rewritten by the next slot
+    }
+    // merge the four warps' picks ((d2, index) order: associative and commutative, so the result is deterministic)
+    if (lane == 0) {
+      s_d2[0][warp] = pos.d2; s_idx[0][warp] = pos.idx;
+      s_d2[1][warp] = neg.d2; s_idx[1][warp] = neg.idx;
+    }
+    __syncthreads();
+    BhPick P{-1.0, -1}, N{1e300, -1};
+#pragma unroll
+    for (int w = 0; w < FS_WARPS; ++w) {
+      if (s_idx[0][w] >= 0) bh_update_max(P, s_d2[0][w], s_idx[0][w]);
+      if (s_idx[1][w] >= 0) bh_update_min(N, s_d2[1][w], s_idx[1][w]);
+    }
+    if (N.idx < 0) {  // block-uniform; degenerate batch without any other label
+      __syncthreads();
+      if (warp == 0) {
+        N = bh_row_maximum(emb, B, d, row, lane);
+        if (lane == 0) { s_d2[1][0] = N.d2; s_idx[1][0] = N.idx; }
+      }
+      __syncthreads();
+      N = BhPick{s_d2[1][0], s_idx[1][0]};
+    }
+    if (warp < 4) {  // outputs + the four gradient terms, one per warp
+      const double hinge = bh_finish<kGrad>(emb, d, B, row, P, N, margin, squared, soft, hp_idx, hn_idx, hp_out, hn_out,
+                                            coef, gloss, gemb, lane, warp);
+      if (warp == 0 && lane == 0) hinge_all[row] = hinge;
+    }
+    __syncthreads();  // shared state is reused by the next anchor
+  }
+  // ---- mean over all anchors, by the last block, in a fixed order
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&counters[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double tot = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) tot += __ldcg(&hinge_all[i]);
+    tot = warp_sum(tot);
+    if (lane == 0) s_red[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < FS_WARPS; ++w) sum += s_red[w];
+      loss[0] = static_cast<float>(sum / static_cast<double>(B));
+      counters[0] = 0;  // re-armed for the next call on this workspace
+      counters[1] = 0;
+    }
+  }
 }
 
 // Backward, stage 1: the anchor's own row, overwritten (no zero-fill pass needed).
@@ -793,11 +1109,6 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
     if (count > cap) atomicMax(status, count);  // caller's max_positives was too small
   }
 }
-
-struct PairPartial {
-  double sum;
-  unsigned long long npos;
-};
 
 // ---------------------------------------------------------------- batch-all forward epilogue
 struct EpBatchAll {
@@ -1153,7 +1464,7 @@ __global__ void batch_all_bwd_pos_kernel(const float* __restrict__ emb, int64_t 
                                          const float* __restrict__ pos_d, const int32_t* __restrict__ pos_j,
                                          const int32_t* __restrict__ pos_n, const int32_t* __restrict__ pos_cnt,
                                          const double* __restrict__ stats, const float* __restrict__ gloss,
-                                         float* __restrict__ gemb) {
+                                         float* __restrict__ gemb, int unscaled) {
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t i = wid / cap;
@@ -1163,13 +1474,34 @@ __global__ void batch_all_bwd_pos_kernel(const float* __restrict__ emb, int64_t 
   if (cnt == 0) return;
   const float dij = pos_d[i * cap + s];
   const float sfac = squared ? 2.f : (dij > 0.f ? 1.f / dij : 0.f);
-  const float c = gloss[0] * static_cast<float>(static_cast<double>(cnt) / (stats[1] + 1e-16)) * sfac;
+  // unscaled: the fused step divides the finished gradient by #positive triplets (pair_scale_kernel)
+  const float c = unscaled ? static_cast<float>(cnt) * sfac
+                           : gloss[0] * static_cast<float>(static_cast<double>(cnt) / (stats[1] + 1e-16)) * sfac;
   if (c == 0.f) return;
   const int64_t j = pos_j[i * cap + s];
   for (int col = lane; col < d; col += 32) {
     const float v = c * (emb[i * d + col] - emb[j * d + col]);
     atomicAdd(&gemb[i * d + col], v);
     atomicAdd(&gemb[j * d + col], -v);
+  }
+}
+
+// gemb *= gloss / #positive triplets: closes the fused batch-all step (the count is only known after the last tile)
+__global__ void pair_scale_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ stats,
+                                  const float* __restrict__ gloss) {
+  const float k = static_cast<float>((gloss ? static_cast<double>(gloss[0]) : 1.0) / (stats[1] + 1e-16));
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (int64_t i = i0; i < n / 4; i += stride) {
+      float4 v = g4[i];
+      v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+      g4[i] = v;
+    }
+    for (int64_t i = (n / 4) * 4 + i0; i < n; i += stride) g[i] *= k;
+  } else {
+    for (int64_t i = i0; i < n; i += stride) g[i] *= k;
   }
 }
 
@@ -1253,7 +1585,8 @@ size_t en_ws_bytes_batch_hard(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles_n = static_cast<size_t>((B + tc::BN - 1) / tc::BN);
   return operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles_n * BH_SLOTS * sizeof(BhCand)) +
-         align_up(static_cast<size_t>((B + FF_WARPS - 1) / FF_WARPS) * sizeof(double)) + align_up(sizeof(unsigned));
+         align_up(static_cast<size_t>(B) * sizeof(double)) + align_up(static_cast<size_t>(B) * sizeof(int32_t)) +
+         align_up(4 * sizeof(unsigned));
 }
 
 static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
@@ -1268,16 +1601,17 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
   TcOperands o;
-  // The GEMM only SELECTS (top-2 candidates per anchor and tile slot); the finalize kernel re-evaluates everything
+  // The GEMM only SELECTS (top-2 candidates per anchor and tile slot); the finalize kernels re-evaluate everything
   // inside the error band exactly.  Split-BF16 operands run the tensor pipe at twice the TF32 rate.
   const int tiles_n = static_cast<int>((B + tc::BN - 1) / tc::BN);
   BhCand* cand = w.take<BhCand>(static_cast<size_t>(B) * tiles_n * BH_SLOTS);
-  const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
-  double* partial = w.take<double>((B + FF_WARPS - 1) / FF_WARPS);
-  unsigned* counter = w.take<unsigned>(1);
+  // per-anchor hinge values (fast path) / per-block partial sums (generic path: one per 8 anchors)
+  double* hinge_all = w.take<double>(B);
+  int32_t* work_list = w.take<int32_t>(B);
+  unsigned* counters = w.take<unsigned>(4);  // [0] work-list length, [1] finished blocks
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "%s: workspace too small or misaligned", who);
-  // the operand split also zeroes the gradient buffer and the finalize counter (no memset nodes in the step)
-  if (int rc = prepare_operands(emb, B, d, w, st, o, false, true, gemb, counter)) return rc;
+  // the operand split also zeroes the gradient buffer and the two counters (no memset nodes in the step)
+  if (int rc = prepare_operands(emb, B, d, w, st, o, false, true, gemb, counters)) return rc;
   // |dot~ - dot| <= c |a||b| with c = 3 * 2^-16 (dropped lo*lo and residual products of the BF16 split) +
   // 2^-22 (d/16 + 1) (accumulator truncation): 5.4e-5 at d = 512 (measured maximum: 4e-6).  Proxy = |b|^2 - 2 dot,
   // |a||b| <= (|a|^2 + |b|^2) / 2, best and contender both off by it: band = 2 c (|a|^2 + |b|^2).
@@ -1286,36 +1620,55 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   const float band_c = 2.0f * (3.0f / 65536.0f + (o.dpad / 16 + 1) / 4194304.0f) + 1.0f / 16384.0f;
   tc::Shape sh = tc::make_shape_symmetric(B, d, 3, 1);  // upper-triangular tiles, one per work item; BF16 planes
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
+  const int sms = device_sm_count();
   prof_begin(st);
-  EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, device_sm_count(), st));
+  EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
   ++launch_counter();
   const bool fast = d % 128 == 0 && d <= 512 && tiles_n * BH_SLOTS <= 128 &&
                     (reinterpret_cast<uintptr_t>(emb) & 15) == 0;
-  const unsigned fblocks = static_cast<unsigned>((B + FF_WARPS - 1) / FF_WARPS);
-#define EN_BH_FAST(G, DV)                                                                                       \
-  batch_hard_finalize_fast_kernel<G, DV><<<fblocks, FF_WARPS * 32, 0, st>>>(                                      \
-      emb, labels, o.norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial, \
-      counter, loss, G ? gloss : nullptr, G ? gemb : nullptr)
-  if (fast && gemb) {
-    if (d == 128) EN_BH_FAST(true, 1);
-    else if (d == 256) EN_BH_FAST(true, 2);
-    else if (d == 384) EN_BH_FAST(true, 3);
-    else EN_BH_FAST(true, 4);
-  } else if (fast) {
-    if (d == 128) EN_BH_FAST(false, 1);
-    else if (d == 256) EN_BH_FAST(false, 2);
-    else if (d == 384) EN_BH_FAST(false, 3);
-    else EN_BH_FAST(false, 4);
-  } else if (gemb)
+  if (fast) {
+    const unsigned fblocks = static_cast<unsigned>((B + FF_WARPS - 1) / FF_WARPS);
+#define EN_BH_FAST(G, DV)                                                                                        \
+  batch_hard_finalize_fast_kernel<G, DV><<<fblocks, FF_WARPS * 32, 0, st>>>(                                       \
+      emb, labels, o.norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, hinge_all, \
+      work_list, counters, G ? gloss : nullptr, G ? gemb : nullptr)
+    if (gemb) {
+      if (d == 128) EN_BH_FAST(true, 1);
+      else if (d == 256) EN_BH_FAST(true, 2);
+      else if (d == 384) EN_BH_FAST(true, 3);
+      else EN_BH_FAST(true, 4);
+    } else {
+      if (d == 128) EN_BH_FAST(false, 1);
+      else if (d == 256) EN_BH_FAST(false, 2);
+      else if (d == 384) EN_BH_FAST(false, 3);
+      else EN_BH_FAST(false, 4);
+    }
+#undef EN_BH_FAST
+    EN_LAUNCHED("batch_hard_finalize_fast_kernel");
+    // the anchors on the work list (a block each; enough blocks that each takes one: the kernel's duration is one
+    // anchor's dependent chain of loads) and the deterministic mean
+    const unsigned sblocks = static_cast<unsigned>(sms > 0 ? sms : 148) * 4;
+    if (gemb)
+      batch_hard_finalize_slow_kernel<true><<<sblocks, FS_WARPS * 32, 0, st>>>(
+          emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef,
+          hinge_all, work_list, counters, loss, gloss, gemb);
+    else
+      batch_hard_finalize_slow_kernel<false><<<sblocks, FS_WARPS * 32, 0, st>>>(
+          emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef,
+          hinge_all, work_list, counters, loss, nullptr, nullptr);
+    EN_LAUNCHED("batch_hard_finalize_slow_kernel");
+    return EN_OK;
+  }
+  const unsigned blocks = static_cast<unsigned>((B + 7) / 8);
+  if (gemb)
     batch_hard_finalize_kernel<true><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
-                                                             squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial,
-                                                             counter, loss, gloss, gemb);
+                                                             squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef,
+                                                             hinge_all, counters + 1, loss, gloss, gemb);
   else
     batch_hard_finalize_kernel<false><<<blocks, 256, 0, st>>>(emb, labels, o.norms, cand, B, d, tiles_n, margin,
-                                                              squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, partial,
-                                                              counter, loss, nullptr, nullptr);
-#undef EN_BH_FAST
+                                                              squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef,
+                                                              hinge_all, counters + 1, loss, nullptr, nullptr);
   EN_LAUNCHED("batch_hard_finalize_kernel");
   return EN_OK;
 }
@@ -1360,7 +1713,9 @@ size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
   const size_t fwd = operand_bytes(B, d) + pos_bytes(B, max_positives) +
                      align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
-  const size_t bwd = pos_bytes(B, kTcBwdMaxPos) + pair_bwd_tc_ws_bytes(B, d);
+  const size_t bwd = pos_bytes(B, kTcBwdMaxPos) +
+                     align_up(static_cast<size_t>(B) * pair_tc_partials_per_row(B, d) * sizeof(PairPartial)) +
+                     pair_tc_ws_bytes(B, d);
   return fwd > bwd ? fwd : bwd;
 }
 
@@ -1439,10 +1794,10 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   if (tensor) {
-    // negatives: two chained tcgen05 GEMMs (csrc/pair_bwd_tc.cu); overwrites gemb
+    // negatives: two chained tcgen05 GEMMs (csrc/pair_tc.cu); overwrites gemb
     void* rest = w.base + w.off;
-    if (int rc = pair_bwd_tc_launch(emb, labels, B, d, 0, squared, margin, 0.f, pl.pos_d, pl.pos_n, pl.pos_cnt, stats,
-                                    gloss, gemb, rest, ws_bytes - w.off, st))
+    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, stats,
+                                gloss, nullptr, gemb, rest, ws_bytes - w.off, st))
       return rc;
   } else {
     // classes with more than 8 positives per anchor: CUDA-core tile kernel
@@ -1457,8 +1812,62 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   // positives: sparse, one warp per (anchor, positive slot), added atomically
   const int64_t warps = B * cap;
   batch_all_bwd_pos_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
-      emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb);
+      emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, 0);
   EN_LAUNCHED("batch_all_bwd_pos_kernel");
+  return EN_OK;
+}
+
+// Loss AND gradient of batch-all from ONE pass over the distance tiles (csrc/pair_tc.cu): positives lists, centred
+// operand planes and S tiles are built once; the gradient is accumulated unscaled and divided by the number of
+// positive triplets at the end (that count is only known once every tile has been seen).
+int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                         int max_positives, float* out, double* stats, const float* gloss, float* gemb, void* ws,
+                         size_t ws_bytes, void* stream) {
+  EN_REQUIRE(emb && labels && out && stats && gemb && B > 1 && d > 0, "en_batch_all_fwd_bwd: bad arguments");
+  EN_REQUIRE(max_positives > 0 && max_positives <= kMaxPos,
+             "en_batch_all_fwd_bwd: max_positives must be in [1, %d] (largest class size - 1); got %d", kMaxPos,
+             max_positives);
+  if (int rc = check_sm100()) return rc;
+  if (!ws || ws_bytes < en_ws_bytes_batch_all(B, d, max_positives))
+    return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  if (max_positives > kTcBwdMaxPos) {
+    // large classes: forward kernel, then the CUDA-core backward (needs a device gloss)
+    EN_REQUIRE(gloss != nullptr, "en_batch_all_fwd_bwd: gloss is required when max_positives > %d", kTcBwdMaxPos);
+    if (int rc = en_batch_all_fwd(emb, labels, B, d, margin, squared, max_positives, out, stats, ws, ws_bytes, stream))
+      return rc;
+    return en_batch_all_bwd(emb, labels, B, d, margin, squared, max_positives, stats, gloss, gemb, ws, ws_bytes, stream);
+  }
+  Workspace w(ws, ws_bytes);
+  const int cap = kTcBwdMaxPos;
+  PosLists pl = take_pos(w, B, cap);
+  const int ppr = pair_tc_partials_per_row(B, d);
+  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * ppr);
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd_bwd: workspace too small or misaligned");
+  EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
+  collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
+  EN_LAUNCHED("collect_positives_kernel");
+  EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
+  EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
+  void* rest = w.base + w.off;
+  if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, nullptr,
+                              nullptr, partial, gemb, rest, ws_bytes - w.off, st))
+    return rc;
+  if (int rc = launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, pl.pos_n, B, 0, out, stats, st)) return rc;
+  const int64_t warps = B * cap;
+  batch_all_bwd_pos_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
+      emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, 1);
+  EN_LAUNCHED("batch_all_bwd_pos_kernel");
+  pair_scale_kernel<<<148 * 4, 256, 0, st>>>(gemb, static_cast<int64_t>(B) * d, stats, gloss);
+  EN_LAUNCHED("pair_scale_kernel");
+  // a class larger than max_positives + 1 would silently drop triplets: surface it (one 4-byte read-back)
+  int32_t status_h = 0;
+  EN_CUDA(cudaMemcpyAsync(&status_h, pl.status, 4, cudaMemcpyDeviceToHost, st));
+  EN_CUDA(cudaStreamSynchronize(st));
+  if (status_h > 0)
+    return fail(EN_ERR_ARG, "en_batch_all_fwd_bwd: a class has %d positives per anchor but max_positives = %d",
+                status_h, max_positives);
   return EN_OK;
 }
 
@@ -1467,7 +1876,8 @@ size_t en_ws_bytes_contrastive_allpairs(int64_t B, int d) {
   if (B <= 0 || d <= 0) return 0;
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
   const size_t fwd = operand_bytes(B, d) + align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
-  const size_t bwd = pair_bwd_tc_ws_bytes(B, d);
+  const size_t bwd = align_up(static_cast<size_t>(B) * pair_tc_partials_per_row(B, d) * sizeof(PairPartial)) +
+                     pair_tc_ws_bytes(B, d);
   return fwd > bwd ? fwd : bwd;
 }
 
@@ -1499,9 +1909,30 @@ int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t
   EN_REQUIRE(emb && labels && gloss && gemb && B > 1 && d > 0, "en_contrastive_allpairs_bwd: bad arguments");
   if (!ws || ws_bytes < en_ws_bytes_contrastive_allpairs(B, d))
     return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_bwd: workspace too small");
-  const float scale = static_cast<float>(1.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
-  return pair_bwd_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, gemb, ws,
-                            ws_bytes, as_stream(stream));
+  const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
+  return pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, nullptr, gemb,
+                        ws, ws_bytes, as_stream(stream));
+}
+
+// Loss AND gradient of the all-pairs contrastive loss from one pass over the distance tiles (csrc/pair_tc.cu).
+int en_contrastive_allpairs_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float* loss,
+                                    const float* gloss, float* gemb, void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(emb && labels && loss && gemb && B > 1 && d > 0, "en_contrastive_allpairs_fwd_bwd: bad arguments");
+  if (int rc = check_sm100()) return rc;
+  if (!ws || ws_bytes < en_ws_bytes_contrastive_allpairs(B, d))
+    return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_fwd_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  Workspace w(ws, ws_bytes);
+  const int ppr = pair_tc_partials_per_row(B, d);
+  PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * ppr);
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_fwd_bwd: workspace too small or misaligned");
+  EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
+  const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
+  void* rest = w.base + w.off;
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, partial,
+                              gemb, rest, ws_bytes - w.off, st))
+    return rc;
+  return launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, nullptr, B, 1, loss, nullptr, st);
 }
 
 }  // extern "C"

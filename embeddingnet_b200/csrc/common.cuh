@@ -86,6 +86,12 @@ inline double cert_bound(int precision, int d) {
   return 1.5 * c;
 }
 
+// Per-(row, column range, half) partial of a pair loss: the sum of its terms and, for batch-all, how many were > 0.
+struct PairPartial {
+  double sum;
+  unsigned long long npos;
+};
+
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

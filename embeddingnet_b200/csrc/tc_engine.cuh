@@ -439,7 +439,7 @@ __device__ __forceinline__ uint16_t to_bf16_bits(float x) {
   asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
   return r;
 }
-// `zero_rows` (optional, rows x d floats) is cleared and `zero_word` (optional) reset on the way: the fused
+// `zero_rows` (optional, rows x d floats) is cleared and `zero_word[0..1]` (optional) reset on the way: the fused
 // loss + gradient step needs a zeroed gradient buffer and counter, and a store here is cheaper than memset nodes.
 static __global__ void split_planes_bf16_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx, int dpad,
                                                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
@@ -448,7 +448,7 @@ static __global__ void split_planes_bf16_kernel(const float* __restrict__ x, int
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  if (zero_word != nullptr && row == 0 && lane == 0) *zero_word = 0u;
+  if (zero_word != nullptr && row == 0 && lane < 2) zero_word[lane] = 0u;  // two adjacent counters
   if (zero_rows != nullptr) {
     float* z = zero_rows + row * d;
     if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(zero_rows) & 15) == 0)

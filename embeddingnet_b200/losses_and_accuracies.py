@@ -194,6 +194,19 @@ def siamese_l1_distance(e1, e2):
 
 
 # ------------------------------------------------------------------------------------------------ batch-hard
+def _consume_stored_gradient(ctx, g, who):
+    """Backward of the fused losses: forward already stored d loss / d emb; hand that buffer to autograd, scaled in
+    place by the upstream gradient (the kernel returns at once when it is exactly 1, i.e. plain loss.backward())."""
+    gemb = getattr(ctx, "gemb", None)
+    if gemb is None:
+        raise RuntimeError("%s: backward was already run for this forward (the fused step stores d loss / d emb "
+                           "once and hands the buffer over); call the loss again" % who)
+    ctx.gemb = None
+    g = g.contiguous().to(torch.float32).reshape(1)
+    _lib.call("en_scale_inplace", ptr(gemb), gemb.numel(), ptr(g), stream_ptr())
+    return gemb
+
+
 class _BatchHard(torch.autograd.Function):
     """Forward computes the loss AND d loss / d emb in the same pass (en_batch_hard_fwd_bwd) whenever a gradient can
     be asked for; backward is then a scalar multiply."""
@@ -221,15 +234,7 @@ class _BatchHard(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        gemb = getattr(ctx, "gemb", None)
-        if gemb is None:
-            raise RuntimeError("batch_hard_triplet_loss: backward was already run for this forward (the fused step "
-                               "stores d loss / d emb once and hands the buffer over); call the loss again")
-        ctx.gemb = None
-        g = g.contiguous().to(torch.float32).reshape(1)
-        # upstream gradient applied in place; the kernel returns at once when it is exactly 1 (plain loss.backward())
-        _lib.call("en_scale_inplace", ptr(gemb), gemb.numel(), ptr(g), stream_ptr())
-        return gemb, None, None, None, None
+        return _consume_stored_gradient(ctx, g, "batch_hard_triplet_loss"), None, None, None, None
 
 
 def batch_hard_triplet_loss(margin=0.5, squared=False, soft=False):
@@ -253,6 +258,9 @@ def batch_hard_triplet_loss(margin=0.5, squared=False, soft=False):
 
 # ------------------------------------------------------------------------------------------------ batch-all
 class _BatchAll(torch.autograd.Function):
+    """When a gradient can be asked for, forward runs the fused pass (en_batch_all_fwd_bwd: distance tiles computed
+    once for loss and gradient) and backward only applies the upstream gradient."""
+
     @staticmethod
     def forward(ctx, emb, labels, margin, squared, max_pos):
         B, d = emb.shape
@@ -261,26 +269,22 @@ class _BatchAll(torch.autograd.Function):
         ws = workspace(lib.en_ws_bytes_batch_all(B, d, max_pos), dev, "batch_all")
         out = torch.empty(2, dtype=torch.float32, device=dev)
         stats = torch.empty(3, dtype=torch.float64, device=dev)
-        _lib.call("en_batch_all_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared), max_pos,
-                  ptr(out), ptr(stats), ptr(ws), ws.numel(), stream_ptr())
-        ctx.save_for_backward(emb, labels, stats)
-        ctx.cfg = (margin, int(squared), max_pos)
+        if ctx.needs_input_grad[0]:
+            gemb = torch.empty_like(emb)
+            ones = torch.ones(1, dtype=torch.float32, device=dev)
+            _lib.call("en_batch_all_fwd_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
+                      max_pos, ptr(out), ptr(stats), ptr(ones), ptr(gemb), ptr(ws), ws.numel(), stream_ptr())
+            ctx.gemb = gemb
+        else:
+            _lib.call("en_batch_all_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared), max_pos,
+                      ptr(out), ptr(stats), ptr(ws), ws.numel(), stream_ptr())
         loss, frac = out[0].clone(), out[1].clone()
         ctx.mark_non_differentiable(frac)
         return loss, frac
 
     @staticmethod
     def backward(ctx, g, _gfrac):
-        emb, labels, stats = ctx.saved_tensors
-        margin, squared, max_pos = ctx.cfg
-        B, d = emb.shape
-        lib = _lib.load()
-        ws = workspace(lib.en_ws_bytes_batch_all(B, d, max_pos), emb.device, "batch_all")
-        g = g.contiguous().to(torch.float32).reshape(1)
-        gemb = torch.empty_like(emb)
-        _lib.call("en_batch_all_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), squared, max_pos,
-                  ptr(stats), ptr(g), ptr(gemb), ptr(ws), ws.numel(), stream_ptr())
-        return gemb, None, None, None, None
+        return _consume_stored_gradient(ctx, g, "batch_all_triplet_loss"), None, None, None, None
 
 
 def batch_all_triplet_loss(margin=0.5, squared=False, max_positives=None, return_fraction=False):
@@ -313,22 +317,19 @@ class _ContrastiveAllPairs(torch.autograd.Function):
         lib = _lib.load()
         ws = workspace(lib.en_ws_bytes_contrastive_allpairs(B, d), emb.device, "contrastive_all")
         loss = torch.empty((), dtype=torch.float32, device=emb.device)
-        _lib.call("en_contrastive_allpairs_fwd", ptr(emb), ptr(labels), B, d, ptr(loss), ptr(ws), ws.numel(),
-                  stream_ptr())
-        ctx.save_for_backward(emb, labels)
+        if ctx.needs_input_grad[0]:
+            gemb = torch.empty_like(emb)
+            _lib.call("en_contrastive_allpairs_fwd_bwd", ptr(emb), ptr(labels), B, d, ptr(loss), None, ptr(gemb),
+                      ptr(ws), ws.numel(), stream_ptr())
+            ctx.gemb = gemb
+        else:
+            _lib.call("en_contrastive_allpairs_fwd", ptr(emb), ptr(labels), B, d, ptr(loss), ptr(ws), ws.numel(),
+                      stream_ptr())
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        emb, labels = ctx.saved_tensors
-        B, d = emb.shape
-        lib = _lib.load()
-        ws = workspace(lib.en_ws_bytes_contrastive_allpairs(B, d), emb.device, "contrastive_all")
-        g = g.contiguous().to(torch.float32).reshape(1)
-        gemb = torch.empty_like(emb)
-        _lib.call("en_contrastive_allpairs_bwd", ptr(emb), ptr(labels), B, d, ptr(g), ptr(gemb), ptr(ws), ws.numel(),
-                  stream_ptr())
-        return gemb, None
+        return _consume_stored_gradient(ctx, g, "contrastive_loss_all_pairs"), None
 
 
 def contrastive_loss_all_pairs():

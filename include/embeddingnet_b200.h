@@ -152,6 +152,13 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
 int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
                      int max_positives, const double* stats, const float* gloss, float* gemb, void* ws,
                      size_t ws_bytes, void* stream);
+/* Loss AND gradient from ONE pass over the distance tiles (what a training step needs; Keras differentiates the loss
+ * callable inside the same train step, train.py:160-162): out / stats as en_batch_all_fwd, gemb (B, d) =
+ * gloss[0] * d loss / d emb (gloss == NULL means 1).  Classes with more than 8 positives per anchor take the two
+ * separate passes internally and need a non-NULL gloss. */
+int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
+                         int max_positives, float* out, double* stats, const float* gloss, float* gemb, void* ws,
+                         size_t ws_bytes, void* stream);
 
 /* All-pairs contrastive loss: losses_and_accuracies.py:4-11 over every ordered pair i != j with
  * y_ij = [label_i == label_j] and d_ij = sqrt(max(|e_i - e_j|^2, 1e-7)) (models.py:225).  loss is 1 float. */
@@ -160,6 +167,9 @@ int en_contrastive_allpairs_fwd(const float* emb, const int32_t* labels, int64_t
                                 size_t ws_bytes, void* stream);
 int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t B, int d, const float* gloss,
                                 float* gemb, void* ws, size_t ws_bytes, void* stream);
+/* Loss AND gradient in one pass (see en_batch_all_fwd_bwd); gloss == NULL means 1. */
+int en_contrastive_allpairs_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float* loss,
+                                    const float* gloss, float* gemb, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- encoding bank: nearest neighbours */
 /* Operand format of the tensor-core scan.  Both split every fp32 value into two planes (hi, lo) and issue three

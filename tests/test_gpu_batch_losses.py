@@ -239,11 +239,15 @@ def run_batch_hard(x, lab, margin=0.5, squared=False, soft=False):
             g.cpu().numpy())
 
 
-@pytest.mark.parametrize("ncls,per,d", [(512, 8, 128),   # B = 4096: fast finalize (DV = 1), 32 row tiles
-                                        (512, 8, 512),   # the headline shape (DV = 4)
-                                        (48, 8, 100)])   # 384 rows, 3 tiles, generic finalize kernel
-@pytest.mark.parametrize("n_dup", [3, 5])
-@pytest.mark.parametrize("kind", ["exact", "near"])
+SAT_CASES = [(ncls, per, d, n_dup, kind)
+             for (ncls, per, d) in [(512, 8, 128),   # B = 4096: fast + slow finalize kernels (DV = 1), 32 row tiles
+                                    (48, 8, 100)]    # 384 rows, 3 tiles, generic finalize kernel
+             for n_dup in (3, 5) for kind in ("exact", "near")]
+# the headline shape (DV = 4); its float64 oracle takes ~20 s per case on the host, so two of the four combinations
+SAT_CASES += [(512, 8, 512, 3, "exact"), (512, 8, 512, 5, "near")]
+
+
+@pytest.mark.parametrize("ncls,per,d,n_dup,kind", SAT_CASES)
 def test_batch_hard_saturated_slots(ncls, per, d, n_dup, kind):
     """Three / five copies (exact, or 1e-7 apart) of one row in ADJACENT rows = inside one record slot (one 64-column
     half of the row view, one 32-row quarter of the column view), placed so that they are the hardest negative and
