@@ -54,7 +54,7 @@ SIGNATURES = {
     "en_ws_bytes_batch_all": (c_size_t, [c_int64, c_int, c_int]),
     "en_batch_all_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, c_size_t, P]),
     "en_batch_all_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, c_size_t, P]),
-    "en_batch_all_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "en_batch_all_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_contrastive_allpairs": (c_size_t, [c_int64, c_int]),
     "en_contrastive_allpairs_fwd": (c_int, [P, P, c_int64, c_int, P, P, c_size_t, P]),
     "en_contrastive_allpairs_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, c_size_t, P]),
@@ -81,7 +81,9 @@ SIGNATURES = {
     "en_dense_plane_bytes": (c_size_t, [c_int, c_int]),
     "en_dense_prepare": (c_int, [P, c_int, c_int, P, P, P]),
     "en_ws_bytes_dense": (c_size_t, [c_int64, c_int]),
-    "en_dense_relu_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P, c_size_t, P]),
+    "en_dense_relu_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P, P, c_size_t, P]),
+    "en_ws_bytes_dense_bwd": (c_size_t, [c_int64, c_int, c_int]),
+    "en_dense_relu_bwd": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "en_synth_fill": (c_int, [P, c_int64, c_int, c_int64, c_uint64, c_uint64, c_int64, c_int64, c_float, c_int, P, P]),
 }
 

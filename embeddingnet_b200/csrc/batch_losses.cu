@@ -21,7 +21,10 @@ size_t pair_tc_ws_bytes(int64_t B, int d);
 int pair_tc_partials_per_row(int64_t B, int d);
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
                    float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
-                   const float* gloss, PairPartial* partial, float* gemb, void* ws, size_t ws_bytes, cudaStream_t st);
+                   PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws, size_t ws_bytes, cudaStream_t st);
+int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, int cap, int squared, const float* pos_d,
+                   const int32_t* pos_j, const int32_t* pos_n, const int32_t* pos_cnt, const double* stats,
+                   const float* gloss, float* gemb, cudaStream_t st);
 
 namespace {
 
@@ -1054,7 +1057,45 @@ __global__ void batch_hard_bwd_scatter_kernel(const float* __restrict__ emb, int
 // =====================================================================================================
 constexpr int kMaxPos = 63;  // largest supported (class size - 1); bounded by the epilogue's shared-memory budget
 
+// exact_d2() for four rows at once: the same per-row arithmetic (element order, fma chain, butterfly), so the
+// results are bit-identical; the loads of all four rows are in flight together.
+__device__ __forceinline__ void exact_d2x4(const float* __restrict__ e, int d, int64_t i, const int (&j)[4], int lane,
+                                           double (&out)[4]) {
+  const float* a = e + i * d;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0) {
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(a + c);
+      float4 y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[u]) * d + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double t;
+        t = static_cast<double>(x.x) - static_cast<double>(y[u].x); acc[u] = fma(t, t, acc[u]);
+        t = static_cast<double>(x.y) - static_cast<double>(y[u].y); acc[u] = fma(t, t, acc[u]);
+        t = static_cast<double>(x.z) - static_cast<double>(y[u].z); acc[u] = fma(t, t, acc[u]);
+        t = static_cast<double>(x.w) - static_cast<double>(y[u].w); acc[u] = fma(t, t, acc[u]);
+      }
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double t = static_cast<double>(a[c]) - static_cast<double>(e[static_cast<int64_t>(j[u]) * d + c]);
+        acc[u] = fma(t, t, acc[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[u] = warp_sum(acc[u]);
+}
+
 // One warp per anchor: list its positives (same label, j != i, ascending j) with exact distances.
+// Two phases so that a warp's chain of dependent memory round trips is short (the kernel is a fraction of one wave:
+// its duration is ONE warp's latency; round 1/2 launch lists: 23 us, more than a third of the distance GEMM it
+// prepares): (1) the label scan, 512 labels per trip with all four 128-bit loads in flight; (2) the distances, four
+// positives per trip.
 __global__ void collect_positives_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                          int64_t B, int d, int squared, int cap, float* __restrict__ pos_d,
                                          int32_t* __restrict__ pos_j, int32_t* __restrict__ pos_n,
@@ -1064,32 +1105,32 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
   if (row >= B) return;
   const int32_t la = labels[row];
   int count = 0;
+  int32_t* mine_j = pos_j + row * cap;
   auto emit = [&](int64_t jj) {
-    const double d2 = exact_d2(emb, d, row, jj, lane);
-    if (count < cap && lane == 0) {
-      pos_d[row * cap + count] = static_cast<float>(squared ? d2 : sqrt(d2));
-      pos_j[row * cap + count] = static_cast<int32_t>(jj);
-    }
+    if (count < cap && lane == 0) mine_j[count] = static_cast<int32_t>(jj);
     ++count;
   };
   int64_t j0 = 0;
   if ((reinterpret_cast<uintptr_t>(labels) & 15) == 0) {
-    // 128 labels per step (one int4 per lane); nearly every step finds nothing (ncu, round 1: the one-label-per-lane
-    // scan made this kernel as slow as the distance GEMM it prepares)
-    for (; j0 + 128 <= B; j0 += 128) {
-      const int4 l4 = __ldg(reinterpret_cast<const int4*>(labels + j0) + lane);
-      const int64_t jb = j0 + 4 * lane;
-      unsigned f = (l4.x == la && jb != row ? 1u : 0u) | (l4.y == la && jb + 1 != row ? 2u : 0u) |
-                   (l4.z == la && jb + 2 != row ? 4u : 0u) | (l4.w == la && jb + 3 != row ? 8u : 0u);
-      unsigned m = __ballot_sync(0xffffffffu, f != 0);
-      while (m) {  // ascending j: lanes in order, then the four labels of a lane in order
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        unsigned fs = __shfl_sync(0xffffffffu, f, src);
-        while (fs) {
-          const int sub = __ffs(fs) - 1;
-          fs &= fs - 1;
-          emit(j0 + 4 * src + sub);
+    for (; j0 + 512 <= B; j0 += 512) {
+      int4 l4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) l4[u] = __ldg(reinterpret_cast<const int4*>(labels + j0 + 128 * u) + lane);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t jb = j0 + 128 * u + 4 * lane;
+        const unsigned f = (l4[u].x == la && jb != row ? 1u : 0u) | (l4[u].y == la && jb + 1 != row ? 2u : 0u) |
+                           (l4[u].z == la && jb + 2 != row ? 4u : 0u) | (l4[u].w == la && jb + 3 != row ? 8u : 0u);
+        unsigned m = __ballot_sync(0xffffffffu, f != 0);
+        while (m) {  // ascending j: lanes in order, then the four labels of a lane in order
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          unsigned fs = __shfl_sync(0xffffffffu, f, src);
+          while (fs) {
+            const int sub = __ffs(fs) - 1;
+            fs &= fs - 1;
+            emit(j0 + 128 * u + 4 * src + sub);
+          }
         }
       }
     }
@@ -1104,8 +1145,21 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
       emit(j0 + src);
     }
   }
+  const int n = count < cap ? count : cap;
+  __syncwarp();  // lane 0's index stores are visible to the warp
+  for (int s0 = 0; s0 < n; s0 += 4) {
+    int jj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) jj[u] = mine_j[s0 + u < n ? s0 + u : s0];
+    double d2[4];
+    exact_d2x4(emb, d, row, jj, lane, d2);
+    if (lane < 4 && s0 + lane < n) {
+      const double v = lane == 0 ? d2[0] : lane == 1 ? d2[1] : lane == 2 ? d2[2] : d2[3];
+      pos_d[row * cap + s0 + lane] = static_cast<float>(squared ? v : sqrt(v));
+    }
+  }
   if (lane == 0) {
-    pos_n[row] = count < cap ? count : cap;
+    pos_n[row] = n;
     if (count > cap) atomicMax(status, count);  // caller's max_positives was too small
   }
 }
@@ -1274,7 +1328,7 @@ __global__ void pair_reduce_stage1_kernel(PairPartial* __restrict__ partial, int
 // Stage 2 (one block): the chunk heads (stride `chunk`), plus the valid-triplet count of batch-all.
 __global__ void pair_reduce_kernel(const PairPartial* __restrict__ partial, int64_t n_partials, int64_t chunk,
                                    const int32_t* __restrict__ pos_n, int64_t B, int mode, float* __restrict__ out,
-                                   double* __restrict__ stats) {
+                                   double* __restrict__ stats, const int32_t* __restrict__ overflow) {
   __shared__ double s_sum[32], s_cnt[32], s_val[32];
   double sum = 0.0, cnt = 0.0, nvalid = 0.0;
   for (int64_t i = static_cast<int64_t>(threadIdx.x) * chunk; i < n_partials; i += blockDim.x * chunk) {
@@ -1297,6 +1351,9 @@ __global__ void pair_reduce_kernel(const PairPartial* __restrict__ partial, int6
   if (threadIdx.x == 0) {
     double a = 0, b = 0, c = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) { a += s_sum[w]; b += s_cnt[w]; c += s_val[w]; }
+    // a class with more positives per anchor than the lists hold would silently drop triplets: poison the results
+    // (loss, fraction, and through stats[1] the gradient) instead -- the fused step does not read the flag back
+    if (overflow != nullptr && *overflow > 0) a = b = c = __longlong_as_double(0x7ff8000000000000ll);
     if (mode == 0) {
       out[0] = static_cast<float>(a / (b + 1e-16));
       out[1] = static_cast<float>(b / (c + 1e-16));
@@ -1459,59 +1516,96 @@ pair_bwd_kernel(const float* __restrict__ emb, const int32_t* __restrict__ label
   }
 }
 
-// Batch-all positive pairs: G_ij = +#{k in N_i : D_ij + m - D_ik > 0} / np, sparse; one warp per (anchor, slot).
+// Batch-all positive pairs: G_ij = +#{k in N_i : D_ij + m - D_ik > 0} / np, sparse.  One warp per anchor i:
+//   grad_i += sum_{j in P(i)} (c_ij + c_ji) (e_i - e_j),  c_ij = cnt(anchor i, slot of j) * s(D_ij) / np
+// (the mirrored term of pair (j, i) lands on row i with the opposite sign of e_j - e_i, so it is the same vector).
+// Each row has a single writer: no atomics (the one-warp-per-(anchor, slot) version issued 33 M float atomics and
+// took 34 us at B = 4096, d = 512; ncu launch list r2).  c_ji is looked up in j's own list (j lists i because the
+// relation "same label" is symmetric and the lists are complete -- the forward pass rejects overflowing classes).
 __global__ void batch_all_bwd_pos_kernel(const float* __restrict__ emb, int64_t B, int d, int cap, int squared,
                                          const float* __restrict__ pos_d, const int32_t* __restrict__ pos_j,
                                          const int32_t* __restrict__ pos_n, const int32_t* __restrict__ pos_cnt,
                                          const double* __restrict__ stats, const float* __restrict__ gloss,
                                          float* __restrict__ gemb, int unscaled) {
-  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t i = wid / cap;
-  const int s = static_cast<int>(wid % cap);
-  if (i >= B || s >= pos_n[i]) return;
-  const int cnt = pos_cnt[i * cap + s];
-  if (cnt == 0) return;
-  const float dij = pos_d[i * cap + s];
-  const float sfac = squared ? 2.f : (dij > 0.f ? 1.f / dij : 0.f);
+  if (i >= B) return;
+  const int n = pos_n[i];
+  if (n == 0) return;
   // unscaled: the fused step divides the finished gradient by #positive triplets (pair_scale_kernel)
-  const float c = unscaled ? static_cast<float>(cnt) * sfac
-                           : gloss[0] * static_cast<float>(static_cast<double>(cnt) / (stats[1] + 1e-16)) * sfac;
-  if (c == 0.f) return;
-  const int64_t j = pos_j[i * cap + s];
-  for (int col = lane; col < d; col += 32) {
-    const float v = c * (emb[i * d + col] - emb[j * d + col]);
-    atomicAdd(&gemb[i * d + col], v);
-    atomicAdd(&gemb[j * d + col], -v);
-  }
-}
-
-// gemb *= gloss / #positive triplets: closes the fused batch-all step (the count is only known after the last tile)
-__global__ void pair_scale_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ stats,
-                                  const float* __restrict__ gloss) {
-  const float k = static_cast<float>((gloss ? static_cast<double>(gloss[0]) : 1.0) / (stats[1] + 1e-16));
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-    float4* g4 = reinterpret_cast<float4*>(g);
-    for (int64_t i = i0; i < n / 4; i += stride) {
-      float4 v = g4[i];
-      v.x *= k; v.y *= k; v.z *= k; v.w *= k;
-      g4[i] = v;
+  const float scale = unscaled ? 1.f : gloss[0] * static_cast<float>(1.0 / (stats[1] + 1e-16));
+  // lane s (and s + 32) prepares the weight of positive s: w_s = (cnt_ij + cnt_ji) * s(D_ij) * scale
+  float wgt[2] = {0.f, 0.f};
+  int jj[2] = {0, 0};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    if (s < n) {
+      const int64_t j = pos_j[i * cap + s];
+      int cnt = pos_cnt[i * cap + s];
+      const int nj = pos_n[j];
+      for (int t = 0; t < nj; ++t)
+        if (pos_j[j * cap + t] == static_cast<int32_t>(i)) {
+          cnt += pos_cnt[j * cap + t];
+          break;
+        }
+      const float dij = pos_d[i * cap + s];
+      const float sfac = squared ? 2.f : (dij > 0.f ? 1.f / dij : 0.f);
+      wgt[h] = static_cast<float>(cnt) * sfac * scale;
+      jj[h] = static_cast<int>(j);
     }
-    for (int64_t i = (n / 4) * 4 + i0; i < n; i += stride) g[i] *= k;
-  } else {
-    for (int64_t i = i0; i < n; i += stride) g[i] *= k;
+  }
+  const float* ei = emb + i * d;
+  float* gi = gemb + i * d;
+  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gemb) & 15) == 0;
+  for (int c0 = 0; c0 < d; c0 += 128) {
+    const int c = c0 + 4 * lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && c < d) x = *reinterpret_cast<const float4*>(ei + c);
+    else if (!vec) {
+      x.x = c < d ? ei[c] : 0.f; x.y = c + 1 < d ? ei[c + 1] : 0.f;
+      x.z = c + 2 < d ? ei[c + 2] : 0.f; x.w = c + 3 < d ? ei[c + 3] : 0.f;
+    }
+    for (int s = 0; s < n; ++s) {
+      const float w = __shfl_sync(0xffffffffu, wgt[s >> 5], s & 31);
+      const int j = __shfl_sync(0xffffffffu, jj[s >> 5], s & 31);
+      if (w == 0.f) continue;  // warp-uniform
+      const float* ej = emb + static_cast<int64_t>(j) * d;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec && c < d) y = __ldg(reinterpret_cast<const float4*>(ej + c));
+      else if (!vec) {
+        y.x = c < d ? ej[c] : 0.f; y.y = c + 1 < d ? ej[c + 1] : 0.f;
+        y.z = c + 2 < d ? ej[c + 2] : 0.f; y.w = c + 3 < d ? ej[c + 3] : 0.f;
+      }
+      acc.x = fmaf(w, x.x - y.x, acc.x);
+      acc.y = fmaf(w, x.y - y.y, acc.y);
+      acc.z = fmaf(w, x.z - y.z, acc.z);
+      acc.w = fmaf(w, x.w - y.w, acc.w);
+    }
+    if (vec) {
+      if (c < d) {
+        float4 g = *reinterpret_cast<float4*>(gi + c);
+        g.x += acc.x; g.y += acc.y; g.z += acc.z; g.w += acc.w;
+        *reinterpret_cast<float4*>(gi + c) = g;
+      }
+    } else {
+      if (c < d) gi[c] += acc.x;
+      if (c + 1 < d) gi[c + 1] += acc.y;
+      if (c + 2 < d) gi[c + 2] += acc.z;
+      if (c + 3 < d) gi[c + 3] += acc.w;
+    }
   }
 }
 
 int launch_pair_reduce(PairPartial* partial, int64_t n_partials, const int32_t* pos_n, int64_t B, int mode,
-                       float* out, double* stats, cudaStream_t st) {
+                       float* out, double* stats, cudaStream_t st, const int32_t* overflow = nullptr) {
   const int64_t chunk = (n_partials + kReduceBlocks - 1) / kReduceBlocks;
   const unsigned blocks = static_cast<unsigned>((n_partials + chunk - 1) / chunk);
   pair_reduce_stage1_kernel<<<blocks, 256, 0, st>>>(partial, n_partials, chunk);
   EN_LAUNCHED("pair_reduce_stage1_kernel");
-  pair_reduce_kernel<<<1, 256, 0, st>>>(partial, n_partials, chunk, pos_n, B, mode, out, stats);
+  pair_reduce_kernel<<<1, 256, 0, st>>>(partial, n_partials, chunk, pos_n, B, mode, out, stats, overflow);
   EN_LAUNCHED("pair_reduce_kernel");
   return EN_OK;
 }
@@ -1794,11 +1888,14 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   if (tensor) {
-    // negatives: two chained tcgen05 GEMMs (csrc/pair_tc.cu); overwrites gemb
+    // negatives: two chained tcgen05 GEMMs (csrc/pair_tc.cu), coefficients unscaled; the finishing kernel adds the
+    // row-sum term and the sparse positive pairs and applies gloss / #positive triplets
     void* rest = w.base + w.off;
-    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, stats,
-                                gloss, nullptr, gemb, rest, ws_bytes - w.off, st))
+    PairTcFinish fin;
+    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, nullptr,
+                                nullptr, gemb, &fin, rest, ws_bytes - w.off, st))
       return rc;
+    return pair_tc_finish(fin, emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, st);
   } else {
     // classes with more than 8 positives per anchor: CUDA-core tile kernel
     EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * 4, st));
@@ -1809,9 +1906,8 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
       EN_LAUNCHED("pair_bwd_kernel<batch_all>");
     }
   }
-  // positives: sparse, one warp per (anchor, positive slot), added atomically
-  const int64_t warps = B * cap;
-  batch_all_bwd_pos_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
+  // positives: sparse, one warp per anchor
+  batch_all_bwd_pos_kernel<<<static_cast<unsigned>((B * 32 + 127) / 128), 128, 0, st>>>(
       emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, 0);
   EN_LAUNCHED("batch_all_bwd_pos_kernel");
   return EN_OK;
@@ -1821,8 +1917,8 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
 // operand planes and S tiles are built once; the gradient is accumulated unscaled and divided by the number of
 // positive triplets at the end (that count is only known once every tile has been seen).
 int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
-                         int max_positives, float* out, double* stats, const float* gloss, float* gemb, void* ws,
-                         size_t ws_bytes, void* stream) {
+                         int max_positives, float* out, double* stats, const float* gloss, float* gemb,
+                         int32_t* overflow, void* ws, size_t ws_bytes, void* stream) {
   EN_REQUIRE(emb && labels && out && stats && gemb && B > 1 && d > 0, "en_batch_all_fwd_bwd: bad arguments");
   EN_REQUIRE(max_positives > 0 && max_positives <= kMaxPos,
              "en_batch_all_fwd_bwd: max_positives must be in [1, %d] (largest class size - 1); got %d", kMaxPos,
@@ -1834,6 +1930,7 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   if (max_positives > kTcBwdMaxPos) {
     // large classes: forward kernel, then the CUDA-core backward (needs a device gloss)
     EN_REQUIRE(gloss != nullptr, "en_batch_all_fwd_bwd: gloss is required when max_positives > %d", kTcBwdMaxPos);
+    if (overflow) EN_CUDA(cudaMemsetAsync(overflow, 0, 4, st));  // the forward pass below checks synchronously
     if (int rc = en_batch_all_fwd(emb, labels, B, d, margin, squared, max_positives, out, stats, ws, ws_bytes, stream))
       return rc;
     return en_batch_all_bwd(emb, labels, B, d, margin, squared, max_positives, stats, gloss, gemb, ws, ws_bytes, stream);
@@ -1851,23 +1948,19 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
   void* rest = w.base + w.off;
+  PairTcFinish fin;
   if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, nullptr,
-                              nullptr, partial, gemb, rest, ws_bytes - w.off, st))
+                              partial, gemb, &fin, rest, ws_bytes - w.off, st))
     return rc;
-  if (int rc = launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, pl.pos_n, B, 0, out, stats, st)) return rc;
-  const int64_t warps = B * cap;
-  batch_all_bwd_pos_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
-      emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, 1);
-  EN_LAUNCHED("batch_all_bwd_pos_kernel");
-  pair_scale_kernel<<<148 * 4, 256, 0, st>>>(gemb, static_cast<int64_t>(B) * d, stats, gloss);
-  EN_LAUNCHED("pair_scale_kernel");
-  // a class larger than max_positives + 1 would silently drop triplets: surface it (one 4-byte read-back)
-  int32_t status_h = 0;
-  EN_CUDA(cudaMemcpyAsync(&status_h, pl.status, 4, cudaMemcpyDeviceToHost, st));
-  EN_CUDA(cudaStreamSynchronize(st));
-  if (status_h > 0)
-    return fail(EN_ERR_ARG, "en_batch_all_fwd_bwd: a class has %d positives per anchor but max_positives = %d",
-                status_h, max_positives);
+  if (int rc = launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, pl.pos_n, B, 0, out, stats, st, pl.status))
+    return rc;
+  if (int rc = pair_tc_finish(fin, emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb,
+                              st))
+    return rc;
+  // A class larger than the lists (8 positives per anchor here) would silently drop triplets.  No host read-back on
+  // this path (a training step must not stall the stream): the results are poisoned with NaN above, and the flag --
+  // the offending positives count, 0 when fine -- is left in `overflow` for the caller to inspect when convenient.
+  if (overflow) EN_CUDA(cudaMemcpyAsync(overflow, pl.status, 4, cudaMemcpyDeviceToDevice, st));
   return EN_OK;
 }
 
@@ -1910,8 +2003,12 @@ int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t
   if (!ws || ws_bytes < en_ws_bytes_contrastive_allpairs(B, d))
     return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_bwd: workspace too small");
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
-  return pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, nullptr, gemb,
-                        ws, ws_bytes, as_stream(stream));
+  PairTcFinish fin;
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, nullptr, gemb,
+                              &fin, ws, ws_bytes, as_stream(stream)))
+    return rc;
+  return pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb,
+                        as_stream(stream));
 }
 
 // Loss AND gradient of the all-pairs contrastive loss from one pass over the distance tiles (csrc/pair_tc.cu).
@@ -1929,8 +2026,11 @@ int en_contrastive_allpairs_fwd_bwd(const float* emb, const int32_t* labels, int
   EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
   void* rest = w.base + w.off;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, gloss, partial,
-                              gemb, rest, ws_bytes - w.off, st))
+  PairTcFinish fin;
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, partial, gemb,
+                              &fin, rest, ws_bytes - w.off, st))
+    return rc;
+  if (int rc = pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb, st))
     return rc;
   return launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, nullptr, B, 1, loss, nullptr, st);
 }

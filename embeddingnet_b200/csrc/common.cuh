@@ -92,6 +92,12 @@ struct PairPartial {
   unsigned long long npos;
 };
 
+// What pair_tc_launch() leaves in its workspace for pair_tc_finish() (csrc/pair_tc.cu)
+struct PairTcFinish {
+  const float* mu;      // [d] column means of the embeddings
+  const float* rowsum;  // [B] row sums of the pair coefficients
+};
+
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -51,13 +51,18 @@ constexpr int G1_STAGE_BYTES = 4 * TILE_BYTES;
 constexpr int ET_STAGES = 2;            // GEMM2 B ring: ET_hi | ET_lo, each [128 gradient columns x 64 rows j] BF16
 constexpr int ET_STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int JB = 64;                  // rows j per GEMM2 k-block (one 128-byte swizzle row of BF16)
-constexpr int EPI_WARPS = 8;
+// Epilogue: 16 warps = 4 per SM sub-partition (TMEM lane quarter = warp id % 4), each owning ONE 32-column chunk of
+// its 32 rows.  ncu r2 (8 warps x 64 columns): 1.7 warp instructions per cycle per SM, i.e. 0.43 per scheduler with
+// two warps each -- the per-element chains (FADD -> FSET -> FADD, MUFU) were latency-, not issue-bound, and the
+// epilogue, which sits between GEMM1 and GEMM2 of a tile, set the tile period.
+constexpr int EPI_Q = 4;                // column chunks (32 wide) per tile row = epilogue warps per lane quarter
+constexpr int EPI_WARPS = 4 * EPI_Q;
 constexpr int CTRL_WARPS = 3;            // warp 0: GEMM1 operand TMA, warp 1: MMA issuer, warp 2: E^T (GEMM2) TMA
 constexpr int NUM_THREADS = 32 * (CTRL_WARPS + EPI_WARPS);
 constexpr int MAXP = 8;                 // positives per anchor handled by this kernel
-constexpr int WARP_SCR = 256 + 256 + 64 * MAXP * 4;  // per warp, for its 64 columns: norms | labels | positives lists
+constexpr int WARP_SCR = 128 + 128 + 32 * MAXP * 4;  // per warp, for its 32 columns: norms | labels | positives lists
 constexpr int SMEM_BYTES = G1_STAGES * G1_STAGE_BYTES + ET_STAGES * ET_STAGE_BYTES + 256 + EPI_WARPS * WARP_SCR +
-                           BM * 2 * 4;
+                           BM * EPI_Q * 4;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 // TMEM (512 columns): S | C_hi | C_lo | G
 constexpr uint32_t TM_S = 0;       // 128 columns (single buffer: the epilogue copies it to registers and releases it)
@@ -76,16 +81,16 @@ struct Bars {
 };
 
 struct Params {
-  const float* emb;
   const int32_t* labels;
   const float* norms;
   const float* pos_d;     // [B][MAXP] (batch-all)
   const int32_t* pos_n;   // [B]
   int32_t* pos_cnt;       // [B][MAXP] out: active negatives per (anchor, positive slot)
-  const float* mu;        // [d] column means of emb
-  float* gemb;            // ZEROED by the caller when n_jparts > 1: items that share rows (J ranges) add into it
-  PairPartial* partial;   // kLoss: [B][n_jparts][2] loss partial sums (+ positive-term counts)
-  const float* gloss;     // optional: upstream gradient, folded into the write
+  float* gemb;            // out: -(C.E) over the centred rows, unscaled by gloss; ZEROED by the caller when n_jparts > 1
+                          // (items that share rows add into it: two addends per element commute, still deterministic)
+  float* rowsum;          // out [B], zeroed by the caller: sum_k C_ik (what the MMAs saw); pair_finish_kernel turns
+                          // the two into the gradient with coalesced accesses
+  PairPartial* partial;   // kLoss: [B][n_jparts][EPI_Q] loss partial sums (+ positive-term counts)
   int64_t B;
   int d, tiles, n_wide, n_jparts, tiles_per_part, kblocks;
   int squared;
@@ -142,7 +147,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint8_t* et = smem + G1_STAGES * G1_STAGE_BYTES;
   Bars* bars = reinterpret_cast<Bars*>(et + ET_STAGES * ET_STAGE_BYTES);
   uint8_t* warp_scr = reinterpret_cast<uint8_t*>(bars) + 256;
-  float* rowsum_x = reinterpret_cast<float*>(warp_scr + EPI_WARPS * WARP_SCR);  // [2][128]
+  float* rowsum_x = reinterpret_cast<float*>(warp_scr + EPI_WARPS * WARP_SCR);  // [EPI_Q][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.tiles * p.n_wide * p.n_jparts;
@@ -291,14 +296,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue warps: loss, C, then the gradient slice
-    const int quarter = warp & 3, half = (warp - CTRL_WARPS) >> 2;  // TMEM lane quarter = warp id % 4
+    const int quarter = warp & 3, cq = (warp - CTRL_WARPS) >> 2;  // TMEM lane quarter = warp id % 4; column chunk
     uint8_t* ws = warp_scr + (warp - CTRL_WARPS) * WARP_SCR;
     float* wf = reinterpret_cast<float*>(ws);
-    int32_t* wi = reinterpret_cast<int32_t*>(ws + 256);
-    float* wpos = reinterpret_cast<float*>(ws + 512);  // [64 columns][MAXP], margin added, -inf padded
+    int32_t* wi = reinterpret_cast<int32_t*>(ws + 128);
+    float* wpos = reinterpret_cast<float*>(ws + 256);  // [32 columns][MAXP], margin added, -inf padded
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t e_it = 0, item_it = 0;
-    const float gl = p.gloss ? p.gloss[0] : 1.f;
     const float cs = p.coef_scale * (p.stats ? static_cast<float>(1.0 / (p.stats[1] + 1e-16)) : 1.f);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
       const Item it = decode_item(p, item);
@@ -324,38 +328,34 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       for (int J = it.j0; J < it.j1; ++J, ++e_it) {
         ptx::mbar_wait(&bars->s_full, e_it & 1);
         ptx::tc_fence_after();
-        // pull this thread's 64 columns of S into registers and hand the accumulator straight back to the MMA warp
-        float sv[2][32];
-        ptx::tmem_ld_32x32(tmem + lane_base + TM_S + (half * 2 + 0) * 32, sv[0]);
-        ptx::tmem_ld_32x32(tmem + lane_base + TM_S + (half * 2 + 1) * 32, sv[1]);
+        // pull this thread's 32 columns of S into registers and hand the accumulator straight back to the MMA warp
+        float w[32];
+        ptx::tmem_ld_32x32(tmem + lane_base + TM_S + cq * 32, w);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->s_empty);
-        // stage this warp's 64 columns' norms / labels / positives lists (one round of global loads per tile)
+        // stage this warp's 32 columns' norms / labels / positives lists (one round of global loads per tile)
         __syncwarp();
-#pragma unroll
-        for (int cc2 = 0; cc2 < 2; ++cc2) {
-          const int64_t cc = static_cast<int64_t>(J) * BN + (half * 2 + cc2) * 32 + lane;
+        {
+          const int64_t cc = static_cast<int64_t>(J) * BN + cq * 32 + lane;
           const bool ok = cc < p.B;
-          wf[cc2 * 32 + lane] = ok ? __ldg(&p.norms[cc]) : 0.f;
-          wi[cc2 * 32 + lane] = ok ? __ldg(&p.labels[cc]) : -2;
+          wf[lane] = ok ? __ldg(&p.norms[cc]) : 0.f;
+          wi[lane] = ok ? __ldg(&p.labels[cc]) : -2;
           if (kMode == 0) {
             const int npk = ok ? p.pos_n[cc] : 0;
 #pragma unroll
             for (int s = 0; s < MAXP; ++s)
-              wpos[(cc2 * 32 + lane) * MAXP + s] = (s < npk) ? p.pos_d[cc * MAXP + s] + p.margin : -INFINITY;
+              wpos[lane * MAXP + s] = (s < npk) ? p.pos_d[cc * MAXP + s] + p.margin : -INFINITY;
           }
         }
         __syncwarp();
-#pragma unroll
-        for (int cc2 = 0; cc2 < 2; ++cc2) {
-          const int c = half * 2 + cc2;
+        {
+          const int c = cq;
           const int64_t col0 = static_cast<int64_t>(J) * BN + c * 32;
-          float (&w)[32] = sv[cc2];
-          const float* wfc = wf + cc2 * 32;
-          const int32_t* wic = wi + cc2 * 32;
-          const float* wposc = wpos + cc2 * 32 * MAXP;
+          const float* wfc = wf;
+          const int32_t* wic = wi;
+          const float* wposc = wpos;
           float chunk_sum = 0.f, chunk_loss = 0.f;
           // interior chunks (no ragged edge, no diagonal) skip the per-element index checks
           const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
@@ -442,11 +442,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         // the C region is free once GEMM2 of the previous tile has retired
         ptx::mbar_wait(&bars->c_empty, (e_it & 1) ^ 1);
         ptx::tc_fence_after();
-#pragma unroll
-        for (int cc2 = 0; cc2 < 2; ++cc2) {
-          const uint32_t* wu = reinterpret_cast<const uint32_t*>(sv[cc2]);
-          // this thread's 32 tile columns (half*2 + cc2)*32 .. +31 = packed columns (half*2 + cc2)*16 .. +15
-          const uint32_t pc0 = (half * 2 + cc2) * 16;
+        {
+          const uint32_t* wu = reinterpret_cast<const uint32_t*>(w);
+          // this thread's 32 tile columns cq*32 .. +31 = packed columns cq*16 .. +15
+          const uint32_t pc0 = cq * 16;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             tmem_st_32x4(tmem + lane_base + TM_CH + pc0 + t * 4, wu + t * 8);
@@ -458,37 +457,57 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->c_full);
       }
-      // ---- loss partial of this (row, J range, column half); only the first column group reports it
+      // ---- loss partial of this (row, J range, column chunk); only the first column group reports it
       if (kLoss && it.wide == 0 && row_ok) {
         unsigned long long np = 0;
         if (kMode == 0) {
 #pragma unroll
           for (int s = 0; s < MAXP; ++s) np += static_cast<unsigned long long>(cnt_s[s]);  // exact integers
         }
-        p.partial[(row * p.n_jparts + it.part) * 2 + half] = PairPartial{loss_sum, np};
+        p.partial[(row * p.n_jparts + it.part) * EPI_Q + cq] = PairPartial{loss_sum, np};
       }
-      // ---- this item's share of the gradient: gl * (rowsum_i * (e_i - mu) - (C.E)_i) over its J range, added into
-      // the zeroed gemb (with two J ranges per row the two additions commute: the result stays deterministic)
-      rowsum_x[half * BM + quarter * 32 + lane] = static_cast<float>(rowsum);
+      // ---- this item's share of the gradient.  grad_i = rowsum_i (e_i - mu) - (C.E)_i: the kernel leaves the two
+      // ingredients -- rowsum_i (first column group only) and -(C.E)_i over its J range, added into the zeroed gemb
+      // with 128-bit reductions (two J ranges per row: the two additions commute, the result stays deterministic) --
+      // and pair_finish_kernel combines them with coalesced row accesses.  Doing it here, one float per lane and row,
+      // made every load / atomic of a warp touch 32 different rows: ncu r2, 44 % of the kernel's stall samples.
+      rowsum_x[cq * BM + quarter * 32 + lane] = static_cast<float>(rowsum);
       ptx::named_bar_sync(1, EPI_WARPS * 32);
-      const float rs = rowsum_x[quarter * 32 + lane] + rowsum_x[BM + quarter * 32 + lane];
+      if (it.wide == 0 && cq == 0 && row_ok) {
+        float rs = 0.f;
+#pragma unroll
+        for (int q = 0; q < EPI_Q; ++q) rs += rowsum_x[q * BM + quarter * 32 + lane];  // fixed order: deterministic
+        atomicAdd(&p.rowsum[row], rs);
+      }
       ptx::mbar_wait(&bars->g_full, item_it & 1);
       ptx::tc_fence_after();
-      for (int c = half * (DW / 64); c < (half + 1) * (DW / 64); ++c) {  // this thread's 128 of the 256 columns
+      const bool vec = (p.d & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gemb) & 15) == 0;
+      for (int c = cq * (DW / 32 / EPI_Q); c < (cq + 1) * (DW / 32 / EPI_Q); ++c) {  // this thread's 64 of the 256 columns
         float v[32];
         ptx::tmem_ld_32x32(tmem + lane_base + TM_G + c * 32, v);
         ptx::tmem_ld_wait();
         if (row_ok) {
           const int col0 = it.wide * DW + c * 32;
-          const float* er = p.emb + row * p.d;
-          float* gr = p.gemb + row * p.d;
+          float* gr = p.gemb + row * p.d + col0;
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.d) {
-              const float g = gl * (rs * (er[col0 + j] - __ldg(&p.mu[col0 + j])) - v[j]);
-              if (p.n_jparts == 1) gr[col0 + j] = g;
-              else atomicAdd(&gr[col0 + j], g);
-            }
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < p.d) {
+                if (p.n_jparts == 1)
+                  *reinterpret_cast<float4*>(gr + j) = make_float4(-v[j], -v[j + 1], -v[j + 2], -v[j + 3]);
+                else
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gr + j), "f"(-v[j]), "f"(-v[j + 1]),
+                               "f"(-v[j + 2]), "f"(-v[j + 3])
+                               : "memory");
+              }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.d) {
+                if (p.n_jparts == 1) gr[j] = -v[j];
+                else atomicAdd(&gr[j], -v[j]);
+              }
+          }
         }
       }
       ptx::tc_fence_before();
@@ -536,6 +555,88 @@ __global__ void transpose_split_bf16_kernel(const float* __restrict__ e, const f
   }
 }
 
+// Closes the step, one warp per row, every access coalesced:
+//   grad_i = scale * ( rowsum_i (e_i - mu) - (C.E)_i  +  sum_{j in P(i)} (cnt_ij + cnt_ji) s(D_ij) (e_i - e_j) )
+// The last sum is batch-all's sparse positive-pair part (G_ij = +#{k : D_ij + m - D_ik > 0}; cnt_ji is looked up in
+// j's own list -- "same label" is symmetric and the lists are complete, the forward rejects overflowing classes);
+// each row has a single writer, no atomics.  scale = gloss (contrastive; the pair coefficients already carry
+// 4 / (B (B-1))) or gloss / #positive triplets (batch-all; the count is only known after the last tile).
+__global__ void pair_finish_kernel(const float* __restrict__ emb, const float* __restrict__ mu,
+                                   const float* __restrict__ rowsum, int64_t B, int d, int cap, int squared,
+                                   const float* __restrict__ pos_d, const int32_t* __restrict__ pos_j,
+                                   const int32_t* __restrict__ pos_n, const int32_t* __restrict__ pos_cnt,
+                                   const double* __restrict__ stats, const float* __restrict__ gloss,
+                                   float* __restrict__ gemb) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= B) return;
+  float scale = gloss ? gloss[0] : 1.f;
+  if (stats) scale = static_cast<float>(static_cast<double>(scale) / (stats[1] + 1e-16));
+  const float rs = rowsum[i];
+  // lane s (and s + 32) prepares the weight of positive s
+  const int n = pos_n ? pos_n[i] : 0;
+  float wgt[2] = {0.f, 0.f};
+  int jj[2] = {0, 0};
+  if (n > 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = lane + 32 * h;
+      if (s < n) {
+        const int64_t j = pos_j[i * cap + s];
+        int cnt = pos_cnt[i * cap + s];
+        const int nj = pos_n[j];
+        for (int t = 0; t < nj; ++t)
+          if (pos_j[j * cap + t] == static_cast<int32_t>(i)) {
+            cnt += pos_cnt[j * cap + t];
+            break;
+          }
+        const float dij = pos_d[i * cap + s];
+        wgt[h] = static_cast<float>(cnt) * (squared ? 2.f : (dij > 0.f ? 1.f / dij : 0.f));
+        jj[h] = static_cast<int>(j);
+      }
+    }
+  }
+  const float* ei = emb + i * d;
+  float* gi = gemb + i * d;
+  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gemb) & 15) == 0 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0;
+  auto ld4 = [&](const float* base, int c) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+      if (c < d) r = *reinterpret_cast<const float4*>(base + c);
+    } else {
+      r.x = c < d ? base[c] : 0.f; r.y = c + 1 < d ? base[c + 1] : 0.f;
+      r.z = c + 2 < d ? base[c + 2] : 0.f; r.w = c + 3 < d ? base[c + 3] : 0.f;
+    }
+    return r;
+  };
+  for (int c0 = 0; c0 < d; c0 += 128) {
+    const int c = c0 + 4 * lane;
+    const float4 x = ld4(ei, c), m = ld4(mu, c), g = ld4(gi, c);
+    float4 acc = make_float4(fmaf(rs, x.x - m.x, g.x), fmaf(rs, x.y - m.y, g.y), fmaf(rs, x.z - m.z, g.z),
+                             fmaf(rs, x.w - m.w, g.w));
+    for (int s = 0; s < n; ++s) {
+      const float w = __shfl_sync(0xffffffffu, wgt[s >> 5], s & 31);
+      const int j = __shfl_sync(0xffffffffu, jj[s >> 5], s & 31);
+      if (w == 0.f) continue;  // warp-uniform
+      const float4 y = ld4(emb + static_cast<int64_t>(j) * d, c);
+      acc.x = fmaf(w, x.x - y.x, acc.x);
+      acc.y = fmaf(w, x.y - y.y, acc.y);
+      acc.z = fmaf(w, x.z - y.z, acc.z);
+      acc.w = fmaf(w, x.w - y.w, acc.w);
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    if (vec) {
+      if (c < d) *reinterpret_cast<float4*>(gi + c) = acc;
+    } else {
+      if (c < d) gi[c] = acc.x;
+      if (c + 1 < d) gi[c + 1] = acc.y;
+      if (c + 2 < d) gi[c + 2] = acc.z;
+      if (c + 3 < d) gi[c + 3] = acc.w;
+    }
+  }
+}
+
 struct Geometry {
   int dpad32, n_wide, rows_t, tiles, n_jparts, tiles_per_part;
   int64_t bpad;
@@ -562,7 +663,7 @@ static Geometry geometry(int64_t B, int d, int sms) {
 // ---------------------------------------------------------------------------------------------- host entry
 size_t pair_tc_ws_bytes(int64_t B, int d) {
   const ptc::Geometry g = ptc::geometry(B, d, 148);
-  return 2 * align_up(static_cast<size_t>(B) * g.dpad32 * 4) + align_up(static_cast<size_t>(B) * 4) +
+  return 2 * align_up(static_cast<size_t>(B) * g.dpad32 * 4) + 2 * align_up(static_cast<size_t>(B) * 4) +
          2 * align_up(static_cast<size_t>(g.rows_t) * g.bpad * 2) + align_up(static_cast<size_t>(d) * 4);
 }
 
@@ -570,7 +671,7 @@ size_t pair_tc_ws_bytes(int64_t B, int d) {
 // through the J-range split, which is capped by the tile count.
 int pair_tc_partials_per_row(int64_t B, int d) {
   const int sms = device_sm_count();
-  return ptc::geometry(B, d, sms > 0 ? sms : 148).n_jparts * 2;
+  return ptc::geometry(B, d, sms > 0 ? sms : 148).n_jparts * ptc::EPI_Q;
 }
 
 // mode 0 = batch-all (pos_* describe lists with capacity 8), mode 1 = all-pairs contrastive.
@@ -578,11 +679,11 @@ int pair_tc_partials_per_row(int64_t B, int d) {
 // coef_scale multiplies every pair coefficient (contrastive: 4 / (B (B-1)), batch-all: 1); stats (optional, device):
 // batch-all coefficients are also divided by stats[1] = #positive triplets -- known when the forward already ran;
 // the fused step passes null and rescales the finished gradient.
-// gemb is fully overwritten (the caller adds the sparse positive-pair terms of batch-all afterwards).
+// gemb receives -(C.E) and `fin` the pointers pair_tc_finish() needs to turn it into the gradient (the caller may
+// reduce the loss partials in between: batch-all's scale 1 / #positive triplets comes out of that reduction).
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
                    float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
-                   const float* gloss, PairPartial* partial, float* gemb, void* ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (int rc = check_sm100()) return rc;
   if (!ws || ws_bytes < pair_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair kernel: workspace too small");
   Workspace w(ws, ws_bytes);
@@ -596,6 +697,7 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
   float* hi = w.take<float>(static_cast<size_t>(B) * g.dpad32);
   float* lo = w.take<float>(static_cast<size_t>(B) * g.dpad32);
   float* norms = w.take<float>(B);
+  float* rowsum = w.take<float>(B);
   uint16_t* et_hi = w.take<uint16_t>(static_cast<size_t>(g.rows_t) * g.bpad);
   uint16_t* et_lo = w.take<uint16_t>(static_cast<size_t>(g.rows_t) * g.bpad);
   float* mu = w.take<float>(d);
@@ -616,13 +718,16 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
       tc::make_plane_tmap_bf16(&teh, et_hi, g.rows_t, g.bpad) || tc::make_plane_tmap_bf16(&tel, et_lo, g.rows_t, g.bpad))
     return fail(EN_ERR_DRIVER, "pair kernel: cuTensorMapEncodeTiled failed");
   ptc::Params p;
-  p.emb = emb; p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt;
-  p.mu = mu; p.gemb = gemb; p.partial = partial; p.gloss = gloss; p.B = B; p.d = d;
+  p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt;
+  p.gemb = gemb; p.rowsum = rowsum; p.partial = partial; p.B = B; p.d = d;
   p.tiles = g.tiles; p.n_wide = g.n_wide; p.n_jparts = g.n_jparts; p.tiles_per_part = g.tiles_per_part;
   p.kblocks = dpad / (g1_bf16 ? tc::BK16 : tc::BK); p.squared = squared; p.margin = margin; p.coef_scale = coef_scale; p.stats = stats;
   const int items = p.tiles * p.n_wide * p.n_jparts;
   const int grid = items < sms ? items : sms;
   if (p.n_jparts > 1) EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * sizeof(float), st));
+  EN_CUDA(cudaMemsetAsync(rowsum, 0, static_cast<size_t>(B) * sizeof(float), st));
+  fin->mu = mu;
+  fin->rowsum = rowsum;
 #define EN_PAIR_LAUNCH(MODE, LOSS, G1B)                                                                              \
   do {                                                                                                              \
     EN_CUDA(cudaFuncSetAttribute(ptc::pair_tc_kernel<MODE, LOSS, G1B>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
@@ -637,6 +742,16 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
   else EN_PAIR_LAUNCH(1, false, true);
 #undef EN_PAIR_LAUNCH
   EN_LAUNCHED("pair_tc_kernel");
+  return EN_OK;
+}
+
+// pos_* may be null (contrastive); stats (device, optional): divide by stats[1]; gloss (device, optional)
+int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, int cap, int squared, const float* pos_d,
+                   const int32_t* pos_j, const int32_t* pos_n, const int32_t* pos_cnt, const double* stats,
+                   const float* gloss, float* gemb, cudaStream_t st) {
+  ptc::pair_finish_kernel<<<static_cast<unsigned>((B * 32 + 127) / 128), 128, 0, st>>>(
+      emb, fin.mu, fin.rowsum, B, d, cap, squared, pos_d, pos_j, pos_n, pos_cnt, stats, gloss, gemb);
+  EN_LAUNCHED("pair_finish_kernel");
   return EN_OK;
 }
 

@@ -257,6 +257,68 @@ def batch_hard_triplet_loss(margin=0.5, squared=False, soft=False):
 
 
 # ------------------------------------------------------------------------------------------------ batch-all
+class _DeferredOverflow:
+    """The fused batch-all step never stalls the stream, so "a class has more positives per anchor than
+    max_positives" cannot raise at once: the kernel poisons loss and gradient with NaN (never silently wrong) and
+    leaves the offending count in a device word, which is copied to pinned host memory behind an event.  The flags of
+    earlier calls are looked at whenever that costs nothing: at the next call (non-blocking ``event.query()``) and,
+    blocking, by ``check()``."""
+
+    SLOTS = 8
+
+    def __init__(self):
+        self._tls = __import__("threading").local()
+
+    def _state(self, device):
+        st = getattr(self._tls, "st", None)
+        if st is None or st["device"] != device:
+            st = {"device": device, "dev": torch.zeros(self.SLOTS, dtype=torch.int32, device=device),
+                  "host": torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory(), "events": [None] * self.SLOTS,
+                  "limits": [0] * self.SLOTS, "next": 0}
+            self._tls.st = st
+        return st
+
+    def slot(self, device, limit):
+        """Device int32 (1,) view for the next call; its previous use, if any, is checked first."""
+        st = self._state(device)
+        self.poll(block=False)
+        k = st["next"]
+        if st["events"][k] is not None:  # ring wrapped around: settle the old use of this slot
+            st["events"][k].synchronize()
+            self._raise_if_set(st, k)
+        st["next"] = (k + 1) % self.SLOTS
+        st["limits"][k] = int(limit)
+        return k, st["dev"][k:k + 1]
+
+    def arm(self, k):
+        st = self._tls.st
+        st["host"][k:k + 1].copy_(st["dev"][k:k + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["events"][k] = ev
+
+    def _raise_if_set(self, st, k):
+        st["events"][k] = None
+        n = int(st["host"][k])
+        if n > 0:
+            raise ValueError("batch_all_triplet_loss: a class has %d positives per anchor but max_positives = %d "
+                             "(that call's loss and gradient were filled with NaN)" % (n, st["limits"][k]))
+
+    def poll(self, block=False):
+        st = getattr(self._tls, "st", None)
+        if st is None:
+            return
+        for k in range(self.SLOTS):
+            ev = st["events"][k]
+            if ev is not None and (block or ev.query()):
+                if block:
+                    ev.synchronize()
+                self._raise_if_set(st, k)
+
+
+_overflow = _DeferredOverflow()
+
+
 class _BatchAll(torch.autograd.Function):
     """When a gradient can be asked for, forward runs the fused pass (en_batch_all_fwd_bwd: distance tiles computed
     once for loss and gradient) and backward only applies the upstream gradient."""
@@ -272,8 +334,11 @@ class _BatchAll(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gemb = torch.empty_like(emb)
             ones = torch.ones(1, dtype=torch.float32, device=dev)
+            k, flag = _overflow.slot(dev, max_pos)
             _lib.call("en_batch_all_fwd_bwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared),
-                      max_pos, ptr(out), ptr(stats), ptr(ones), ptr(gemb), ptr(ws), ws.numel(), stream_ptr())
+                      max_pos, ptr(out), ptr(stats), ptr(ones), ptr(gemb), ptr(flag), ptr(ws), ws.numel(),
+                      stream_ptr())
+            _overflow.arm(k)
             ctx.gemb = gemb
         else:
             _lib.call("en_batch_all_fwd", ptr(emb), ptr(labels), B, d, ctypes.c_float(margin), int(squared), max_pos,
@@ -306,6 +371,7 @@ def batch_all_triplet_loss(margin=0.5, squared=False, max_positives=None, return
         return (loss, frac) if return_fraction else loss
 
     loss_function.last_fraction = None
+    loss_function.check = lambda: _overflow.poll(block=True)  # settles the deferred max_positives checks
     return loss_function
 
 

@@ -154,11 +154,13 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
                      size_t ws_bytes, void* stream);
 /* Loss AND gradient from ONE pass over the distance tiles (what a training step needs; Keras differentiates the loss
  * callable inside the same train step, train.py:160-162): out / stats as en_batch_all_fwd, gemb (B, d) =
- * gloss[0] * d loss / d emb (gloss == NULL means 1).  Classes with more than 8 positives per anchor take the two
- * separate passes internally and need a non-NULL gloss. */
+ * gloss[0] * d loss / d emb (gloss == NULL means 1).  Asynchronous (no host read-back): if a class turns out to have
+ * more positives per anchor than max_positives, out / stats / gemb are filled with NaN and `overflow` (device int32,
+ * optional) receives that count (0 when fine).  Classes with more than 8 positives per anchor take the two separate
+ * passes internally (synchronous check, non-NULL gloss required). */
 int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
-                         int max_positives, float* out, double* stats, const float* gloss, float* gemb, void* ws,
-                         size_t ws_bytes, void* stream);
+                         int max_positives, float* out, double* stats, const float* gloss, float* gemb,
+                         int32_t* overflow, void* ws, size_t ws_bytes, void* stream);
 
 /* All-pairs contrastive loss: losses_and_accuracies.py:4-11 over every ordered pair i != j with
  * y_ij = [label_i == label_j] and d_ij = sqrt(max(|e_i - e_j|^2, 1e-7)) (models.py:225).  loss is 1 float. */
@@ -272,12 +274,21 @@ int en_mine_bank_select(const float* anchors, const int32_t* anchor_labels, cons
  * en_dense_prepare: w is the Keras kernel, (n_in, n_out) row-major; w_hi / w_lo receive its transposed TF32 planes,
  * en_dense_plane_bytes() each (once per set of weights).
  * en_dense_relu_fwd: x (B, n_in) -> out (B, n_out) = relu(x . w + bias), each row scaled by
- * rsqrt(max(sum y^2, 1e-12)) when normalize != 0.  bias may be NULL. */
+ * rsqrt(max(sum y^2, 1e-12)) when normalize != 0.  bias may be NULL.  inv_norm (optional, (B,), normalize only)
+ * receives that row scale for the backward pass (negated for rows below the 1e-12 clamp).
+ * en_dense_relu_bwd: the training direction (the reference trains through these layers, backbones.py:114-119 under
+ * model.fit, train.py:172): gy = dL/d out -> gx (B, n_in), gw (n_in, n_out; the Keras kernel layout), gb (n_out,);
+ * any of the three may be NULL.  w is the fp32 Keras kernel; y / inv_norm are the forward's outputs.  Two tcgen05
+ * 3xTF32 GEMMs (gpre . w^T and x^T . gpre) after a row-wise kernel that undoes the normalisation and the ReLU. */
 size_t en_dense_plane_bytes(int n_in, int n_out);
 int en_dense_prepare(const float* w, int n_in, int n_out, float* w_hi, float* w_lo, void* stream);
 size_t en_ws_bytes_dense(int64_t B, int n_in);
 int en_dense_relu_fwd(const float* x, int64_t B, int n_in, const float* w_hi, const float* w_lo, const float* bias,
-                      int n_out, int normalize, float* out, void* ws, size_t ws_bytes, void* stream);
+                      int n_out, int normalize, float* out, float* inv_norm, void* ws, size_t ws_bytes, void* stream);
+size_t en_ws_bytes_dense_bwd(int64_t B, int n_in, int n_out);
+int en_dense_relu_bwd(const float* x, int64_t B, int n_in, const float* w, int n_out, int normalize, const float* y,
+                      const float* inv_norm, const float* gy, float* gx, float* gw, float* gb, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- synthetic data (bench / tests) */
 /* x[r, c] = u(r, c) in [-1, 1) from a splitmix64 counter hash; optional class structure:

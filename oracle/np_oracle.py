@@ -126,6 +126,26 @@ def dense_relu(x, kernel, bias=None, normalize=False):
     return y.astype(F32)
 
 
+def dense_relu_grad(x, kernel, bias, normalize, upstream):
+    """float64 autograd gradients (gx, gw, gb) of ``dense_relu`` for an upstream gradient on its output
+    (tf.nn.relu passes the gradient where the input is > 0; K.l2_normalize = x * rsqrt(max(sum x^2, 1e-12)))."""
+    import torch
+
+    xt = torch.tensor(np.asarray(x, np.float64), requires_grad=True)
+    wt = torch.tensor(np.asarray(kernel, np.float64), requires_grad=True)
+    bt = torch.tensor(np.asarray(bias, np.float64), requires_grad=True) if bias is not None else None
+    y = xt @ wt
+    if bt is not None:
+        y = y + bt[None, :]
+    y = torch.relu(y)
+    if normalize:
+        ss = (y * y).sum(dim=1, keepdim=True)
+        y = y * torch.rsqrt(torch.clamp(ss, min=1e-12))
+    y.backward(torch.tensor(np.asarray(upstream, np.float64)))
+    return (xt.grad.numpy().astype(F32), wt.grad.numpy().astype(F32),
+            bt.grad.numpy().astype(F32) if bt is not None else None)
+
+
 def l2_normalize_grad(x, upstream):
     x = np.asarray(x, np.float64)
     g = np.asarray(upstream, np.float64)

@@ -404,6 +404,27 @@ def test_batch_all_tensor_core_backward_matches_cuda_core_backward():
             assert_grad_close_up_to_hinge_flips(g, ga, lab, x, 0.5, squared)
 
 
+def test_batch_all_fused_step_reports_overflow_without_stalling():
+    """The fused loss+gradient step is asynchronous: a class with more positives per anchor than its lists hold (8)
+    poisons loss and gradient with NaN at once and raises at the next opportunity (``check()`` / the next call)."""
+    from embeddingnet_b200 import losses_and_accuracies as lac
+
+    x, lab = make_batch(4, 12, 64, True, False)          # 11 positives per anchor
+    fn = lac.batch_all_triplet_loss(0.5, max_positives=7)
+    e = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = fn(lab, e)
+    loss.backward()
+    assert torch.isnan(loss).item() and torch.isnan(e.grad).all().item()
+    with pytest.raises(ValueError, match="11 positives"):
+        fn.check()
+    fn.check()                                             # reported once
+    x2, lab2 = make_batch(8, 8, 64, True, False)
+    e2 = torch.tensor(x2, device="cuda", requires_grad=True)
+    loss2 = fn(lab2, e2)
+    fn.check()
+    assert abs(loss2.item() - float(O.batch_all(lab2, x2, 0.5, False)["loss"])) < 1e-5
+
+
 def test_batch_all_rejects_too_small_max_positives():
     from embeddingnet_b200 import losses_and_accuracies as lac
 

@@ -121,6 +121,68 @@ def test_dense_relu_head(B, n_in, units, normalize):
     assert not np.isnan(got).any()
 
 
+@pytest.mark.parametrize("B,n_in,units", [(128, 512, 256), (300, 100, 130), (5, 33, 7), (1000, 256, 512)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_dense_relu_head_backward(B, n_in, units, normalize):
+    """Training direction of the head (the reference fits through Dense(relu) -> Dense(relu) -> l2_normalize,
+    backbones.py:114-119): gx, gw, gb of en_dense_relu_bwd vs float64 autograd, gradients 1e-4 (norm-wise)."""
+    import torch
+    from embeddingnet_b200.backbones import DenseReLU
+
+    x, _ = synth.make_numpy(B, n_in, seed_noise=11)
+    w, _ = synth.make_numpy(n_in, units, seed_noise=12)
+    w = (w / np.sqrt(n_in)).astype(np.float32)
+    b, _ = synth.make_numpy(1, units, seed_noise=13)
+    b = (0.1 * b[0]).astype(np.float32)
+    g, _ = synth.make_numpy(B, units, seed_noise=14)
+    if B > 4:
+        x[3] = -np.abs(x[3]) * 100.0           # an all-zero output row: the normalisation clamp branch
+    layer = DenseReLU(w, b, normalize=normalize, trainable=True)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    y = layer(xt)
+    y.backward(torch.tensor(g, device="cuda"))
+    gx, gw, gb = O.dense_relu_grad(x, w, b, normalize, g)
+
+    def rel(a, ref):
+        return float(np.linalg.norm(a.astype(np.float64) - ref) / (np.linalg.norm(ref) + 1e-30))
+
+    assert rel(xt.grad.cpu().numpy(), gx) < 1e-4
+    assert rel(layer.kernel.grad.cpu().numpy(), gw) < 1e-4
+    assert rel(layer.bias.grad.cpu().numpy(), gb) < 1e-4
+    want = O.dense_relu(x, w, b, normalize)
+    assert np.abs(y.detach().cpu().numpy() - want).max() <= 1e-5 * (np.abs(want).max() + 1e-30)
+
+
+def test_training_step_through_head_and_batch_hard():
+    """features -> EmbeddingHead (two Dense + l2_normalize) -> batch-hard loss -> backward: one SGD step lowers the
+    loss, and the head's weight gradient matches float64 autograd through the same chain."""
+    import torch
+    from embeddingnet_b200 import losses_and_accuracies as lac
+    from embeddingnet_b200.backbones import EmbeddingHead
+
+    f, lab = synth.make_numpy(256, 96, n_classes=32, rows_per_class=8, noise=0.5, relu=True)
+    k1, _ = synth.make_numpy(96, 64, seed_noise=22)
+    k2, _ = synth.make_numpy(64, 128, seed_noise=23)
+    k1, k2 = (k1 / 10).astype(np.float32), (k2 / 8).astype(np.float32)
+    b1, b2 = np.full(64, 0.05, np.float32), np.full(128, 0.02, np.float32)
+    head = EmbeddingHead(k1, b1, k2, b2, trainable=True)
+    fn = lac.batch_hard_triplet_loss(0.5)
+    ft = torch.tensor(f, device="cuda")
+    loss0 = fn(lab, head(ft))
+    loss0.backward()
+    # float64 reference of d loss / d k2 through the selected pairs (the selection is piecewise constant)
+    emb = O.dense_relu(O.dense_relu(f, k1, b1), k2, b2, normalize=True)
+    _, gemb = O.batch_hard_grad(lab.astype(np.int64), emb, 0.5)
+    _, gw2, _ = O.dense_relu_grad(O.dense_relu(f, k1, b1), k2, b2, True, gemb)
+    got = head.fc2.kernel.grad.cpu().numpy()
+    assert np.linalg.norm(got - gw2) <= 2e-4 * np.linalg.norm(gw2)
+    with torch.no_grad():
+        for p_ in head.parameters():
+            p_ -= 0.5 * p_.grad
+    loss1 = fn(lab, head(ft))
+    assert loss1.item() < loss0.item()
+
+
 def test_embedding_head_feeds_the_bank_path_on_device():
     """EmbeddingHead.predict keeps CUDA tensors on the device and matches the two-layer oracle."""
     import torch
