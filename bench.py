@@ -316,9 +316,17 @@ def main():
 
         # NCCL's own init log (rank / nranks lines) is the evidence that the sharded path really spans N ranks: keep
         # it on, but on stderr, so that stdout stays the one JSON line
+        # (through a per-rank file that is replayed on stderr at the end: pointing NCCL_DEBUG_FILE at /dev/stderr makes
+        # every rank fopen(.., "w") -- i.e. truncate -- whatever file stderr is redirected to)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log = None
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            import tempfile
+
+            nccl_log = os.path.join(tempfile.gettempdir(), "en_bench_nccl_%s_r%d.log" % (
+                os.environ.get("MASTER_PORT", "0"), rank))
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     lib = _lib.load()  # raises if the CUDA extension is missing
@@ -705,14 +713,14 @@ def main():
             on_stream = qn <= clf.stream_max_q
             stream[qn] = {
                 "what": ("%d query(ies) per call, CUDA-core fp32 streaming scan of the bank shard + exact re-rank" if
-                         on_stream else "%d query(ies) per call, tensor-core scan of the shard's BF16 planes (same "
-                         "bytes as the fp32 rows) + exact re-rank") % qn,
+                         on_stream else "%d query(ies) per call, bank-stationary tcgen05 scan of the shard's BF16 planes "
+                         "(same bytes as the fp32 rows; queries resident in shared memory) + exact re-rank") % qn,
                 "queries_per_sec": qn / (call_ms * 1e-3), "ms_per_call": call_ms,
                 "roofline": {"bound": "hbm", "achieved": stream_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": stream_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "traffic": ncu_traffic("knn_stream_q%d_dram_bytes_per_launch" % qn),
                              "kernel": ("knn_stream_kernel<8,4,%d,true>" % qn) if on_stream else
-                             "dist_gemm_kernel<EpTopK<8>> (one query tile)", "kernel_ms": k_ms,
+                             "knn_smallq_kernel<16> (bank = 128-row MMA operand)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": stream_bytes}}
         # C4: offline hard-negative mining over a bank = label-excluded nearest neighbours (1M x 256, 64k anchors)
         mining = None
@@ -802,6 +810,12 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+        if nccl_log and os.path.exists(nccl_log):
+            with open(nccl_log) as f:
+                keep = [ln for ln in f if "nranks" in ln or "Init COMPLETE" in ln or "NCCL version" in ln]
+            sys.stderr.write("".join(keep[:8]))
+            sys.stderr.flush()
+            os.remove(nccl_log)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libembeddingnet_b200.so")
 
 EN_MODE_SEMIHARD, EN_MODE_HARDEST, EN_MODE_RANDOM_HARD = 0, 1, 2
-EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q = 3, 29, 8, 64
+EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q, EN_KNN_SMALLQ_MAX_Q = 3, 29, 8, 64, 64
 EN_PREC_TF32X3, EN_PREC_BF16X3 = 0, 1
 EN_MINE_MAX_SLOTS = 8
 
@@ -65,11 +65,15 @@ SIGNATURES = {
     "en_ws_bytes_knn": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "en_knn_shard_topk": (c_int, [P, c_int64, c_int, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, P, P, P,
                                   c_size_t, P]),
+    "en_ws_bytes_knn_smallq": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "en_knn_smallq_topk": (c_int, [P, c_int64, c_int, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_knn_exact": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "en_knn_exact_topk": (c_int, [P, c_int64, c_int, P, c_int64, c_int64, c_int, P, P, P, P, P, c_size_t, P]),
+    "en_knn_exact_redo": (c_int, [P, c_int64, c_int, P, c_int64, c_int64, c_int, P, P, P, P, P, P, c_size_t, P]),
     "en_ws_bytes_knn_stream": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "en_knn_stream_topk": (c_int, [P, c_int64, c_int, P, P, c_int64, c_int64, c_int, P, P, P, P, c_size_t, P]),
     "en_knn_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
+    "en_knn_merge_packed": (c_int, [P, c_int, c_int64, c_int, P, P, P]),
     "en_knn_finalize_dist": (c_int, [P, c_int64, P, P]),
     "en_knn_vote": (c_int, [P, c_int64, c_int, P, c_int64, P, P]),
     "en_knn_accuracy": (c_int, [P, P, P, c_int64, c_int, P, c_int64, P, P]),

@@ -403,18 +403,22 @@ __global__ void max_norm_kernel(const float* __restrict__ norms, int64_t n, unsi
 // (cert_bound(): common.cuh)
 
 // ---------------------------------------------------------------- merge of per-shard lists
+// part_stride: elements between consecutive parts (Q * k for separate arrays, 2 * Q * k for the packed records of one
+// all-gather); only_flagged (optional): leave the outputs of queries whose flag is 0 untouched.
 __global__ void knn_merge_kernel(const double* __restrict__ d2p, const int64_t* __restrict__ idp, int P, int64_t Q,
-                                 int k, double* __restrict__ d2, int64_t* __restrict__ ids) {
+                                 int k, double* __restrict__ d2, int64_t* __restrict__ ids, int64_t part_stride,
+                                 const int32_t* __restrict__ only_flagged) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= Q) return;
+  if (only_flagged != nullptr && only_flagged[q] == 0) return;
   double last_d = -1.0;
   int64_t last_i = -1;
   for (int r = 0; r < k; ++r) {
     double bd = INFINITY;
     int64_t bi = -1;
     for (int p = 0; p < P; ++p) {
-      const double* dd = d2p + (static_cast<int64_t>(p) * Q + q) * k;
-      const int64_t* ii = idp + (static_cast<int64_t>(p) * Q + q) * k;
+      const double* dd = d2p + static_cast<int64_t>(p) * part_stride + q * k;
+      const int64_t* ii = idp + static_cast<int64_t>(p) * part_stride + q * k;
       for (int c = 0; c < k; ++c) {
         const int64_t i = ii[c];
         if (i < 0) continue;
@@ -579,8 +583,13 @@ __global__ void __launch_bounds__(EX_WARPS * 32)
 knn_exact_kernel(const float* __restrict__ queries, int Q, int d, const float* __restrict__ bank, int64_t n_bank,
                  int64_t id_offset, int k, const int32_t* __restrict__ query_labels,
                  const int32_t* __restrict__ bank_labels, int64_t rows_per_warp, double* __restrict__ pd2,
-                 int64_t* __restrict__ pid) {
+                 int64_t* __restrict__ pid, const int32_t* __restrict__ only_flagged) {
   extern __shared__ __align__(16) uint8_t ex_smem[];
+  if (only_flagged != nullptr) {  // device-side decision: nothing to redo for this group of queries
+    bool any = false;
+    for (int q = blockIdx.y * EX_QT; q < min(blockIdx.y * EX_QT + EX_QT, Q); ++q) any = any || only_flagged[q] != 0;
+    if (!any) return;  // block-uniform
+  }
   float* qs = reinterpret_cast<float*>(ex_smem);                                       // [EX_QT][d]
   double* ld = reinterpret_cast<double*>(ex_smem + ((static_cast<size_t>(EX_QT) * d * 4 + 15) / 16) * 16);
   int32_t* li = reinterpret_cast<int32_t*>(ld + EX_WARPS * EX_QT * EX_KMAX);           // same shape as ld
@@ -738,6 +747,257 @@ int launch_stream_d(const float* queries, int64_t Q, int d, const float* bank, c
   return launch_stream_n<KC, false>(queries, Q, d, bank, nullptr, n_bank, rpw, blocks, lists, st);
 }
 
+// ---------------------------------------------------------------- stage 1c: small query sets on the tensor cores
+// 5 <= Q <= 64 queries per call.  The engine above makes the QUERIES the 128-row operand: with a handful of queries
+// it still issues full 128 x 128 MMAs per bank tile and re-fetches the query tile for every bank tile, and ran at
+// 0.61 of the HBM roofline at one GPU (0.49 at eight; driver SCALE_r01 tails).  Here the roles are swapped:
+//   A (M = 128) = a BANK tile, streamed once from HBM through a TMA ring (both BF16 planes);
+//   B (N = QP)  = the query set padded to 16 / 32 / 64 rows, loaded into shared memory ONCE and kept there;
+//   D (TMEM)    = 128 bank rows x QP queries, main (hi.hi) and cross (lo.hi + hi.lo) accumulators, double buffered.
+// Tensor time per tile shrinks with QP / 128 and the kernel is bounded by the bank stream: algorithmic bytes per
+// call = n_bank * d * 4 (the two BF16 planes are exactly as large as the fp32 rows).  Each epilogue thread owns one
+// bank row of the tile and QP proxies; a warp keeps one sorted list per query in shared memory (inserts are rare
+// once the lists have warmed up: a tile is skipped with one vote), the CTA merges its four warps' lists at the end
+// and the exact re-rank + certificate of stage 2 take over.  Same arithmetic as the engine (split-BF16, separate
+// cross accumulator), hence the same certificate bound.
+namespace sq {
+constexpr int STAGE_BYTES = 2 * tc::TILE_BYTES;  // A_hi | A_lo of one k-block (64 BF16 columns x 128 bank rows)
+constexpr int EPI_WARPS = 4;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int KC = 8;                            // k <= 5 with the usual slack of 3
+constexpr int MAX_STAGES = 6;
+
+struct Bars {
+  uint64_t q_full;
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+inline size_t smem_bytes(int qp, int kblocks, int stages) {
+  return static_cast<size_t>(2) * kblocks * qp * 128 + static_cast<size_t>(stages) * STAGE_BYTES + 256 +
+         static_cast<size_t>(EPI_WARPS) * qp * KC * 8;
+}
+// ring depth that fits beside the resident queries (0 = this shape does not fit: use the engine)
+inline int pick_stages(int qp, int kblocks) {
+  for (int s = MAX_STAGES; s >= 2; --s)
+    if (smem_bytes(qp, kblocks, s) <= 227 * 1024) return s;
+  return 0;
+}
+
+template <int QP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+knn_smallq_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const float* __restrict__ bank_norms, int64_t n_bank, int Q, int kblocks, int stages,
+                  Cand* __restrict__ lists /*[Q][gridDim.x][KC]*/) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  const int q_plane = kblocks * QP * 128;          // bytes of one query plane
+  uint8_t* q_hi = smem;
+  uint8_t* q_lo = smem + q_plane;
+  uint8_t* ring = smem + 2 * q_plane;
+  Bars* bars = reinterpret_cast<Bars*>(ring + stages * STAGE_BYTES);
+  float* l_t = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [warp][QP][KC]
+  int32_t* l_i = reinterpret_cast<int32_t*>(l_t + EPI_WARPS * QP * KC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_total = static_cast<int>((n_bank + tc::BM - 1) / tc::BM);
+  const int t0 = static_cast<int>(static_cast<int64_t>(tiles_total) * blockIdx.x / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<int64_t>(tiles_total) * (blockIdx.x + 1) / gridDim.x);
+  constexpr int ACC = 2 * QP;                      // main | cross
+  constexpr uint32_t TMEM_COLS = 2 * ACC <= 32 ? 32 : (2 * ACC <= 64 ? 64 : (2 * ACC <= 128 ? 128 : 256));
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q_hi);
+    ptx::prefetch_tmap(&tm_q_lo);
+    ptx::prefetch_tmap(&tm_b_hi);
+    ptx::prefetch_tmap(&tm_b_lo);
+    ptx::mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(&bars->full[s], 1); ptx::mbar_init(&bars->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&bars->tmem_full[a], 1); ptx::mbar_init(&bars->tmem_empty[a], EPI_WARPS); }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  for (int i = threadIdx.x; i < EPI_WARPS * QP * KC; i += blockDim.x) {
+    l_t[i] = kInf;
+    l_i[i] = -1;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: queries once, then the bank stream
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->q_full, 2 * q_plane);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::tma_load_2d(&tm_q_hi, &bars->q_full, q_hi + kb * QP * 128, kb * tc::BK16, 0);
+        ptx::tma_load_2d(&tm_q_lo, &bars->q_full, q_lo + kb * QP * 128, kb * tc::BK16, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* st = ring + stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+          ptx::tma_load_2d(&tm_b_hi, &bars->full[stage], st, kb * tc::BK16, t * tc::BM);
+          ptx::tma_load_2d(&tm_b_lo, &bars->full[stage], st + tc::TILE_BYTES, kb * tc::BK16, t * tc::BM);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(tc::BM, QP);
+      ptx::mbar_wait(&bars->q_full, 0);
+      ptx::tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0, acc_it = 0;
+      for (int t = t0; t < t1; ++t, ++acc_it) {
+        const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+        ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tm_d = tmem_base + acc * ACC, tm_x = tm_d + QP;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t st = ptx::smem_u32(ring + stage * STAGE_BYTES);
+          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st), a_lo = ptx::make_kmajor_sw128_desc(st + tc::TILE_BYTES);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(ptx::smem_u32(q_hi + kb * QP * 128));
+          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(ptx::smem_u32(q_lo + kb * QP * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(k * 2);  // 16 BF16 = 32 bytes along the swizzle row
+            ptx::mma_bf16_ss(tm_x, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+            ptx::mma_bf16_ss(tm_x, a_hi + koff, b_lo + koff, idesc, 1);
+            ptx::mma_bf16_ss(tm_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+          }
+          ptx::mma_commit(&bars->empty[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&bars->tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: one bank row per thread, QP proxies
+    const int ew = warp - 2;          // list owner index 0..3
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may read
+    float* my_t = l_t + ew * QP * KC;
+    int32_t* my_i = l_i + ew * QP * KC;
+    uint32_t acc_it = 0;
+    for (int t = t0; t < t1; ++t, ++acc_it) {
+      const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+      const int64_t row = static_cast<int64_t>(t) * tc::BM + quarter * 32 + lane;
+      const float nb = row < n_bank ? __ldg(&bank_norms[row]) : kInf;   // rows past the end never qualify
+      ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC;
+      constexpr int CH = QP < 32 ? QP : 32;       // query columns per TMEM load
+#pragma unroll
+      for (int c0 = 0; c0 < QP; c0 += CH) {
+        float dot[CH], cross[CH];
+        if (CH == 16) {
+          ptx::tmem_ld_32x16(taddr + c0, reinterpret_cast<float (&)[16]>(dot));
+          ptx::tmem_ld_32x16(taddr + QP + c0, reinterpret_cast<float (&)[16]>(cross));
+        } else {
+          ptx::tmem_ld_32x32(taddr + c0, reinterpret_cast<float (&)[32]>(dot));
+          ptx::tmem_ld_32x32(taddr + QP + c0, reinterpret_cast<float (&)[32]>(cross));
+        }
+        ptx::tmem_ld_wait();
+        unsigned mask = 0;                        // queries (of this chunk) for which this row beats the list's worst
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          dot[j] = fmaf(-2.f, dot[j] + cross[j], nb);
+          mask |= (dot[j] < my_t[(c0 + j) * KC + KC - 1] ? 1u : 0u) << j;
+        }
+        unsigned any = __reduce_or_sync(0xffffffffu, mask);
+        // rare once the lists are warm: per query with a hit, the hitting lanes in ascending row order
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (any & (1u << j)) {                  // warp-uniform
+            unsigned m = __ballot_sync(0xffffffffu, (mask >> j) & 1u);
+            while (m) {
+              const int src = __ffs(m) - 1;
+              m &= m - 1;
+              const float tv = __shfl_sync(0xffffffffu, dot[j], src);
+              if (lane == 0) {
+                float* lt = my_t + (c0 + j) * KC;
+                int32_t* li = my_i + (c0 + j) * KC;
+                if (tv < lt[KC - 1]) {            // an earlier insert of this tile may have raised the bar
+                  int pos = KC - 1;
+                  while (pos > 0 && tv < lt[pos - 1]) {  // strict: equal proxies keep the earlier (lower) row first
+                    lt[pos] = lt[pos - 1];
+                    li[pos] = li[pos - 1];
+                    --pos;
+                  }
+                  lt[pos] = tv;
+                  li[pos] = static_cast<int32_t>(static_cast<int64_t>(t) * tc::BM + quarter * 32 + src);
+                }
+              }
+            }
+            __syncwarp();                          // the list (shared memory) is read again by all lanes
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
+    }
+    // ---- merge the four warps' lists per query and publish (t, idx) in ascending order
+    ptx::named_bar_sync(1, EPI_WARPS * 32);
+    const int tid = threadIdx.x - 64;
+    for (int q = tid; q < Q; q += EPI_WARPS * 32) {
+      int head[EPI_WARPS] = {0, 0, 0, 0};
+      Cand* out = lists + (static_cast<int64_t>(q) * gridDim.x + blockIdx.x) * KC;
+      for (int e = 0; e < KC; ++e) {
+        float bt = kInf;
+        int32_t bi = 0x7fffffff;
+        int bw = -1;
+#pragma unroll
+        for (int w = 0; w < EPI_WARPS; ++w) {
+          if (head[w] < KC) {
+            const float tv = l_t[(w * QP + q) * KC + head[w]];
+            const int32_t iv = l_i[(w * QP + q) * KC + head[w]];
+            if (iv >= 0 && (tv < bt || (tv == bt && iv < bi))) { bt = tv; bi = iv; bw = w; }
+          }
+        }
+        if (bw >= 0) {
+          ++head[bw];
+          out[e] = Cand{bt, bi};
+        } else {
+          out[e] = Cand{kInf, -1};
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+inline int pad_q(int64_t Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : 64); }
+
+template <int QP>
+int launch(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& bh, const CUtensorMap& bl,
+           const float* norms, int64_t n_bank, int Q, int kblocks, int stages, int grid, Cand* lists, cudaStream_t st) {
+  const size_t smem = smem_bytes(QP, kblocks, stages);
+  EN_CUDA(cudaFuncSetAttribute(knn_smallq_kernel<QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  prof_begin(st);
+  knn_smallq_kernel<QP><<<grid, NUM_THREADS, smem, st>>>(qh, ql, bh, bl, norms, n_bank, Q, kblocks, stages, lists);
+  prof_end(st);
+  EN_LAUNCHED("knn_smallq_kernel");
+  return EN_OK;
+}
+}  // namespace sq
+
 }  // namespace
 }  // namespace en
 
@@ -880,9 +1140,10 @@ size_t en_ws_bytes_knn_exact(int64_t Q, int64_t n_bank, int d, int k) {
   return 2 * align_up(static_cast<size_t>(blocks) * Q * k * 8);
 }
 
-int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
-                      int k, const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids,
-                      void* ws, size_t ws_bytes, void* stream) {
+static int knn_exact_impl(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                          int k, const int32_t* query_labels, const int32_t* bank_labels, const int32_t* only_flagged,
+                          double* d2, int64_t* ids, void* ws, size_t ws_bytes, void* stream, const char* who) {
+  (void)who;
   EN_REQUIRE(queries && bank && d2 && ids && Q > 0 && n_bank > 0 && d > 0, "en_knn_exact_topk: bad arguments");
   EN_REQUIRE(Q <= EN_KNN_EXACT_MAX_Q, "en_knn_exact_topk: at most %d queries per call (got %lld)",
              EN_KNN_EXACT_MAX_Q, (long long)Q);
@@ -906,18 +1167,105 @@ int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank,
   const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>((Q + EX_QT - 1) / EX_QT));
   const int32_t* ql = bank_labels ? query_labels : nullptr;
   knn_exact_kernel<<<grid, EX_WARPS * 32, smem, st>>>(queries, static_cast<int>(Q), d, bank, n_bank, id_offset, k, ql,
-                                                      bank_labels, rpw, pd2, pid);
+                                                      bank_labels, rpw, pd2, pid, only_flagged);
   EN_LAUNCHED("knn_exact_kernel");
-  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, st>>>(pd2, pid, blocks, Q, k, d2, ids);
+  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, st>>>(pd2, pid, blocks, Q, k, d2, ids, Q * k,
+                                                                           only_flagged);
   EN_LAUNCHED("knn_merge_kernel");
   return EN_OK;
+}
+
+int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                      int k, const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids,
+                      void* ws, size_t ws_bytes, void* stream) {
+  return knn_exact_impl(queries, Q, d, bank, n_bank, id_offset, k, query_labels, bank_labels, nullptr, d2, ids, ws,
+                        ws_bytes, stream, "en_knn_exact_topk");
+}
+
+// The same brute force, decided on the device: only the queries whose flag (the `uncertified` output of a scan) is
+// non-zero are recomputed and overwritten in d2 / ids; with no flag set the two launches return at once.  Lets a
+// small-batch predict call finish without reading the certificate back to the host.
+int en_knn_exact_redo(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                      int k, const int32_t* query_labels, const int32_t* bank_labels, const int32_t* flags, double* d2,
+                      int64_t* ids, void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(flags != nullptr, "en_knn_exact_redo: flags is null");
+  return knn_exact_impl(queries, Q, d, bank, n_bank, id_offset, k, query_labels, bank_labels, flags, d2, ids, ws,
+                        ws_bytes, stream, "en_knn_exact_redo");
+}
+
+size_t en_ws_bytes_knn_smallq(int64_t Q, int64_t n_bank, int d, int k) {
+  if (Q <= 0 || Q > EN_KNN_SMALLQ_MAX_Q || n_bank <= 0 || d <= 0 || k <= 0 || k + EN_KNN_SLACK > sq::KC) return 0;
+  const int dpad = en_bank_dpad(d, EN_PREC_BF16X3);
+  if (sq::pick_stages(sq::pad_q(Q), dpad / tc::BK16) == 0) return 0;  // the resident query tile does not fit
+  const size_t qp = static_cast<size_t>(sq::pad_q(Q));
+  return 2 * align_up(qp * dpad * 2) + align_up(qp * 4) + align_up(4) +
+         align_up(static_cast<size_t>(Q) * 160 * sq::KC * sizeof(Cand));  // sized for the largest SM count
+}
+
+// 5 <= Q <= 64 queries against the BF16 planes of the bank (en_bank_prepare with EN_PREC_BF16X3): bank-stationary
+// tensor-core scan bounded by the bank stream, then the exact re-rank / certificate of en_knn_shard_topk.
+int en_knn_smallq_topk(const float* queries, int64_t Q, int d, const float* bank, const void* bank_hi,
+                       const void* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                       double* d2, int64_t* ids, int32_t* uncertified, void* ws, size_t ws_bytes, void* stream) {
+  EN_REQUIRE(queries && bank && bank_hi && bank_lo && bank_norms && d2 && ids && Q > 0 && n_bank > 0 && d > 0,
+             "en_knn_smallq_topk: bad arguments");
+  EN_REQUIRE(Q <= EN_KNN_SMALLQ_MAX_Q, "en_knn_smallq_topk: at most %d queries per call (got %lld)",
+             EN_KNN_SMALLQ_MAX_Q, (long long)Q);
+  EN_REQUIRE(k > 0 && k + EN_KNN_SLACK <= sq::KC, "en_knn_smallq_topk: k must be in [1, %d]", sq::KC - EN_KNN_SLACK);
+  EN_REQUIRE(n_bank < (int64_t(1) << 31), "en_knn_smallq_topk: shard too large");
+  if (int rc = check_sm100()) return rc;
+  const size_t need = en_ws_bytes_knn_smallq(Q, n_bank, d, k);
+  EN_REQUIRE(need != 0, "en_knn_smallq_topk: d = %d does not fit the resident query tile (use en_knn_shard_topk)", d);
+  if (!ws || ws_bytes < need) return fail(EN_ERR_WORKSPACE, "en_knn_smallq_topk: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int sms = device_sm_count();
+  const int dpad = en_bank_dpad(d, EN_PREC_BF16X3);
+  const int kblocks = dpad / tc::BK16;
+  const int qp = sq::pad_q(Q);
+  const int stages = sq::pick_stages(qp, kblocks);
+  Workspace w(ws, ws_bytes);
+  uint16_t* qhi = w.take<uint16_t>(static_cast<size_t>(qp) * dpad);
+  uint16_t* qlo = w.take<uint16_t>(static_cast<size_t>(qp) * dpad);
+  float* qn = w.take<float>(qp);
+  unsigned* bmax2 = w.take<unsigned>(1);
+  const int tiles_total = static_cast<int>((n_bank + tc::BM - 1) / tc::BM);
+  const int grid = tiles_total < sms ? tiles_total : sms;
+  Cand* lists = w.take<Cand>(static_cast<size_t>(Q) * grid * sq::KC);
+  if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_knn_smallq_topk: workspace too small or misaligned");
+  EN_CUDA(tc::launch_split_bf16(queries, Q, d, d, dpad, qhi, qlo, qn, st));
+  ++launch_counter();
+  CUtensorMap tqh, tql, tbh, tbl;
+  if (tc::make_plane_tmap_bf16(&tqh, qhi, Q, dpad, qp) || tc::make_plane_tmap_bf16(&tql, qlo, Q, dpad, qp) ||
+      tc::make_plane_tmap_bf16(&tbh, bank_hi, n_bank, dpad) || tc::make_plane_tmap_bf16(&tbl, bank_lo, n_bank, dpad))
+    return fail(EN_ERR_DRIVER, "en_knn_smallq_topk: cuTensorMapEncodeTiled failed");
+  int rc;
+  if (qp == 16) rc = sq::launch<16>(tqh, tql, tbh, tbl, bank_norms, n_bank, static_cast<int>(Q), kblocks, stages, grid, lists, st);
+  else if (qp == 32) rc = sq::launch<32>(tqh, tql, tbh, tbl, bank_norms, n_bank, static_cast<int>(Q), kblocks, stages, grid, lists, st);
+  else rc = sq::launch<64>(tqh, tql, tbh, tbl, bank_norms, n_bank, static_cast<int>(Q), kblocks, stages, grid, lists, st);
+  if (rc) return rc;
+  CertParams cert{0, cert_bound(EN_PREC_BF16X3, dpad), bmax2, uncertified};
+  if (uncertified != nullptr)
+    if (int rc2 = launch_max_norm(bank_norms, n_bank, bmax2, st)) return rc2;
+  return dispatch_rerank(sq::KC, queries, Q, d, bank, id_offset, lists, grid, k, d2, ids, cert, st);
 }
 
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
                  int64_t* ids, void* stream) {
   EN_REQUIRE(d2_parts && id_parts && d2 && ids && n_parts > 0 && Q > 0 && k > 0, "en_knn_merge: bad arguments");
-  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(d2_parts, id_parts, n_parts,
-                                                                                          Q, k, d2, ids);
+  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(
+      d2_parts, id_parts, n_parts, Q, k, d2, ids, Q * k, nullptr);
+  EN_LAUNCHED("knn_merge_kernel");
+  return EN_OK;
+}
+
+// The same merge over the packed records of ONE all-gather: parts is (n_parts, 2, Q, k) 8-byte words, per part the
+// (Q, k) float64 squared distances followed by the (Q, k) int64 ids.
+int en_knn_merge_packed(const void* parts, int n_parts, int64_t Q, int k, double* d2, int64_t* ids, void* stream) {
+  EN_REQUIRE(parts && d2 && ids && n_parts > 0 && Q > 0 && k > 0, "en_knn_merge_packed: bad arguments");
+  const double* dp = static_cast<const double*>(parts);
+  const int64_t* ip = static_cast<const int64_t*>(parts) + Q * k;
+  knn_merge_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, as_stream(stream)>>>(dp, ip, n_parts, Q, k, d2,
+                                                                                          ids, 2 * Q * k, nullptr);
   EN_LAUNCHED("knn_merge_kernel");
   return EN_OK;
 }

@@ -95,9 +95,11 @@ def mine_batch_triplets(all_embeddings, labels, margin=0.5, mode="semihard", exa
     else:
         counts = scan_h[1] if mode == "random_hard" else scan_h[2]          # dg:192-199
         rank = np.full(n_pairs, -1, dtype=np.int32)
-        for p in range(n_pairs):                                            # reference pair order => same RNG stream
-            if counts[p] > 0:
-                rank[p] = np.random.randint(0, counts[p])
+        has = counts > 0
+        if has.any():
+            # one vectorised draw in the reference's pair order: same bit stream as the per-pair
+            # np.random.randint(len(candidates)) calls (pinned by tests/test_host_logic_cpu.py)
+            rank[has] = np.random.randint(0, counts[has].astype(np.int64))
         rank_d = torch.from_numpy(rank).to(dev)
         sel = torch.empty(n_pairs, dtype=torch.int32, device=dev)
         _lib.call("en_mine_batch_select", ptr(D), ptr(lab_d), n, ptr(pairs_d), n_pairs, ctypes.c_float(margin),

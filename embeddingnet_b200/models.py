@@ -38,15 +38,17 @@ def draw_candidate_ranks(shard_counts, n_slots, my_rank):
     world, A, slots = counts.shape
     total = counts.sum(axis=0)
     local = np.full((A, slots), -1, dtype=np.int32)
-    ii, ss = np.nonzero(total[:, :n_slots] > 0)
-    for i, s in zip(ii.tolist(), ss.tolist()):
-        r = int(np.random.randint(0, int(total[i, s])))
-        for q in range(world):
-            if r < counts[q, i, s]:
-                if q == my_rank:
-                    local[i, s] = r
-                break
-            r -= int(counts[q, i, s])
+    ii, ss = np.nonzero(total[:, :n_slots] > 0)          # row-major = the reference's (anchor, slot) order
+    if ii.size == 0:
+        return local
+    # ONE vectorised call: RandomState.randint with an array of upper bounds draws element by element from the same
+    # bit stream as the per-pair scalar calls (pinned by tests/test_host_logic_cpu.py), without a Python loop per pair
+    r = np.random.randint(0, total[ii, ss])
+    cum = np.cumsum(counts[:, ii, ss], axis=0)           # (world, pairs): candidates in shards 0..q
+    owner = (r[None, :] >= cum).sum(axis=0)              # first shard whose prefix exceeds the draw
+    before = np.where(owner > 0, cum[np.maximum(owner - 1, 0), np.arange(ii.size)], 0)
+    mine = owner == my_rank
+    local[ii[mine], ss[mine]] = (r - before)[mine].astype(np.int32)
     return local
 
 
@@ -74,10 +76,23 @@ class BankKNNClassifier:
         self.device = device
         self.precision = precision
         self.certify = bool(certify)
-        self.last_uncertified = 0
+        self._last_flags = None
+        self._last_uncertified = 0
         # queries per call up to which the CUDA-core streaming scan is used instead of the tensor-core scan
-        self.stream_max_q = 4  # measured on B200 (tools/time_knn_smallq.py): Q >= 5 is faster on the tensor path
+        # measured on B200 (tools/time_knn_smallq.py, 4M x 512 bank, ms per pass): Q = 1, 2: stream 1.42 / 1.32, small-Q
+        # tensor scan 1.38; Q = 4: 1.98 vs 1.37; Q = 32: 1.53; Q = 64: 2.77 (engine: 2.2)
+        self.stream_max_q = 2
+        self.smallq_max_q = 32
         self._fitted = False
+
+    @property
+    def last_uncertified(self):
+        """Queries of the last search whose exactness certificate failed (they were redone by float64 brute force).
+        Small batches decide the redo on the device, so the count is only read back when someone asks for it."""
+        if self._last_flags is not None:
+            self._last_uncertified = int(self._last_flags.sum().item())
+            self._last_flags = None
+        return self._last_uncertified
 
     # -- sharding helpers
     def _world(self):
@@ -154,19 +169,35 @@ class BankKNNClassifier:
             raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d, "
                              "n_samples = %d" % (k, self._n_total, Q))
         n = self._bank.shape[0]
-        d2 = torch.full((Q, k), float("inf"), dtype=torch.float64, device=dev)
-        ids = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
+        # one buffer, two halves: the sharded path all-gathers (d2, ids) as ONE packed record per rank
+        rec = torch.empty((2, Q, k), dtype=torch.int64, device=dev)
+        d2 = rec[0].view(torch.float64)
+        ids = rec[1]
+        d2.fill_(float("inf"))
+        ids.fill_(-1)
+        self._last_flags = None
+        self._last_uncertified = 0
         if n > 0 and Q > 0:
             ql = bl = None
             if exclude_labels is not None:
                 ql = exclude_labels.to(dev, torch.int32).contiguous()
                 bl = self._labels[self._offset:self._offset + n]
             flags = torch.empty(Q, dtype=torch.int32, device=dev) if self.certify else None
+            smallq_ws = 0
+            if (ql is None and self.stream_max_q < Q <= min(self.smallq_max_q, _lib.EN_KNN_SMALLQ_MAX_Q) and
+                    self._prec == _lib.EN_PREC_BF16X3):
+                smallq_ws = lib.en_ws_bytes_knn_smallq(Q, n, d, k)   # 0: k or d outside what that kernel holds
             if Q <= min(self.stream_max_q, _lib.EN_KNN_STREAM_MAX_Q) and ql is None:
                 # the reference's own call pattern: one image per predict() -> HBM-bound streaming scan
                 ws = workspace(lib.en_ws_bytes_knn_stream(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_stream_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._norms), n, self._offset, k,
                           ptr(d2), ptr(ids), ptr(flags), ptr(ws), ws.numel(), stream_ptr())
+            elif smallq_ws:
+                # a handful of queries: bank-stationary tensor-core scan, bounded by the bank stream
+                ws = workspace(smallq_ws, dev, "knn")
+                _lib.call("en_knn_smallq_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._hi), ptr(self._lo),
+                          ptr(self._norms), n, self._offset, k, ptr(d2), ptr(ids), ptr(flags), ptr(ws), ws.numel(),
+                          stream_ptr())
             else:
                 ws = workspace(lib.en_ws_bytes_knn(Q, n, d, k), dev, "knn")
                 _lib.call("en_knn_shard_topk", ptr(q), Q, d, ptr(self._bank), ptr(self._hi), ptr(self._lo),
@@ -178,23 +209,30 @@ class BankKNNClassifier:
         if world > 1:
             import torch.distributed as dist
 
-            d2_all = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
-            id_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(d2_all, d2, group=self.process_group)   # NCCL over NVLink
-            dist.all_gather_into_tensor(id_all, ids, group=self.process_group)
-            d2m = torch.empty_like(d2)
-            idm = torch.empty_like(ids)
-            _lib.call("en_knn_merge", ptr(d2_all), ptr(id_all), world, Q, k, ptr(d2m), ptr(idm), stream_ptr())
+            rec_all = torch.empty((world, 2, Q, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(rec_all, rec, group=self.process_group)   # ONE NCCL all-gather over NVLink
+            d2m = torch.empty((Q, k), dtype=torch.float64, device=dev)
+            idm = torch.empty((Q, k), dtype=torch.int64, device=dev)
+            _lib.call("en_knn_merge_packed", ptr(rec_all), world, Q, k, ptr(d2m), ptr(idm), stream_ptr())
             d2, ids = d2m, idm
         return d2, ids
 
     def _redo_uncertified(self, q, k, ql, bl, flags, d2, ids):
         """Float64 brute force for the queries whose certificate failed (near-ties at the candidate cut-off)."""
-        self.last_uncertified = int(flags.sum().item())     # the one host read of the certified path
-        if self.last_uncertified == 0:
-            return
         lib = _lib.load()
         n, d = self._bank.shape
+        Q = q.shape[0]
+        if Q <= _lib.EN_KNN_EXACT_MAX_Q:
+            # small batches (the reference's per-image predict): the redo is decided on the DEVICE -- flagged queries
+            # are recomputed in place, no flag means two launches that return at once; no host read-back
+            ws = workspace(lib.en_ws_bytes_knn_exact(Q, n, d, k), q.device, "knn_exact")
+            _lib.call("en_knn_exact_redo", ptr(q), Q, d, ptr(self._bank), n, self._offset, k, ptr(ql), ptr(bl),
+                      ptr(flags), ptr(d2), ptr(ids), ptr(ws), ws.numel(), stream_ptr())
+            self._last_flags = flags
+            return
+        self._last_uncertified = int(flags.sum().item())     # the one host read of the certified path
+        if self._last_uncertified == 0:
+            return
         todo = flags.nonzero().reshape(-1)
         step = _lib.EN_KNN_EXACT_MAX_Q
         for s in range(0, todo.numel(), step):

@@ -208,6 +208,18 @@ int en_knn_shard_topk(const float* queries, int64_t Q, int d, const float* bank,
                       const void* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
                       int precision, const int32_t* query_labels, const int32_t* bank_labels, double* d2,
                       int64_t* ids, int32_t* uncertified, void* ws, size_t ws_bytes, void* stream);
+/* Small query sets (5 <= Q <= EN_KNN_SMALLQ_MAX_Q; between the one-image-per-call pattern of models.py:122,135 and
+ * the batched accuracy loop of models.py:144-161) on the tensor cores with the BANK as the 128-row operand and the
+ * queries resident in shared memory: the kernel is bounded by the bank stream (n_bank * d * 4 bytes of BF16 planes
+ * per call), not by 128-row MMAs on a mostly empty query tile.  Needs the EN_PREC_BF16X3 planes of en_bank_prepare
+ * and k <= 5.  Same outputs, exact re-rank and certificate as en_knn_shard_topk.  en_ws_bytes_knn_smallq returns 0
+ * when d is too large for the resident query tile (use en_knn_shard_topk then). */
+#define EN_KNN_SMALLQ_MAX_Q 64
+size_t en_ws_bytes_knn_smallq(int64_t Q, int64_t n_bank, int d, int k);
+int en_knn_smallq_topk(const float* queries, int64_t Q, int d, const float* bank, const void* bank_hi,
+                       const void* bank_lo, const float* bank_norms, int64_t n_bank, int64_t id_offset, int k,
+                       double* d2, int64_t* ids, int32_t* uncertified, void* ws, size_t ws_bytes, void* stream);
+
 /* Float64 brute force over the shard (sum (q-b)^2 for every admissible row, ordered by (d2, id)): the reference
  * semantics with no filter in front.  For the queries en_knn_shard_topk / en_knn_stream_topk flag as uncertified;
  * Q <= EN_KNN_EXACT_MAX_Q per call.  Same outputs. */
@@ -216,6 +228,12 @@ size_t en_ws_bytes_knn_exact(int64_t Q, int64_t n_bank, int d, int k);
 int en_knn_exact_topk(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
                       int k, const int32_t* query_labels, const int32_t* bank_labels, double* d2, int64_t* ids,
                       void* ws, size_t ws_bytes, void* stream);
+/* The same brute force decided on the DEVICE: only queries whose flag (the `uncertified` output of a scan) is non-zero
+ * are recomputed and overwritten in d2 / ids; with no flag set the launches return at once.  A one-image predict call
+ * (models.py:122,135) then never reads the certificate back to the host. */
+int en_knn_exact_redo(const float* queries, int64_t Q, int d, const float* bank, int64_t n_bank, int64_t id_offset,
+                      int k, const int32_t* query_labels, const int32_t* bank_labels, const int32_t* flags, double* d2,
+                      int64_t* ids, void* ws, size_t ws_bytes, void* stream);
 /* Small-batch variant for the reference's actual call pattern (one query per predict(), models.py:122,135):
  * a CUDA-core fp32 streaming scan bounded by HBM bandwidth; Q <= EN_KNN_STREAM_MAX_Q.  Same outputs.
  * bank_norms (n_bank squared row norms from en_bank_prepare) may be NULL: the scan then evaluates
@@ -228,6 +246,10 @@ int en_knn_stream_topk(const float* queries, int64_t Q, int d, const float* bank
 /* Merge P per-shard lists (P, Q, k) (as gathered by an NCCL all-gather) into the global top-k by (d2, id). */
 int en_knn_merge(const double* d2_parts, const int64_t* id_parts, int n_parts, int64_t Q, int k, double* d2,
                  int64_t* ids, void* stream);
+/* Merge over the packed records of ONE all-gather: parts is (n_parts, 2, Q, k) 8-byte words -- per shard the (Q, k)
+ * float64 squared distances followed by the (Q, k) int64 ids, i.e. what a rank holds when d2 and ids are the two halves
+ * of one buffer. */
+int en_knn_merge_packed(const void* parts, int n_parts, int64_t Q, int k, double* d2, int64_t* ids, void* stream);
 /* distances (Q, k) float32 = sqrt(d2). */
 int en_knn_finalize_dist(const double* d2, int64_t n, float* dist, void* stream);
 /* Majority vote of KNeighborsClassifier.predict (models.py:136): labels of the k neighbours are looked up by

@@ -58,6 +58,35 @@ def test_knn_vs_oracle(N, d, Q, k, precision):
         assert np.all(idx[:, kk:] == -1)
 
 
+@pytest.mark.parametrize("N,d,Q,k", [(777, 100, 5, 5), (20000, 512, 8, 5), (20000, 512, 16, 5), (5000, 64, 17, 1),
+                                     (20000, 256, 33, 5), (40000, 512, 64, 5), (300, 32, 64, 3), (129, 512, 40, 5)])
+def test_knn_small_query_sets_take_the_bank_stationary_scan(N, d, Q, k):
+    """5 <= Q <= 64 (between models.py:122's one image per call and the batched accuracy loop): the bank-stationary
+    tcgen05 scan (en_knn_smallq_topk) -- ids bit-exact vs the float64 oracle, ties to the lowest id, ragged bank
+    tiles, and the same answer as the engine path."""
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    bank, labels = synth.make_numpy(N, d, n_classes=max(2, N // 20), noise=0.5, relu=True)
+    bank = unit_rows(bank)
+    bank[N // 2] = bank[3]                      # exact duplicates: equal distances, the lower id must come first
+    bank[N - 1] = bank[3]
+    q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=max(2, N // 20), noise=0.6, relu=True)
+    q = unit_rows(q)
+    q[0] = bank[3]
+    clf = BankKNNClassifier(n_neighbors=k).fit(bank, labels)
+    clf.smallq_max_q = 64                       # also exercise the 64-wide instantiation (default cut-over: 32)
+    assert _lib.load().en_ws_bytes_knn_smallq(Q, N, d, k) > 0
+    dist, idx = clf.kneighbors(q, n_neighbors=k)
+    rd, ri = O.knn_exact(bank, q, k)
+    np.testing.assert_array_equal(idx, ri)
+    np.testing.assert_allclose(dist, rd, rtol=1e-5, atol=1e-7)
+    assert idx[0, 0] == 3 and (k < 3 or list(idx[0, :3]) == [3, N // 2, N - 1])
+    # the engine path gives the same ids
+    big = BankKNNClassifier(n_neighbors=k, precision="tf32x3").fit(bank, labels)   # no BF16 planes: engine path
+    np.testing.assert_array_equal(big.kneighbors(q, n_neighbors=k)[1], ri)
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
 def test_knn_ties_resolve_to_lowest_id(precision):
     from embeddingnet_b200.models import BankKNNClassifier

@@ -234,3 +234,36 @@ def test_draw_candidate_ranks_assigns_each_draw_to_exactly_one_shard():
             assert counts[:q, i, s].sum() + per_rank[q][i, s] == r and per_rank[q][i, s] < counts[q, i, s]
     assert np.random.random_sample() == after
     assert all((p[:, 5:] == -1).all() for p in per_rank)
+
+
+def test_vectorised_rank_draw_consumes_the_reference_rng_stream():
+    """The mining paths draw ``np.random.randint(len(candidates))`` per pair in the reference's pair order
+    (datagenerators.py:194,199 via np.random.choice).  The host code issues ONE vectorised call with an array of
+    upper bounds: same values, same generator state afterwards, including empty pairs, singletons and huge counts."""
+    from embeddingnet_b200.models import draw_candidate_ranks
+
+    rs = np.random.RandomState(3)
+    world, A, slots = 3, 400, 8
+    counts = rs.randint(0, 4, size=(world, A, slots)) * rs.randint(0, 2, size=(world, A, slots))
+    counts[:, 5, 2] = [2 ** 31 - 7, 2 ** 31 - 1, 11]        # a total beyond 32 bits
+    counts[:, 9, :] = 0
+    total = counts.sum(axis=0)
+    # the reference way: one scalar draw per pair with candidates, (anchor, slot) order
+    np.random.seed(77)
+    want = np.full((A, slots), -1, np.int64)
+    for i in range(A):
+        for s_ in range(5):
+            if total[i, s_] > 0:
+                want[i, s_] = np.random.randint(0, int(total[i, s_]))
+    state_want = np.random.get_state()
+    got = np.full((A, slots), -1, np.int64)
+    for q in range(world):
+        np.random.seed(77)
+        local = draw_candidate_ranks(counts, 5, q)
+        state_got = np.random.get_state()
+        before = counts[:q].sum(axis=0)
+        m = local >= 0
+        assert (got[m] == -1).all()                         # each draw lands in exactly one shard
+        got[m] = local[m] + before[m]
+    np.testing.assert_array_equal(got, want)
+    assert state_got[2] == state_want[2] and np.array_equal(state_got[1], state_want[1])
