@@ -318,8 +318,11 @@ def main():
         # it on, but on stderr, so that stdout stays the one JSON line
         # (through a per-rank file that is replayed on stderr at the end: pointing NCCL_DEBUG_FILE at /dev/stderr makes
         # every rank fopen(.., "w") -- i.e. truncate -- whatever file stderr is redirected to)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (the image presets NCCL_DEBUG=VERSION, which prints a banner on stdout: raised to INFO like an unset value; a
+        # caller's INFO / TRACE is left as it is)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         nccl_log = None
         if "NCCL_DEBUG_FILE" not in os.environ:
             import tempfile
@@ -722,25 +725,44 @@ def main():
                              "kernel": ("knn_stream_kernel<8,4,%d,true>" % qn) if on_stream else
                              "knn_smallq_kernel<16> (bank = 128-row MMA operand)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": stream_bytes}}
-        # C4: offline hard-negative mining over a bank = label-excluded nearest neighbours (1M x 256, 64k anchors)
+        # C4: offline hard-negative mining over a 1M x 256 bank with the generator's strategies.  Two banks: the
+        # SURVEY 8(d) one (noise 0.5: classes well separated, few pairs have a semi-hard candidate) and a candidate-rich
+        # one (noise 0.6: classes overlap, most pairs have candidates); 64k-anchor subset for both, plus ALL 1M rows as
+        # anchors for the hardest strategy ("anchors = all rows (report also a 64k-anchor subset)").
         mining = None
         if args.knn_bank >= 1_000_000:
             del clf, bank, queries
             torch.cuda.empty_cache()
             n4 = 1_000_000
             lo4, hi4 = BankKNNClassifier.shard_bounds(n4, world, rank)
-            bank4, _ = synth.make_device(hi4 - lo4, 256, row_offset=lo4, n_classes=10_000, noise=0.5, device=dev)
             ids4 = (torch.arange(n4, dtype=torch.int64, device=dev) % 10_000).to(torch.int32)
-            bank4 = lac.l2_normalize(bank4).detach().contiguous()  # embeddings_normalization=True, the reference default
-            clf4 = BankKNNClassifier(n_neighbors=1, process_group=group, device=dev)
-            clf4.fit_shard(bank4, ids4, lo4, n4, classes=np.arange(10_000))
             a_idx = torch.arange(0, n4, n4 // 65536, device=dev)[:65536]
-            full4 = lac.l2_normalize(synth.make_device(n4, 256, n_classes=10_000, noise=0.5, device=dev)[0]).detach() \
-                if world > 1 else bank4
-            anchors = full4[a_idx].contiguous()
-            positives = full4[(a_idx + 10_000) % n4].unsqueeze(1).contiguous()  # label = id % 10000: same class
-            del full4
             a_lab = ids4[a_idx].contiguous()
+
+            def mining_bank(noise):
+                full4 = lac.l2_normalize(synth.make_device(n4, 256, n_classes=10_000, noise=noise, device=dev)[0]).detach()
+                bank4 = full4[lo4:hi4].contiguous()   # embeddings_normalization=True, the reference default
+                clf4 = BankKNNClassifier(n_neighbors=1, process_group=group, device=dev)
+                clf4.fit_shard(bank4, ids4, lo4, n4, classes=np.arange(10_000))
+                anchors = full4[a_idx].contiguous()
+                positives = full4[(a_idx + 10_000) % n4].unsqueeze(1).contiguous()  # label = id % 10000: same class
+                return full4, clf4, anchors, positives
+
+            def timed_semihard(clf4, anchors, positives, what):
+                np.random.seed(0)
+                clf4.mine_negatives(anchors[:4096], a_lab[:4096], positives=positives[:4096], margin=MARGIN,
+                                    mode="semihard")
+                barrier()
+                t0 = time.perf_counter()
+                sel = clf4.mine_negatives(anchors, a_lab, positives=positives, margin=MARGIN, mode="semihard")
+                torch.cuda.synchronize()
+                s_dt = max_over_ranks(time.perf_counter() - t0)
+                return {"workload": "C4: semihard negative (datagenerators.py:196-199 over the whole bank) for 65536 "
+                                    "(anchor, positive) pairs, 1M x 256 bank (%s), %d GPU(s); count scan + host RNG "
+                                    "draws + select scan over the anchors that own a draw" % (what, world),
+                        "ms": s_dt * 1e3, "pairs_per_sec": 65536 / s_dt, "pairs_with_a_candidate": int((sel >= 0).sum())}
+
+            full4, clf4, anchors, positives = mining_bank(0.5)
             for _ in range(2):
                 clf4.kneighbors_device(anchors, n_neighbors=1, exclude_labels=a_lab)
             barrier()
@@ -752,18 +774,27 @@ def main():
             m_ms = max_over_ranks(m0.elapsed_time(m1))
             mining = {"workload": "C4: hardest negative of 65536 anchors over a 1M x 256 bank (label-excluded 1-NN), "
                                   "%d GPU(s)" % world, "ms": m_ms, "anchors_per_sec": 65536 / (m_ms * 1e-3)}
-            # the generator's default strategy at bank scale: count pass + host rank draw + select pass
-            np.random.seed(0)
-            clf4.mine_negatives(anchors[:4096], a_lab[:4096], positives=positives[:4096], margin=MARGIN, mode="semihard")
+            mining["semihard"] = timed_semihard(clf4, anchors, positives, "noise 0.5: separated classes")
+            # all 1M rows as anchors (hardest strategy): 2 * (1e6)^2 * 256 = 512 TFLOP algorithmic
             barrier()
-            t0 = time.perf_counter()
-            sel = clf4.mine_negatives(anchors, a_lab, positives=positives, margin=MARGIN, mode="semihard")
-            torch.cuda.synchronize()
-            s_dt = max_over_ranks(time.perf_counter() - t0)
-            mining["semihard"] = {
-                "workload": "C4: semihard negative (datagenerators.py:196-199 over the whole bank) for 65536 "
-                            "(anchor, positive) pairs, 1M x 256 bank, %d GPU(s); two scans + host RNG draws" % world,
-                "ms": s_dt * 1e3, "pairs_per_sec": 65536 / s_dt, "pairs_with_a_candidate": int((sel >= 0).sum())}
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            clf4.kneighbors_device(full4, n_neighbors=1, exclude_labels=ids4)
+            f1.record()
+            barrier()
+            f_ms = max_over_ranks(f0.elapsed_time(f1))
+            mining["all_rows_hardest"] = {
+                "workload": "C4 at its stated size: hardest negative of ALL 1,000,000 rows over the 1M x 256 bank, "
+                            "%d GPU(s)" % world, "ms": f_ms, "anchors_per_sec": n4 / (f_ms * 1e-3),
+                "tflops_algorithmic": 2.0 * n4 * n4 * 256 / (f_ms * 1e-3) / 1e12,
+                "frac_of_bf16x3_roofline": 2.0 * n4 * n4 * 256 / (f_ms * 1e-3) / 1e12 / world /
+                                           (peaks["bf16_sustained"] / 3.0)}
+            del full4, clf4, anchors, positives
+            torch.cuda.empty_cache()
+            full4, clf4, anchors, positives = mining_bank(0.6)
+            mining["semihard_candidate_rich"] = timed_semihard(clf4, anchors, positives,
+                                                               "noise 0.6: overlapping classes")
+            del full4, clf4, anchors, positives
         # Key order matters to the reader of a truncated log: bulky sub-records first, the headline of the sharded
         # path (value, time, roofline, e2e, parity hash, NCCL ranks) last.
         knn = {

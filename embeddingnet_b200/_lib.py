@@ -16,6 +16,7 @@ EN_MODE_SEMIHARD, EN_MODE_HARDEST, EN_MODE_RANDOM_HARD = 0, 1, 2
 EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q, EN_KNN_SMALLQ_MAX_Q = 3, 29, 8, 64, 64
 EN_PREC_TF32X3, EN_PREC_BF16X3 = 0, 1
 EN_MINE_MAX_SLOTS = 8
+EN_COMM_ID_BYTES = 128
 
 P = c_void_p  # every device pointer / stream crosses the boundary as an opaque address
 
@@ -88,6 +89,11 @@ SIGNATURES = {
     "en_dense_relu_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P, P, c_size_t, P]),
     "en_ws_bytes_dense_bwd": (c_size_t, [c_int64, c_int, c_int]),
     "en_dense_relu_bwd": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+    "en_comm_unique_id": (c_int, [P]),
+    "en_comm_init": (c_int, [c_int, c_int, P, ctypes.POINTER(c_void_p)]),
+    "en_comm_allgather": (c_int, [P, P, P, c_size_t, P]),
+    "en_comm_allreduce_max_i64": (c_int, [P, P, P, c_size_t, P]),
+    "en_comm_destroy": (c_int, [P]),
     "en_synth_fill": (c_int, [P, c_int64, c_int, c_int64, c_uint64, c_uint64, c_int64, c_int64, c_float, c_int, P, P]),
 }
 

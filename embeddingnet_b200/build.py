@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libembeddingnet_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["core.cu", "rowwise.cu", "pairwise.cu", "batch_losses.cu", "pair_tc.cu", "knn.cu", "head.cu", "mine_bank.cu"]
+SOURCES = ["core.cu", "rowwise.cu", "pairwise.cu", "batch_losses.cu", "pair_tc.cu", "knn.cu", "head.cu", "mine_bank.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

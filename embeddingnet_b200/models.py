@@ -339,11 +339,27 @@ class BankKNNClassifier:
             allc = mine.unsqueeze(0)
         local_rank = draw_candidate_ranks(allc.cpu().numpy(), S, rank)
         sel = torch.full((A, MS), -1, dtype=torch.int64, device=dev)
-        if n > 0:
-            rk = torch.from_numpy(local_rank).to(dev)
-            _lib.call("en_mine_bank_select", ptr(a), ptr(al), ptr(pos_d), A, d, S, ctypes.c_float(margin), MODES[mode],
-                      ptr(rk), ptr(self._bank), ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl), n,
-                      self._offset, self._prec, ptr(sel), ptr(ws), ws.numel(), stream_ptr())
+        # The select pass only has work for anchors with a draw that landed in THIS shard: compact them (the ranks are
+        # on the host anyway), so a bank where few pairs have a candidate -- or a shard that owns few of the draws --
+        # is walked by a fraction of the anchor tiles instead of all of them.
+        need = np.nonzero((local_rank >= 0).any(axis=1))[0]
+        if n > 0 and need.size > 0:
+            if need.size == A:
+                a_s, al_s, pd_s, rk = a, al, pos_d, torch.from_numpy(local_rank).to(dev)
+                sel_s = sel
+            else:
+                idx = torch.from_numpy(need).to(dev)
+                a_s = a.index_select(0, idx).contiguous()
+                al_s = al.index_select(0, idx).contiguous()
+                pd_s = pos_d.index_select(0, idx).contiguous()
+                rk = torch.from_numpy(np.ascontiguousarray(local_rank[need])).to(dev)
+                sel_s = torch.full((need.size, MS), -1, dtype=torch.int64, device=dev)
+            ws_s = workspace(lib.en_ws_bytes_mine_bank(a_s.shape[0], d), dev, "mine_bank")
+            _lib.call("en_mine_bank_select", ptr(a_s), ptr(al_s), ptr(pd_s), a_s.shape[0], d, S, ctypes.c_float(margin),
+                      MODES[mode], ptr(rk), ptr(self._bank), ptr(self._hi), ptr(self._lo), ptr(self._norms), ptr(bl),
+                      n, self._offset, self._prec, ptr(sel_s), ptr(ws_s), ws_s.numel(), stream_ptr())
+            if need.size != A:
+                sel.index_copy_(0, idx, sel_s)
         if world > 1:
             import torch.distributed as dist_
 

@@ -31,6 +31,7 @@ extern "C" {
 #define EN_ERR_WORKSPACE (-2)  /* workspace too small or misaligned */
 #define EN_ERR_DRIVER (-3)     /* cuTensorMapEncodeTiled unavailable / failed */
 #define EN_ERR_ARCH (-4)       /* device is not sm_100 */
+#define EN_ERR_COMM (-5)       /* NCCL reported an error (en_comm_*) */
 
 #define EN_MODE_SEMIHARD 0     /* datagenerators.py:196-199 */
 #define EN_MODE_HARDEST 1      /* datagenerators.py:188-190 */
@@ -319,6 +320,24 @@ int en_dense_relu_bwd(const float* x, int64_t B, int n_in, const float* w, int n
 int en_synth_fill(float* x, int64_t rows, int d, int64_t row_offset, uint64_t seed_centre, uint64_t seed_noise,
                   int64_t n_classes, int64_t rows_per_class, float noise, int relu, int32_t* labels_out,
                   void* stream);
+
+/* ---------------------------------------------------------------- NCCL plumbing of the sharded bank paths */
+/* The only partitioned paths: bank kNN (models.py:128-161 at bank scale) and bank mining
+ * (datagenerators.py:188-199 at bank scale), bank rows sharded over one process per GPU.  Their exchange step is one
+ * all-gather of small records (per-shard top-k lists / candidate counts) and, for mining, one all-reduce(max) of the
+ * selected ids.  The Python host issues them through torch.distributed; these entry points let any other host do the
+ * same through this library (NCCL is bound with dlopen at first use; the reference itself has no collective).
+ *   rank 0:     en_comm_unique_id(id)            -> ship the EN_COMM_ID_BYTES bytes to the other ranks (file, socket..)
+ *   every rank: cudaSetDevice(rank's GPU); en_comm_init(nranks, rank, id, &comm)
+ *   per search: en_knn_shard_topk(..., d2, ids) into the two halves of one (2, Q, k) buffer,
+ *               en_comm_allgather(comm, buffer, all, 2*Q*k*8, stream), en_knn_merge_packed(all, nranks, Q, k, ...)
+ * Collectives on one communicator must be issued in the same order on every rank and not concurrently. */
+#define EN_COMM_ID_BYTES 128
+int en_comm_unique_id(void* id_bytes_host);
+int en_comm_init(int nranks, int rank, const void* id_bytes_host, void** comm_out);
+int en_comm_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+int en_comm_allreduce_max_i64(void* comm, const int64_t* send, int64_t* recv, size_t count, void* stream);
+int en_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

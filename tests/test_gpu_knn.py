@@ -476,3 +476,32 @@ def test_knn_large_bank_planted_neighbours_and_empty_inputs():
                                   pos_dist=np.zeros((0, 2), np.float32)).shape == (0, 2)
         del clf
     np.testing.assert_array_equal(results["bf16x3"], results["tf32x3"])
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_sharded_knn_through_the_c_abi_alone(nranks, tmp_path):
+    """The exchange step of the sharded path through en_comm_* (NCCL bound by the library, no torch.distributed):
+    one process per GPU, unique id handed over through a file, packed all-gather + en_knn_merge_packed, and the
+    all-reduce(max) of the mining protocol.  nranks = 1 runs on the single-GPU box too."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "comm_abi_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(nranks), str(tmp_path / "id.bin"),
+                               str(tmp_path / ("out%d.npz" % r))], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(nranks)]
+    outs = [p.communicate(timeout=300)[0].decode(errors="replace") for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)[-3000:]
+    N, d, Q, k = 6000, 96, 150, 5
+    bank, _ = synth.make_numpy(N, d, n_classes=60, noise=0.5)
+    q, _ = synth.make_numpy(Q, d, seed_noise=synth.SEED_QUERY, n_classes=60, noise=0.5)
+    rd, ri = O.knn_exact(bank, q, k)
+    want_red = np.arange(Q) + 1000 * (np.arange(Q) % nranks)
+    for r in range(nranks):
+        z = np.load(tmp_path / ("out%d.npz" % r))
+        np.testing.assert_array_equal(z["ids"], ri)
+        np.testing.assert_allclose(np.sqrt(z["d2"]), rd, rtol=1e-5)
+        np.testing.assert_array_equal(z["reduced"], want_red)

@@ -24,4 +24,8 @@ if k:
     if "bank_mining" in k:
         m = k["bank_mining"]
         print("  mining hardest %.1f ms semihard %.1f ms (%d with candidate)" % (m["ms"], m["semihard"]["ms"], m["semihard"]["pairs_with_a_candidate"]))
+        if "all_rows_hardest" in m:
+            print("  all-rows hardest %.1f ms (%.3f of bf16x3 roofline); rich semihard %.1f ms (%d with candidate)" % (
+                m["all_rows_hardest"]["ms"], m["all_rows_hardest"]["frac_of_bf16x3_roofline"],
+                m["semihard_candidate_rich"]["ms"], m["semihard_candidate_rich"]["pairs_with_a_candidate"]))
 print("clocks", l.get("clocks"))
