@@ -28,6 +28,7 @@ SIGNATURES = {
     "en_launch_count_reset": (None, []),
     "en_prof_enable": (c_int, [c_int]),
     "en_prof_last_ms": (c_int, [P]),
+    "en_prof_marks_ms": (c_int, [P, c_int, P]),
     "en_l2_normalize_fwd": (c_int, [P, P, c_int64, c_int, P]),
     "en_l2_normalize_bwd": (c_int, [P, P, P, c_int64, c_int, P]),
     "en_triplet_apn_fwd": (c_int, [P, c_int64, c_int, c_float, P, P]),

@@ -11,6 +11,7 @@
 // Numerics: the tensor-core pass (3xTF32; split-BF16 for batch-hard) only *selects* (arg-max positive, arg-min negative) or feeds sums whose
 // terms are O(1); every distance that reaches a loss value or a gradient of the batch-hard path is re-evaluated
 // exactly (float64 sum (a-b)^2) for the one or two candidates per anchor that matter.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_engine.cuh"
 
@@ -278,14 +279,51 @@ __device__ __forceinline__ float lane_d2_f32(const float* __restrict__ e, int d,
   return (s0 + s1) + (s2 + s3);
 }
 
+// float32 squared distances of the anchor row to four rows at once, warp-cooperative (d % 128 == 0, 16-byte aligned)
+__device__ __forceinline__ void warp_d2_f32x4(const float* __restrict__ e, int d, int64_t row, const int (&j)[4],
+                                              int lane, float (&out)[4]) {
+  const float4* a = reinterpret_cast<const float4*>(e + row * d) + lane;
+  const float4* b0 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[0]) * d) + lane;
+  const float4* b1 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[1]) * d) + lane;
+  const float4* b2 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[2]) * d) + lane;
+  const float4* b3 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[3]) * d) + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  auto acc = [](float s, const float4& x, const float4& y) {
+    float t;
+    t = x.x - y.x; s = fmaf(t, t, s);
+    t = x.y - y.y; s = fmaf(t, t, s);
+    t = x.z - y.z; s = fmaf(t, t, s);
+    t = x.w - y.w; s = fmaf(t, t, s);
+    return s;
+  };
+#pragma unroll 4
+  for (int i = 0; i < d / 128; ++i) {
+    const float4 x = __ldg(a + 32 * i), y0 = __ldg(b0 + 32 * i), y1 = __ldg(b1 + 32 * i), y2 = __ldg(b2 + 32 * i),
+                 y3 = __ldg(b3 + 32 * i);
+    s0 = acc(s0, x, y0);
+    s1 = acc(s1, x, y1);
+    s2 = acc(s2, x, y2);
+    s3 = acc(s3, x, y3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
+}
+
 // Re-scan of ONE record slot: every row the slot covers (64 columns of the row view, 32 rows of the column view)
-// with the wanted label relation is measured in float32, one row per lane; the rows within the float32 error of the
-// slot's best are then re-evaluated in float64 by the same exact_d2() every other candidate goes through (so exact
-// duplicates compare equal bit for bit and resolve to the lowest index).  Used when the slot is SATURATED: its
-// second entry is itself a contender, so the slot may hide further contenders behind its top-2 (three duplicates of
-// the hardest negative in adjacent rows -- the reference's sampler draws with replacement,
-// embedding_net/datagenerators.py:205 -- or three near-ties).  A hidden entry's packed key is never better than the
-// slot's second one, so "second entry outside the band" proves that nothing hidden matters.
+// with the wanted label relation is measured in float32 (four rows per trip, all loads of a trip in flight; rows
+// of other shapes: one row per lane); the rows within the float32 error of the slot's best are then re-evaluated in
+// float64 by the same exact_d2() every other candidate goes through (so exact duplicates compare equal bit for bit
+// and resolve to the lowest index).  Used when the slot is SATURATED: its second entry is itself a contender, so
+// the slot may hide further contenders behind its top-2 (three duplicates of the hardest negative in adjacent rows
+// -- the reference's sampler draws with replacement, embedding_net/datagenerators.py:205 -- or three near-ties).
+// A hidden entry's packed key is never better than the slot's second one, so "second entry outside the band"
+// proves that nothing hidden matters.
 __device__ __noinline__ BhPick bh_rescan_slot(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                               int64_t B, int d, int64_t row, int32_t la, int t, int my_tile,
                                               bool want_same, int lane, BhPick win) {
@@ -293,14 +331,33 @@ __device__ __noinline__ BhPick bh_rescan_slot(const float* __restrict__ emb, con
   const bool col_view = tile < my_tile;
   const int len = col_view ? 32 : 64;
   const int64_t j0 = static_cast<int64_t>(tile) * tc::BN + slot * len;
-  const float rel = static_cast<float>(d / 4 + 8) * 2.4e-7f;  // both the best and the contender carry the error
+  const bool coop = (d & 127) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0;
+  const float rel = static_cast<float>(d / 4 + 16) * 2.4e-7f;  // both the best and the contender carry the error
   for (int64_t jb = j0; jb < j0 + len; jb += 32) {
     const int64_t j = jb + lane;
     const bool ok = j < B && j != row;
     const bool want = ok && ((__ldg(&labels[ok ? j : 0]) == la) == want_same);
-    if (!__any_sync(0xffffffffu, want)) continue;
+    unsigned wm = __ballot_sync(0xffffffffu, want);
+    if (wm == 0) continue;
     float f = want_same ? -1.f : kBig;
-    if (want) f = lane_d2_f32(emb, d, row, j);
+    if (coop) {
+      while (wm) {
+        int l[4], jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          l[u] = wm ? __ffs(wm) - 1 : l[0];
+          if (wm) wm &= wm - 1;
+          jj[u] = static_cast<int>(jb) + l[u];
+        }
+        float f4[4];
+        warp_d2_f32x4(emb, d, row, jj, lane, f4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (lane == l[u]) f = f4[u];
+      }
+    } else if (want) {
+      f = lane_d2_f32(emb, d, row, j);
+    }
     float best = f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -524,7 +581,7 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
 // negative at all -- takes the generic per-candidate path on the same registers.
 constexpr int FF_WARPS = 4;  // anchors per block: small blocks so that one slow warp holds back few others
 template <bool kGrad, int DV>
-__global__ void __launch_bounds__(FF_WARPS * 32, 6)  // 85 registers: no spills (ncu: local loads/stores were 6 % of the instructions)
+__global__ void __launch_bounds__(FF_WARPS * 32, 7)  // 72 registers: 7 blocks = 28 warps per SM, all 4096 anchors of the headline shape resident in ONE wave
 batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                 const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B,
                                 int tiles_n, float margin, int squared, int soft, float band_c,
@@ -597,8 +654,9 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
     const bool no_neg = !__any_sync(0xffffffffu, nc > 0);
     if (overflow || no_neg) {
       // A saturated slot, three contenders queued on one lane, or no negative at all: the anchor goes on the work
-      // list of batch_hard_finalize_slow_kernel (a whole block per anchor).  Resolving it here, one warp per anchor,
-      // held the block's slot for tens of microseconds and doubled the kernel's duration with ~5 % such anchors.
+      // list of batch_hard_finalize_slow_kernel (a whole block per anchor).  Resolving it here, one warp per anchor
+      // (tried twice in round 2, the second time with the four-rows-per-trip float32 filter of bh_rescan_slot), made
+      // the ~5 % such anchors the critical path of this kernel: 51 us instead of 12 + 17 us for the two kernels.
       if (lane == 0) work_list[atomicAdd(&counters[0], 1u)] = static_cast<int32_t>(row);
       return;
     }
@@ -720,42 +778,6 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
 // exact duplicates compare equal bit for bit and resolve to the lowest index.  The last block to finish adds the
 // per-anchor hinge values of BOTH kernels in a fixed order (deterministic mean).
 constexpr int FS_WARPS = 8;
-
-// float32 squared distances of the anchor row to four rows at once, warp-cooperative (d % 128 == 0, 16-byte aligned)
-__device__ __forceinline__ void warp_d2_f32x4(const float* __restrict__ e, int d, int64_t row, const int (&j)[4],
-                                              int lane, float (&out)[4]) {
-  const float4* a = reinterpret_cast<const float4*>(e + row * d) + lane;
-  const float4* b0 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[0]) * d) + lane;
-  const float4* b1 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[1]) * d) + lane;
-  const float4* b2 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[2]) * d) + lane;
-  const float4* b3 = reinterpret_cast<const float4*>(e + static_cast<int64_t>(j[3]) * d) + lane;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  auto acc = [](float s, const float4& x, const float4& y) {
-    float t;
-    t = x.x - y.x; s = fmaf(t, t, s);
-    t = x.y - y.y; s = fmaf(t, t, s);
-    t = x.z - y.z; s = fmaf(t, t, s);
-    t = x.w - y.w; s = fmaf(t, t, s);
-    return s;
-  };
-#pragma unroll 4
-  for (int i = 0; i < d / 128; ++i) {
-    const float4 x = __ldg(a + 32 * i), y0 = __ldg(b0 + 32 * i), y1 = __ldg(b1 + 32 * i), y2 = __ldg(b2 + 32 * i),
-                 y3 = __ldg(b3 + 32 * i);
-    s0 = acc(s0, x, y0);
-    s1 = acc(s1, x, y1);
-    s2 = acc(s2, x, y2);
-    s3 = acc(s3, x, y3);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-  }
-  out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
-}
 
 // hinge / outputs / gradient of one anchor from its resolved picks (one warp); returns the hinge value
 template <bool kGrad>
@@ -957,10 +979,18 @@ batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __
     }
     __syncthreads();  // shared state is reused by the next anchor
   }
-  // ---- mean over all anchors, by the last block, in a fixed order
+  // ---- mean over all anchors, in a fixed order, by the last WORKING block (blocks without an anchor leave at
+  // once: with every block taking part, the 592 fences + atomics on one word were most of this kernel's ~15 us
+  // when the list is short) -- or by block 0 when the list is empty
+  const unsigned n_working = n_work < gridDim.x ? n_work : gridDim.x;
+  if (blockIdx.x >= n_working && !(n_working == 0 && blockIdx.x == 0)) return;
   if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(&counters[1], 1u) == gridDim.x - 1;
+    if (n_working == 0) {
+      s_last = true;
+    } else {
+      __threadfence();
+      s_last = atomicAdd(&counters[1], 1u) == n_working - 1;
+    }
   }
   __syncthreads();
   if (s_last) {
@@ -1705,7 +1735,9 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   unsigned* counters = w.take<unsigned>(4);  // [0] work-list length, [1] finished blocks
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "%s: workspace too small or misaligned", who);
   // the operand split also zeroes the gradient buffer and the two counters (no memset nodes in the step)
+  prof_mark(st, 0);
   if (int rc = prepare_operands(emb, B, d, w, st, o, false, true, gemb, counters)) return rc;
+  prof_mark(st, 1);
   // |dot~ - dot| <= c |a||b| with c = 3 * 2^-16 (dropped lo*lo and residual products of the BF16 split) +
   // 2^-22 (d/16 + 1) (accumulator truncation): 5.4e-5 at d = 512 (measured maximum: 4e-6).  Proxy = |b|^2 - 2 dot,
   // |a||b| <= (|a|^2 + |b|^2) / 2, best and contender both off by it: band = 2 c (|a|^2 + |b|^2).
@@ -1718,13 +1750,14 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   prof_begin(st);
   EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
   prof_end(st);
+  prof_mark(st, 2);
   ++launch_counter();
   const bool fast = d % 128 == 0 && d <= 512 && tiles_n * BH_SLOTS <= 128 &&
                     (reinterpret_cast<uintptr_t>(emb) & 15) == 0;
   if (fast) {
     const unsigned fblocks = static_cast<unsigned>((B + FF_WARPS - 1) / FF_WARPS);
-#define EN_BH_FAST(G, DV)                                                                                        \
-  batch_hard_finalize_fast_kernel<G, DV><<<fblocks, FF_WARPS * 32, 0, st>>>(                                       \
+#define EN_BH_FAST(G, DV)                                                                                         \
+  batch_hard_finalize_fast_kernel<G, DV><<<fblocks, FF_WARPS * 32, 0, st>>>(                                        \
       emb, labels, o.norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef, hinge_all, \
       work_list, counters, G ? gloss : nullptr, G ? gemb : nullptr)
     if (gemb) {
@@ -1740,6 +1773,7 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
     }
 #undef EN_BH_FAST
     EN_LAUNCHED("batch_hard_finalize_fast_kernel");
+    prof_mark(st, 3);
     // the anchors on the work list (a block each; enough blocks that each takes one: the kernel's duration is one
     // anchor's dependent chain of loads) and the deterministic mean
     const unsigned sblocks = static_cast<unsigned>(sms > 0 ? sms : 148) * 4;
@@ -1752,6 +1786,7 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
           emb, labels, o.norms, cand, B, d, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx, hp, hn, coef,
           hinge_all, work_list, counters, loss, nullptr, nullptr);
     EN_LAUNCHED("batch_hard_finalize_slow_kernel");
+    prof_mark(st, 4);
     return EN_OK;
   }
   const unsigned blocks = static_cast<unsigned>((B + 7) / 8);

@@ -67,6 +67,7 @@ struct Workspace {
 // distance-GEMM / streaming-scan launch with CUDA events recorded on the launching stream.
 void prof_begin(cudaStream_t st);
 void prof_end(cudaStream_t st);
+void prof_mark(cudaStream_t st, int slot);  // stage boundaries of a multi-kernel entry point (en_prof_marks_ms)
 
 int device_sm_count();  // SM count of the current device (cached per device), <0 on error
 int check_sm100();      // 0 when the current device is compute capability 10.x

@@ -18,6 +18,8 @@ struct ProfState {
   bool on = false;
   bool have = false;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_marks = 0;
 };
 ProfState& prof() {
   static thread_local ProfState p;
@@ -39,6 +41,16 @@ void prof_end(cudaStream_t st) {
   if (!p.on || !p.e0) return;
   cudaEventRecord(p.e1, st);
   p.have = true;
+}
+
+// stage boundaries of a multi-kernel entry point (en_prof_marks_ms); slot 0 = entry
+void prof_mark(cudaStream_t st, int slot) {
+  ProfState& p = prof();
+  if (!p.on || slot < 0 || slot >= 8) return;
+  if (!p.marks[slot]) cudaEventCreate(&p.marks[slot]);
+  cudaEventRecord(p.marks[slot], st);
+  if (slot == 0) p.n_marks = 1;
+  else if (slot + 1 > p.n_marks) p.n_marks = slot + 1;
 }
 
 int device_sm_count() {
@@ -126,6 +138,18 @@ int en_prof_last_ms(float* ms_host) {
   if (!p.have) return fail(EN_ERR_ARG, "en_prof_last_ms: no timed launch recorded (call en_prof_enable(1) first)");
   EN_CUDA(cudaEventSynchronize(p.e1));
   EN_CUDA(cudaEventElapsedTime(ms_host, p.e0, p.e1));
+  return EN_OK;
+}
+
+int en_prof_marks_ms(float* ms_host, int capacity, int* n_out) {
+  EN_REQUIRE(ms_host != nullptr && n_out != nullptr && capacity > 0, "en_prof_marks_ms: bad arguments");
+  ProfState& p = prof();
+  const int n = p.n_marks - 1 < capacity ? p.n_marks - 1 : capacity;
+  *n_out = n < 0 ? 0 : n;
+  for (int i = 0; i < n; ++i) {
+    EN_CUDA(cudaEventSynchronize(p.marks[i + 1]));
+    EN_CUDA(cudaEventElapsedTime(&ms_host[i], p.marks[i], p.marks[i + 1]));
+  }
   return EN_OK;
 }
 

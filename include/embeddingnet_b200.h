@@ -48,6 +48,9 @@ void en_launch_count_reset(void);
  * the second event and returns the kernel's duration in milliseconds (host pointer). */
 int en_prof_enable(int on);
 int en_prof_last_ms(float* ms_host);
+/* Stage times of the last multi-kernel entry point that marks its stages (en_batch_hard_fwd[_bwd]: operand split,
+ * distance GEMM, fast finalize, slow finalize), in milliseconds; n_out receives how many were written. */
+int en_prof_marks_ms(float* ms_host, int capacity, int* n_out);
 
 /* ---------------------------------------------------------------- row-wise kernels (memory bound) */
 /* K.l2_normalize(x, axis=1): y = x * rsqrt(max(sum x^2, 1e-12)).  backbones.py:38,77,118 */

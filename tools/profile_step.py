@@ -51,6 +51,32 @@ if what == "mining":
     for mode in ("hardest", "semihard"):
         clf.mine_negatives(anchors, a_lab, positives=pos, margin=0.5, mode=mode)
     torch.cuda.synchronize()
+if what == "smallq":
+    # the reference's small call patterns against a 4M x 512 bank: 1 query (streaming scan) and 8 / 32 queries
+    # (bank-stationary tensor scan)
+    n = 4_000_000
+    bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
+    ids = (torch.arange(n, device=dev) % 100000).to(torch.int32)
+    clf = BankKNNClassifier(5, device=dev).fit_shard(bank, ids, 0, n, classes=np.arange(100000))
+    q, _ = synth.make_device(64, 512, seed_noise=synth.SEED_QUERY, n_classes=100000, noise=0.5, device=dev)
+    for qn in (1, 8, 32):
+        for _ in range(2):
+            clf.kneighbors_device(q[:qn].contiguous())
+    torch.cuda.synchronize()
+if what == "rowwise":
+    from embeddingnet_b200 import _lib
+    from embeddingnet_b200._runtime import ptr, stream_ptr
+    rows, d = 1_000_000, 256
+    x = synth.make_device(rows, d, n_classes=rows // 8, rows_per_class=8, noise=0.5, relu=True, device=dev)[0]
+    g = synth.make_device(rows, d, seed_noise=77, device=dev)[0]
+    y = torch.empty_like(x)
+    v = torch.empty(rows, device=dev)
+    for _ in range(2):
+        _lib.call("en_l2_normalize_fwd", ptr(x), ptr(y), rows, d, stream_ptr())
+        _lib.call("en_l2_normalize_bwd", ptr(x), ptr(g), ptr(y), rows, d, stream_ptr())
+        _lib.call("en_siamese_l2_fwd", ptr(x), ptr(g), rows, d, ptr(v), stream_ptr())
+        _lib.call("en_query_distances", ptr(x), ptr(g), rows, d, ptr(v), stream_ptr())
+    torch.cuda.synchronize()
 if what in ("all", "knn"):
     n, Q = 400_000, 8192
     bank, _ = synth.make_device(n, 512, n_classes=100000, noise=0.5, device=dev)
