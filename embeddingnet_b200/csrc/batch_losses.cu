@@ -580,21 +580,20 @@ __global__ void batch_hard_finalize_kernel(const float* __restrict__ emb, const 
 // the two exact distances AND the gradient).  Anything unusual -- several contenders inside the error band, no
 // negative at all -- takes the generic per-candidate path on the same registers.
 constexpr int FF_WARPS = 4;  // anchors per block: small blocks so that one slow warp holds back few others
+// One warp, one anchor.  Returns true when the anchor is COMPLEX (a saturated slot, three contenders queued on one
+// lane, or no negative at all) and was left untouched for the block-level resolver.
 template <bool kGrad, int DV>
-__global__ void __launch_bounds__(FF_WARPS * 32, 7)  // 72 registers: 7 blocks = 28 warps per SM, all 4096 anchors of the headline shape resident in ONE wave
-batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
-                                const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B,
-                                int tiles_n, float margin, int squared, int soft, float band_c,
-                                int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
-                                float* __restrict__ hp_out, float* __restrict__ hn_out, float* __restrict__ coef,
-                                double* __restrict__ hinge_all, int32_t* __restrict__ work_list,
-                                unsigned* __restrict__ counters, const float* __restrict__ gloss,
-                                float* __restrict__ gemb) {
+__device__ __forceinline__ bool bh_fast_anchor(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                               const float* __restrict__ norms, const BhCand* __restrict__ cand,
+                                               int64_t B, int tiles_n, float margin, int squared, int soft,
+                                               float band_c, int32_t* __restrict__ hp_idx,
+                                               int32_t* __restrict__ hn_idx, float* __restrict__ hp_out,
+                                               float* __restrict__ hn_out, float* __restrict__ coef,
+                                               double* __restrict__ hinge_all, const float* __restrict__ gloss,
+                                               float* __restrict__ gemb, int64_t row, int lane) {
   constexpr int d = 128 * DV;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * FF_WARPS + warp;
   double hinge = 0.0;
-  if (row < B) {
+  {
     const int n_cand = tiles_n * BH_SLOTS;  // <= 128
     const int my_tile = static_cast<int>(row / tc::BM);
     const BhCand* mine = cand + row * n_cand;
@@ -652,14 +651,11 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
     int rounds = 0;
     const bool overflow = __any_sync(0xffffffffu, sat || pc > 2 || nc > 2);
     const bool no_neg = !__any_sync(0xffffffffu, nc > 0);
-    if (overflow || no_neg) {
-      // A saturated slot, three contenders queued on one lane, or no negative at all: the anchor goes on the work
-      // list of batch_hard_finalize_slow_kernel (a whole block per anchor).  Resolving it here, one warp per anchor
-      // (tried twice in round 2, the second time with the four-rows-per-trip float32 filter of bh_rescan_slot), made
-      // the ~5 % such anchors the critical path of this kernel: 51 us instead of 12 + 17 us for the two kernels.
-      if (lane == 0) work_list[atomicAdd(&counters[0], 1u)] = static_cast<int32_t>(row);
-      return;
-    }
+    // A saturated slot, three contenders queued on one lane, or no negative at all: the anchor goes on the work list
+    // of the block-level resolver (a whole block per anchor).  Resolving it here, one warp per anchor (tried twice in
+    // round 2, the second time with the four-rows-per-trip float32 filter of bh_rescan_slot), made the ~5 % such
+    // anchors the critical path of this kernel: 51 us instead of 12 + 17 us for the two kernels.
+    if (overflow || no_neg) return true;
     {
       // Each round re-evaluates one positive and one negative contender exactly, all row loads of the round in one
       // batch.  The usual case is a single round (one contender each; none for an anchor alone in its class).
@@ -769,6 +765,26 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
       }
     }
   }
+  return false;
+}
+
+template <bool kGrad, int DV>
+__global__ void __launch_bounds__(FF_WARPS * 32, 7)  // 72 registers: 7 blocks = 28 warps per SM, all 4096 anchors of the headline shape resident in ONE wave
+batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
+                                const float* __restrict__ norms, const BhCand* __restrict__ cand, int64_t B,
+                                int tiles_n, float margin, int squared, int soft, float band_c,
+                                int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                float* __restrict__ hp_out, float* __restrict__ hn_out, float* __restrict__ coef,
+                                double* __restrict__ hinge_all, int32_t* __restrict__ work_list,
+                                unsigned* __restrict__ counters, const float* __restrict__ gloss,
+                                float* __restrict__ gemb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * FF_WARPS + warp;
+  if (row >= B) return;
+  if (bh_fast_anchor<kGrad, DV>(emb, labels, norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx,
+                                hp_out, hn_out, coef, hinge_all, gloss, gemb, row, lane) &&
+      lane == 0)
+    work_list[atomicAdd(&counters[0], 1u)] = static_cast<int32_t>(row);
 }
 
 // ---- slow finalize: the anchors the fast kernel put on the work list, one BLOCK per anchor -------------------
@@ -826,6 +842,178 @@ __device__ __forceinline__ double bh_finish(const float* __restrict__ emb, int d
   return hinge;
 }
 
+// Shared state of one block resolving one listed anchor (NW warps)
+template <int NW>
+struct BhBlockShared {
+  float bp[NW], bn[NW];
+  double d2[2][NW];
+  int idx[2][NW];
+  int nsat;
+  int sat[2 * 128];
+  float f[64];
+};
+
+// All NW warps of a block resolve ONE anchor: records over the first four warps, a saturated slot's candidates over
+// all of them; outputs, hinge value and gradient are written by warps 0..3.  Contains block-wide barriers.
+template <bool kGrad, int NW>
+__device__ __forceinline__ void bh_block_resolve(BhBlockShared<NW>& sm, const float* __restrict__ emb,
+                                                 const int32_t* __restrict__ labels, const float* __restrict__ norms,
+                                                 const BhCand* __restrict__ cand, int64_t B, int d, int tiles_n,
+                                                 float margin, int squared, int soft, float band_c, int64_t row,
+                                                 int32_t* __restrict__ hp_idx, int32_t* __restrict__ hn_idx,
+                                                 float* __restrict__ hp_out, float* __restrict__ hn_out,
+                                                 float* __restrict__ coef, double* __restrict__ hinge_all,
+                                                 const float* __restrict__ gloss, float* __restrict__ gemb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cand = tiles_n * BH_SLOTS;  // <= 128: the records live in warps 0..3
+  const int my_tile = static_cast<int>(row / tc::BM);
+  const BhCand* mine = cand + row * n_cand;
+  const float na = norms[row];
+  const int32_t la = labels[row];
+  const int t = warp * 32 + lane;
+  float4 v = make_float4(-kBig, -kBig, kBig, kBig);
+  if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
+  float bp = v.x, bn = v.z;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+    bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+  }
+  if (lane == 0) { sm.bp[warp] = bp; sm.bn[warp] = bn; }
+  if (threadIdx.x == 0) sm.nsat = 0;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { bp = fmaxf(bp, sm.bp[w]); bn = fminf(bn, sm.bn[w]); }
+  const BhThr thr = bh_thresholds(na, bp, bn, band_c);
+  const bool cp1 = bh_valid(v.x) && v.x >= thr.p, cp2 = bh_valid(v.y) && v.y >= thr.p;
+  const bool cn1 = bh_valid(v.z) && v.z <= thr.n, cn2 = bh_valid(v.w) && v.w <= thr.n;
+  const int ip = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.x) & 0x7Fu);
+  const int in = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.z) & 0x7Fu);
+  BhPick pos{-1.0, -1}, neg{1e300, -1};
+  // entries of unsaturated slots: exact, one by one
+  unsigned m = __ballot_sync(0xffffffffu, cp1 && !cp2);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int ci = __shfl_sync(0xffffffffu, ip, src);
+    bh_update_max(pos, exact_d2(emb, d, row, ci, lane), ci);
+  }
+  m = __ballot_sync(0xffffffffu, cn1 && !cn2);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int ci = __shfl_sync(0xffffffffu, in, src);
+    bh_update_min(neg, exact_d2(emb, d, row, ci, lane), ci);
+  }
+  // saturated slots (second entry inside the band): queued for the whole block
+  if (cp2) sm.sat[atomicAdd(&sm.nsat, 1)] = t * 2 + 1;
+  if (cn2) sm.sat[atomicAdd(&sm.nsat, 1)] = t * 2;
+  __syncthreads();
+  const int n_sat = sm.nsat;
+  const float rel = static_cast<float>(d / 32 + 16) * 2.4e-7f;  // float32 error of both values being compared
+  for (int s = 0; s < n_sat; ++s) {
+    const int code = sm.sat[s];
+    const bool want_same = (code & 1) != 0;
+    const int tt = code >> 1, tile = tt >> 2, slot = tt & 3;
+    const int len = tile < my_tile ? 32 : 64;  // column view: 32-row quarters; row view: 64-column halves
+    const int j0 = tile * tc::BN + slot * len;
+    const int per = len / NW;                  // candidates per warp
+    const int64_t jq = static_cast<int64_t>(j0) + warp * per + lane;
+    const bool ok = lane < per && jq < B && jq != row;
+    const bool want = ok && ((__ldg(&labels[ok ? jq : 0]) == la) == want_same);
+    unsigned wm = __ballot_sync(0xffffffffu, want);
+    float myf = want_same ? -1.f : kBig;       // "not a candidate"
+    while (wm) {
+      int l[4], jj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        l[u] = wm ? __ffs(wm) - 1 : l[0];
+        if (wm) wm &= wm - 1;
+        jj[u] = j0 + warp * per + l[u];
+      }
+      float f4[4];
+      warp_d2_f32x4(emb, d, row, jj, lane, f4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane == l[u]) myf = f4[u];
+    }
+    if (lane < per) sm.f[warp * per + lane] = myf;
+    __syncthreads();
+    const float f0 = lane < len ? sm.f[lane] : (want_same ? -1.f : kBig);
+    const float f1 = lane + 32 < len ? sm.f[lane + 32] : (want_same ? -1.f : kBig);
+    float best = want_same ? fmaxf(f0, f1) : fminf(f0, f1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = want_same ? fmaxf(best, other) : fminf(best, other);
+    }
+    const float lim = want_same ? best - best * rel - 1e-30f : best + best * rel + 1e-30f;
+    const bool v0 = want_same ? f0 >= 0.f : f0 < 1e38f, v1 = want_same ? f1 >= 0.f : f1 < 1e38f;
+    const unsigned m0 = __ballot_sync(0xffffffffu, v0 && (want_same ? f0 >= lim : f0 <= lim));
+    const unsigned m1 = __ballot_sync(0xffffffffu, v1 && (want_same ? f1 >= lim : f1 <= lim));
+    int n_surv = 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      unsigned mm = h ? m1 : m0;
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if ((n_surv++ % NW) == warp) {  // survivors round-robin over the warps
+          const int ci = j0 + h * 32 + src;
+          const double d2 = exact_d2(emb, d, row, ci, lane);
+          if (want_same) bh_update_max(pos, d2, ci);
+          else bh_update_min(neg, d2, ci);
+        }
+      }
+    }
+    __syncthreads();  // sm.f is rewritten by the next slot
+  }
+  // merge the warps' picks ((d2, index) order: associative and commutative, so the result is deterministic)
+  if (lane == 0) {
+    sm.d2[0][warp] = pos.d2; sm.idx[0][warp] = pos.idx;
+    sm.d2[1][warp] = neg.d2; sm.idx[1][warp] = neg.idx;
+  }
+  __syncthreads();
+  BhPick P{-1.0, -1}, N{1e300, -1};
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    if (sm.idx[0][w] >= 0) bh_update_max(P, sm.d2[0][w], sm.idx[0][w]);
+    if (sm.idx[1][w] >= 0) bh_update_min(N, sm.d2[1][w], sm.idx[1][w]);
+  }
+  if (N.idx < 0) {  // block-uniform; degenerate batch without any other label
+    __syncthreads();
+    if (warp == 0) {
+      N = bh_row_maximum(emb, B, d, row, lane);
+      if (lane == 0) { sm.d2[1][0] = N.d2; sm.idx[1][0] = N.idx; }
+    }
+    __syncthreads();
+    N = BhPick{sm.d2[1][0], sm.idx[1][0]};
+  }
+  if (warp < 4) {  // outputs + the four gradient terms, one per warp
+    const double hinge = bh_finish<kGrad>(emb, d, B, row, P, N, margin, squared, soft, hp_idx, hn_idx, hp_out, hn_out,
+                                          coef, gloss, gemb, lane, warp);
+    if (warp == 0 && lane == 0) hinge_all[row] = hinge;
+  }
+  __syncthreads();  // shared state is reused by the next anchor
+}
+
+// hinge_all[0..B) -> loss, in a fixed order (deterministic), by the calling block
+template <int NW>
+__device__ __forceinline__ void bh_block_mean(const double* __restrict__ hinge_all, int64_t B, double* s_red,
+                                              float* __restrict__ loss) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double tot = 0.0;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) tot += __ldcg(&hinge_all[i]);
+  tot = warp_sum(tot);
+  if (lane == 0) s_red[warp] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int w = 0; w < NW; ++w) sum += s_red[w];
+    loss[0] = static_cast<float>(sum / static_cast<double>(B));
+  }
+}
+
 template <bool kGrad>
 __global__ void __launch_bounds__(FS_WARPS * 32)
 batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
@@ -836,152 +1024,15 @@ batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __
                                 double* __restrict__ hinge_all, const int32_t* __restrict__ work_list,
                                 unsigned* __restrict__ counters, float* __restrict__ loss,
                                 const float* __restrict__ gloss, float* __restrict__ gemb) {
-  __shared__ float s_bp[FS_WARPS], s_bn[FS_WARPS];
-  __shared__ double s_d2[2][FS_WARPS];
-  __shared__ int s_idx[2][FS_WARPS];
-  __shared__ int s_nsat;
-  __shared__ int s_sat[2 * 128];
-  __shared__ float s_f[64];
+  __shared__ BhBlockShared<FS_WARPS> sm;
   __shared__ double s_red[FS_WARPS];
   __shared__ bool s_last;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned n_work = *reinterpret_cast<volatile unsigned*>(&counters[0]);
-  const int n_cand = tiles_n * BH_SLOTS;  // <= 128: the records live in warps 0..3
-  for (unsigned k = blockIdx.x; k < n_work; k += gridDim.x) {
-    const int64_t row = work_list[k];
-    const int my_tile = static_cast<int>(row / tc::BM);
-    const BhCand* mine = cand + row * n_cand;
-    const float na = norms[row];
-    const int32_t la = labels[row];
-    const int t = warp * 32 + lane;
-    float4 v = make_float4(-kBig, -kBig, kBig, kBig);
-    if (t < n_cand && ((t & 3) < 2 || (t >> 2) < my_tile)) v = __ldcg(reinterpret_cast<const float4*>(mine + t));
-    float bp = v.x, bn = v.z;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
-      bn = fminf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
-    }
-    if (lane == 0) { s_bp[warp] = bp; s_bn[warp] = bn; }
-    if (threadIdx.x == 0) s_nsat = 0;
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < FS_WARPS; ++w) { bp = fmaxf(bp, s_bp[w]); bn = fminf(bn, s_bn[w]); }
-    const BhThr thr = bh_thresholds(na, bp, bn, band_c);
-    const bool cp1 = bh_valid(v.x) && v.x >= thr.p, cp2 = bh_valid(v.y) && v.y >= thr.p;
-    const bool cn1 = bh_valid(v.z) && v.z <= thr.n, cn2 = bh_valid(v.w) && v.w <= thr.n;
-    const int ip = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.x) & 0x7Fu);
-    const int in = (t >> 2) * tc::BN + static_cast<int>(__float_as_uint(v.z) & 0x7Fu);
-    BhPick pos{-1.0, -1}, neg{1e300, -1};
-    // entries of unsaturated slots: exact, one by one
-    unsigned m = __ballot_sync(0xffffffffu, cp1 && !cp2);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int ci = __shfl_sync(0xffffffffu, ip, src);
-      bh_update_max(pos, exact_d2(emb, d, row, ci, lane), ci);
-    }
-    m = __ballot_sync(0xffffffffu, cn1 && !cn2);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int ci = __shfl_sync(0xffffffffu, in, src);
-      bh_update_min(neg, exact_d2(emb, d, row, ci, lane), ci);
-    }
-    // saturated slots (second entry inside the band): queued for the whole block
-    if (cp2) s_sat[atomicAdd(&s_nsat, 1)] = t * 2 + 1;
-    if (cn2) s_sat[atomicAdd(&s_nsat, 1)] = t * 2;
-    __syncthreads();
-    const int n_sat = s_nsat;
-    const float rel = static_cast<float>(d / 32 + 16) * 2.4e-7f;  // float32 error of both values being compared
-    for (int s = 0; s < n_sat; ++s) {
-      const int code = s_sat[s];
-      const bool want_same = (code & 1) != 0;
-      const int tt = code >> 1, tile = tt >> 2, slot = tt & 3;
-      const int len = tile < my_tile ? 32 : 64;  // column view: 32-row quarters; row view: 64-column halves
-      const int j0 = tile * tc::BN + slot * len;
-      const int per = len / FS_WARPS;            // candidates per warp: 8 or 16
-      const int64_t jq = static_cast<int64_t>(j0) + warp * per + lane;
-      const bool ok = lane < per && jq < B && jq != row;
-      const bool want = ok && ((__ldg(&labels[ok ? jq : 0]) == la) == want_same);
-      unsigned wm = __ballot_sync(0xffffffffu, want);
-      float myf = want_same ? -1.f : kBig;       // "not a candidate"
-      while (wm) {
-        int l[4], jj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          l[u] = wm ? __ffs(wm) - 1 : l[0];
-          if (wm) wm &= wm - 1;
-          jj[u] = j0 + warp * per + l[u];
-        }
-        float f4[4];
-        warp_d2_f32x4(emb, d, row, jj, lane, f4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (lane == l[u]) myf = f4[u];
-      }
-      if (lane < per) s_f[warp * per + lane] = myf;
-      __syncthreads();
-      const float f0 = lane < len ? s_f[lane] : (want_same ? -1.f : kBig);
-      const float f1 = lane + 32 < len ? s_f[lane + 32] : (want_same ? -1.f : kBig);
-      float best = want_same ? fmaxf(f0, f1) : fminf(f0, f1);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = want_same ? fmaxf(best, other) : fminf(best, other);
-      }
-      const float lim = want_same ? best - best * rel - 1e-30f : best + best * rel + 1e-30f;
-      const bool v0 = want_same ? f0 >= 0.f : f0 < 1e38f, v1 = want_same ? f1 >= 0.f : f1 < 1e38f;
-      const unsigned m0 = __ballot_sync(0xffffffffu, v0 && (want_same ? f0 >= lim : f0 <= lim));
-      const unsigned m1 = __ballot_sync(0xffffffffu, v1 && (want_same ? f1 >= lim : f1 <= lim));
-      int n_surv = 0;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        unsigned mm = h ? m1 : m0;
-        while (mm) {
-          const int src = __ffs(mm) - 1;
-          mm &= mm - 1;
-          if ((n_surv++ % FS_WARPS) == warp) {  // survivors round-robin over the warps
-            const int ci = j0 + h * 32 + src;
-            const double d2 = exact_d2(emb, d, row, ci, lane);
-            if (want_same) bh_update_max(pos, d2, ci);
-            else bh_update_min(neg, d2, ci);
-          }
-        }
-      }
-      __syncthreads();  // s_f is rewritten by the next slot
-    }
-    // merge the four warps' picks ((d2, index) order: associative and commutative, so the result is deterministic)
-    if (lane == 0) {
-      s_d2[0][warp] = pos.d2; s_idx[0][warp] = pos.idx;
-      s_d2[1][warp] = neg.d2; s_idx[1][warp] = neg.idx;
-    }
-    __syncthreads();
-    BhPick P{-1.0, -1}, N{1e300, -1};
-#pragma unroll
-    for (int w = 0; w < FS_WARPS; ++w) {
-      if (s_idx[0][w] >= 0) bh_update_max(P, s_d2[0][w], s_idx[0][w]);
-      if (s_idx[1][w] >= 0) bh_update_min(N, s_d2[1][w], s_idx[1][w]);
-    }
-    if (N.idx < 0) {  // block-uniform; degenerate batch without any other label
-      __syncthreads();
-      if (warp == 0) {
-        N = bh_row_maximum(emb, B, d, row, lane);
-        if (lane == 0) { s_d2[1][0] = N.d2; s_idx[1][0] = N.idx; }
-      }
-      __syncthreads();
-      N = BhPick{s_d2[1][0], s_idx[1][0]};
-    }
-    if (warp < 4) {  // outputs + the four gradient terms, one per warp
-      const double hinge = bh_finish<kGrad>(emb, d, B, row, P, N, margin, squared, soft, hp_idx, hn_idx, hp_out, hn_out,
-                                            coef, gloss, gemb, lane, warp);
-      if (warp == 0 && lane == 0) hinge_all[row] = hinge;
-    }
-    __syncthreads();  // shared state is reused by the next anchor
-  }
+  for (unsigned k = blockIdx.x; k < n_work; k += gridDim.x)
+    bh_block_resolve<kGrad, FS_WARPS>(sm, emb, labels, norms, cand, B, d, tiles_n, margin, squared, soft, band_c,
+                                      work_list[k], hp_idx, hn_idx, hp_out, hn_out, coef, hinge_all, gloss, gemb);
   // ---- mean over all anchors, in a fixed order, by the last WORKING block (blocks without an anchor leave at
-  // once: with every block taking part, the 592 fences + atomics on one word were most of this kernel's ~15 us
-  // when the list is short) -- or by block 0 when the list is empty
+  // once) -- or by block 0 when the list is empty
   const unsigned n_working = n_work < gridDim.x ? n_work : gridDim.x;
   if (blockIdx.x >= n_working && !(n_working == 0 && blockIdx.x == 0)) return;
   if (threadIdx.x == 0) {
@@ -995,15 +1046,8 @@ batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __
   __syncthreads();
   if (s_last) {
     __threadfence();
-    double tot = 0.0;
-    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) tot += __ldcg(&hinge_all[i]);
-    tot = warp_sum(tot);
-    if (lane == 0) s_red[warp] = tot;
-    __syncthreads();
+    bh_block_mean<FS_WARPS>(hinge_all, B, s_red, loss);
     if (threadIdx.x == 0) {
-      double sum = 0.0;
-      for (int w = 0; w < FS_WARPS; ++w) sum += s_red[w];
-      loss[0] = static_cast<float>(sum / static_cast<double>(B));
       counters[0] = 0;  // re-armed for the next call on this workspace
       counters[1] = 0;
     }

@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round-2 profile collection, run ON the GPU box (under gpurun): launch lists + `ncu --set full` captures of the hot
+# kernels.  Only text digests are left under gpurun_out/ (the .ncu-rep files exceed the 64 MiB copy-back limit):
+#   r02_launches_bench.csv / r02_launches_mining.csv   per-launch device time (cold cache, serialised: compare SHARES)
+#   r02_ncu_summary.md                                  tools/ncu_summary.py over every capture
+#   r02_sass_hot_<kernel>.txt                           tools/ncu_sass_hot.py: opcode mix, stall reasons, hottest lines
+set -u
+T=/tmp/en_prof; mkdir -p $T gpurun_out
+NCU="ncu --clock-control none"
+$NCU --metrics gpu__time_duration.sum -c 700 --csv --log-file gpurun_out/r02_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --skip-knn --skip-cpu > /dev/null 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_mining.csv \
+    python tools/profile_step.py mining > /dev/null 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_smallq.csv \
+    python tools/profile_step.py smallq > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:"dist_gemm_kernel|batch_hard_finalize|split_planes" -s 8 -c 4 -o $T/bh \
+    python tools/profile_step.py triplet > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:"pair_tc_kernel|pair_finish|collect_positives" -c 8 -o $T/pair \
+    python tools/profile_step.py pairbwd > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:"knn_smallq|knn_stream" -c 6 -o $T/smallq \
+    python tools/profile_step.py smallq > /dev/null 2>&1
+$NCU --set full -k regex:"l2norm|row_dist" -s 4 -c 4 -o $T/rowwise python tools/profile_step.py rowwise > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:"EpMine" -c 2 -o $T/mine python tools/profile_step.py mining > /dev/null 2>&1
+python tools/ncu_summary.py $T/bh.ncu-rep $T/pair.ncu-rep $T/smallq.ncu-rep $T/rowwise.ncu-rep $T/mine.ncu-rep \
+    > gpurun_out/r02_ncu_summary.md 2> gpurun_out/r02_ncu_summary.err
+hot() {  # <rep> <kernel id (1-based)> <name>
+  ncu -i $T/$1.ncu-rep --page source --csv --kernel-id :::$2 > $T/src.csv 2>/dev/null
+  python tools/ncu_sass_hot.py $T/src.csv 25 > gpurun_out/r02_sass_hot_$3.txt 2>&1
+}
+hot bh 2 bh_gemm; hot bh 3 bh_finalize_fast; hot bh 4 bh_finalize_slow
+hot pair 2 pair_tc_batch_all; hot pair 6 pair_tc_contrastive
+hot smallq 3 knn_smallq_q8; hot mine 1 mine_count
+ls -la $T gpurun_out | tail -30
