@@ -53,6 +53,11 @@ SIGNATURES = {
     "en_batch_hard_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "en_batch_hard_fwd_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "en_batch_hard_bwd": (c_int, [P, c_int64, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "en_bh_host_pipe_device_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "en_bh_host_pipe_create": (c_int, [c_int64, c_int, c_float, c_int, c_int, c_int, P, c_size_t, ctypes.POINTER(c_void_p)]),
+    "en_bh_host_pipe_submit": (c_int, [P, P, P, P, P, P, P, ctypes.POINTER(c_int64)]),
+    "en_bh_host_pipe_wait": (c_int, [P, c_int64]),
+    "en_bh_host_pipe_destroy": (c_int, [P]),
     "en_ws_bytes_batch_all": (c_size_t, [c_int64, c_int, c_int]),
     "en_batch_all_fwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, c_size_t, P]),
     "en_batch_all_bwd": (c_int, [P, P, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, c_size_t, P]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libembeddingnet_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["core.cu", "rowwise.cu", "pairwise.cu", "batch_losses.cu", "pair_tc.cu", "knn.cu", "head.cu", "mine_bank.cu", "comm.cu"]
+SOURCES = ["core.cu", "rowwise.cu", "pairwise.cu", "batch_losses.cu", "pair_tc.cu", "knn.cu", "head.cu", "mine_bank.cu", "comm.cu", "host_pipe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

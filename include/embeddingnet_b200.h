@@ -147,6 +147,27 @@ int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int
                       const float* hp, const float* hn, const float* coef, const float* gloss, float* gemb,
                       void* stream);
 
+/* ---------------------------------------------------------------- host-buffer batch-hard step (pipelined)
+ * The loss callable of embedding_net/losses_and_accuracies.py:14-44 for a caller whose batch lives in HOST memory
+ * (NumPy arrays, a data loader's pinned staging buffers): embeddings (B, d) + labels (B,) in, loss (1 float) and
+ * d loss / d embeddings (B, d) out, every pointer below a HOST pointer.  A pipe owns `depth` (1..8) slots carved
+ * from the caller's device block (en_bh_host_pipe_device_bytes, 256-byte aligned), three internal streams
+ * (upload | compute | download) and one CUDA graph of the en_batch_hard_fwd_bwd kernels per slot, so consecutive
+ * steps overlap: the PCIe link, which bounds this call, stays busy in both directions.
+ *   submit: enqueues one step and returns its ticket; blocks only when all `depth` slots are still in flight
+ *           (then it waits for the oldest).  hp_idx_host / hn_idx_host (B,) int32 are optional (NULL = not wanted).
+ *           Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister); pageable memory is accepted
+ *           but serialises the copies.  They must stay valid and untouched until wait(ticket) returns.
+ *   wait:   returns once that step's outputs are in host memory.
+ * One pipe is driven by one thread at a time, with the device that was current at creation current. */
+size_t en_bh_host_pipe_device_bytes(int64_t B, int d, int depth);
+int en_bh_host_pipe_create(int64_t B, int d, float margin, int squared, int soft, int depth, void* device_mem,
+                           size_t device_bytes, void** pipe_out);
+int en_bh_host_pipe_submit(void* pipe, const float* emb_host, const int32_t* labels_host, float* loss_host,
+                           float* grad_host, int32_t* hp_idx_host, int32_t* hn_idx_host, int64_t* ticket_out);
+int en_bh_host_pipe_wait(void* pipe, int64_t ticket);
+int en_bh_host_pipe_destroy(void* pipe);
+
 /* Batch-all triplet loss: sum over valid (i,j,k) of max(D_ij - D_ik + margin, 0) / #{terms > 1e-16}.
  * out[0] = loss, out[1] = fraction of positive triplets.  max_positives >= largest class size - 1 (<= 64).
  * stats (3 doubles, device): hinge sum, #positive terms, #valid triplets -- kept for the backward. */

@@ -159,6 +159,51 @@ def test_fused_step_matches_separate_fwd_and_bwd():
         assert rel_err(g1.cpu().numpy(), g) < 1e-4
 
 
+def test_host_buffer_pipeline_matches_the_oracle_step_by_step():
+    """en_bh_host_pipe_*: host pointers in and out, several steps in flight in different slots.  Every step carries
+    DIFFERENT data (a slot mix-up or a premature slot reuse would be visible), loss / gradient / selected indices
+    are compared with the float64 oracle per step; pinned tensors and pageable NumPy arrays both work."""
+    from embeddingnet_b200.fused import BatchHardHostPipeline
+
+    n_steps, depth = 7, 3
+    batches = []
+    for s in range(n_steps):
+        x, lab = make_batch(24, 6, 128, True, s % 2 == 1, noise=0.4 + 0.05 * s)
+        batches.append((np.roll(x, s, axis=1).copy(), lab))
+    B, d = batches[0][0].shape
+    pipe = BatchHardHostPipeline(B, d, margin=0.5, depth=depth)
+    pin = BatchHardHostPipeline.pinned
+    for pinned in (True, False):
+        ins, outs, tickets = [], [], []
+        for x, lab in batches:
+            if pinned:
+                e_h, l_h = pin((B, d)), pin((B,), torch.int32)
+                e_h.copy_(torch.from_numpy(x))
+                l_h.copy_(torch.from_numpy(lab.astype(np.int32)))
+                out = (pin((1,)), pin((B, d)), pin((B,), torch.int32), pin((B,), torch.int32))
+            else:
+                e_h, l_h = x.astype(np.float32), lab.astype(np.int32)
+                out = (np.zeros(1, np.float32), np.zeros((B, d), np.float32), np.zeros(B, np.int32), np.zeros(B, np.int32))
+            ins.append((e_h, l_h))
+            outs.append(out)
+            tickets.append(pipe.submit(e_h, l_h, *out))
+        assert tickets == list(range(tickets[0], tickets[0] + n_steps))
+        for t in reversed(tickets):  # any order; early tickets were already waited for by slot reuse
+            pipe.wait(t)
+        for (x, lab), out in zip(batches, outs):
+            loss, grad, hp, hn = (np.asarray(o) for o in out)
+            ref = O.batch_hard(lab, x, 0.5, False, False)
+            _, g = O.batch_hard_grad(lab, x, 0.5, False, False)
+            assert abs(float(loss[0]) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+            assert rel_err(grad, g) < 1e-4
+            assert np.array_equal(hp, ref["hp_idx"]) and np.array_equal(hn, ref["hn_idx"])
+    with pytest.raises(ValueError):
+        pipe.wait(10 ** 6)
+    pipe.close()
+    with pytest.raises(ValueError):
+        BatchHardHostPipeline(B, d, depth=99)
+
+
 def test_batch_hard_edge_cases():
     from embeddingnet_b200 import losses_and_accuracies as lac
 

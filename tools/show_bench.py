@@ -7,7 +7,7 @@ print("value %.3g emb/s  ms/step %.4f  launches/step %s" % (l["value"], l["ms_pe
 r = l["roofline"]
 print("gemm: %.1f TF/s frac %.3f kernel_ms %.4f share %.2f" % (r["achieved"], r["frac"], r["kernel_ms"], r["share_of_step"]))
 e = l["e2e"]
-print("e2e %.3g emb/s (%.4f ms)  autograd %.4f ms  serial %.4f ms" % (e["value"], e["ms_per_step"], e["autograd_api"]["ms_per_step"], e["serial"]["ms_per_step"]))
+print("e2e %.3g emb/s (%.4f ms)  python pipeline %.4f ms  autograd %.4f ms  serial %.4f ms" % (e["value"], e["ms_per_step"], e.get("python_pipeline", {}).get("ms_per_step", float("nan")), e["autograd_api"]["ms_per_step"], e["serial"]["ms_per_step"]))
 for k, v in l.get("other_configs", {}).items():
     if k == "rowwise_hbm":
         for tag, rec in v.items():
