@@ -21,8 +21,9 @@ namespace en {
 size_t pair_tc_ws_bytes(int64_t B, int d);
 int pair_tc_partials_per_row(int64_t B, int d);
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
-                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
-                   PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, int cap,
+                   const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
+                   size_t ws_bytes, cudaStream_t st);
 int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, int cap, int squared, const float* pos_d,
                    const int32_t* pos_j, const int32_t* pos_n, const int32_t* pos_cnt, const double* stats,
                    const float* gloss, float* gemb, cudaStream_t st);
@@ -30,7 +31,16 @@ int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, 
 namespace {
 
 constexpr float kBig = 3.0e38f;
-constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps the positives lists in registers / 2 KB of smem per warp
+constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps eight positives per anchor in registers / scratch per pass
+// list capacity of the tensor-core pair kernel for a class bound: 8, or the next multiple of 8 (at most 64) --
+// longer lists are walked eight slots per pass over a tile (pair_tc_kernel<..., kBig>)
+static int tc_list_cap(int max_positives) { return max_positives <= kTcBwdMaxPos ? kTcBwdMaxPos : (max_positives + 7) / 8 * 8; }
+// EN_BATCH_ALL_CUDA_CORE=1 sends classes with more than 8 positives per anchor to the CUDA-core tile kernel of
+// round 1 (kept as an independent implementation for the tests to compare against)
+static bool cuda_core_bwd_requested() {
+  const char* e = getenv("EN_BATCH_ALL_CUDA_CORE");
+  return e && e[0] == '1';
+}
 
 // warp-cooperative exact squared distance between rows i and j (float64 accumulate); result in every lane
 // (not inlined: it is called from many sites of kernels whose warps run the code once, where instruction fetch,
@@ -1886,7 +1896,7 @@ size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
   const size_t fwd = operand_bytes(B, d) + pos_bytes(B, max_positives) +
                      align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
-  const size_t bwd = pos_bytes(B, kTcBwdMaxPos) +
+  const size_t bwd = pos_bytes(B, tc_list_cap(max_positives)) +
                      align_up(static_cast<size_t>(B) * pair_tc_partials_per_row(B, d) * sizeof(PairPartial)) +
                      pair_tc_ws_bytes(B, d);
   return fwd > bwd ? fwd : bwd;
@@ -1957,8 +1967,8 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
     return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   Workspace w(ws, ws_bytes);
-  const bool tensor = max_positives <= kTcBwdMaxPos;
-  const int cap = tensor ? kTcBwdMaxPos : max_positives;
+  const bool tensor = max_positives <= kTcBwdMaxPos || !cuda_core_bwd_requested();
+  const int cap = tensor ? tc_list_cap(max_positives) : max_positives;
   PosLists pl = take_pos(w, B, cap);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
@@ -1971,12 +1981,12 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
     // row-sum term and the sparse positive pairs and applies gloss / #positive triplets
     void* rest = w.base + w.off;
     PairTcFinish fin;
-    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, nullptr,
-                                nullptr, gemb, &fin, rest, ws_bytes - w.off, st))
+    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, cap,
+                                nullptr, nullptr, gemb, &fin, rest, ws_bytes - w.off, st))
       return rc;
     return pair_tc_finish(fin, emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, st);
   } else {
-    // classes with more than 8 positives per anchor: CUDA-core tile kernel
+    // EN_BATCH_ALL_CUDA_CORE=1: CUDA-core tile kernel (independent implementation, for comparison)
     EN_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(B) * d * 4, st));
     CoefBatchAll ba{pl.pos_d, pl.pos_n, cap, margin, squared, 0.0};
     const unsigned blocks = static_cast<unsigned>((B + PT - 1) / PT);
@@ -2006,8 +2016,8 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   if (!ws || ws_bytes < en_ws_bytes_batch_all(B, d, max_positives))
     return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
-  if (max_positives > kTcBwdMaxPos) {
-    // large classes: forward kernel, then the CUDA-core backward (needs a device gloss)
+  if (max_positives > kTcBwdMaxPos && cuda_core_bwd_requested()) {
+    // comparison path: forward kernel, then the CUDA-core backward (needs a device gloss)
     EN_REQUIRE(gloss != nullptr, "en_batch_all_fwd_bwd: gloss is required when max_positives > %d", kTcBwdMaxPos);
     if (overflow) EN_CUDA(cudaMemsetAsync(overflow, 0, 4, st));  // the forward pass below checks synchronously
     if (int rc = en_batch_all_fwd(emb, labels, B, d, margin, squared, max_positives, out, stats, ws, ws_bytes, stream))
@@ -2015,7 +2025,7 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
     return en_batch_all_bwd(emb, labels, B, d, margin, squared, max_positives, stats, gloss, gemb, ws, ws_bytes, stream);
   }
   Workspace w(ws, ws_bytes);
-  const int cap = kTcBwdMaxPos;
+  const int cap = tc_list_cap(max_positives);
   PosLists pl = take_pos(w, B, cap);
   const int ppr = pair_tc_partials_per_row(B, d);
   PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * ppr);
@@ -2028,7 +2038,7 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
   void* rest = w.base + w.off;
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, nullptr,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, cap, nullptr,
                               partial, gemb, &fin, rest, ws_bytes - w.off, st))
     return rc;
   if (int rc = launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, pl.pos_n, B, 0, out, stats, st, pl.status))
@@ -2083,7 +2093,7 @@ int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t
     return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_bwd: workspace too small");
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, nullptr, gemb,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, 0, nullptr, nullptr, gemb,
                               &fin, ws, ws_bytes, as_stream(stream)))
     return rc;
   return pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb,
@@ -2106,7 +2116,7 @@ int en_contrastive_allpairs_fwd_bwd(const float* emb, const int32_t* labels, int
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
   void* rest = w.base + w.off;
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, partial, gemb,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, 0, nullptr, partial, gemb,
                               &fin, rest, ws_bytes - w.off, st))
     return rc;
   if (int rc = pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb, st))

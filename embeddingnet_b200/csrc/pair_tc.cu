@@ -59,7 +59,8 @@ constexpr int EPI_Q = 4;                // column chunks (32 wide) per tile row 
 constexpr int EPI_WARPS = 4 * EPI_Q;
 constexpr int CTRL_WARPS = 3;            // warp 0: GEMM1 operand TMA, warp 1: MMA issuer, warp 2: E^T (GEMM2) TMA
 constexpr int NUM_THREADS = 32 * (CTRL_WARPS + EPI_WARPS);
-constexpr int MAXP = 8;                 // positives per anchor handled by this kernel
+constexpr int MAXP = 8;                 // positives per anchor held in registers per pass over a tile
+constexpr int MAXP_BIG = 64;            // kBig: lists of up to 64 positives, taken eight at a time (cap / 8 passes)
 constexpr int WARP_SCR = 128 + 128 + 32 * MAXP * 4;  // per warp, for its 32 columns: norms | labels | positives lists
 constexpr int SMEM_BYTES = G1_STAGES * G1_STAGE_BYTES + ET_STAGES * ET_STAGE_BYTES + 256 + EPI_WARPS * WARP_SCR +
                            BM * EPI_Q * 4;
@@ -83,9 +84,10 @@ struct Bars {
 struct Params {
   const int32_t* labels;
   const float* norms;
-  const float* pos_d;     // [B][MAXP] (batch-all)
+  const float* pos_d;     // [B][cap] (batch-all)
   const int32_t* pos_n;   // [B]
-  int32_t* pos_cnt;       // [B][MAXP] out: active negatives per (anchor, positive slot)
+  int32_t* pos_cnt;       // [B][cap] out: active negatives per (anchor, positive slot)
+  int cap;                // list capacity: MAXP, or a multiple of 8 up to MAXP_BIG (kBig)
   float* gemb;            // out: -(C.E) over the centred rows, unscaled by gloss; ZEROED by the caller when n_jparts > 1
                           // (items that share rows add into it: two addends per element commute, still deterministic)
   float* rowsum;          // out [B], zeroed by the caller: sum_k C_ik (what the MMAs saw); pair_finish_kernel turns
@@ -136,7 +138,11 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 // kMode: 0 = batch-all, 1 = contrastive (template parameter so that each instantiation carries only its own
 // coefficient code: both together overflowed the instruction cache, ncu r1: stall_no_instruction 5.4 / issue).
 // kLoss: also accumulate the forward loss.  kG1Bf16: GEMM1 on BF16 planes (backward-only contrastive).
-template <int kMode, bool kLoss, bool kG1Bf16>
+// kBig (batch-all only): classes with more than MAXP positives per anchor.  The positives lists (row anchor's and
+// column anchors') are taken eight at a time: cap / 8 passes over the tile's S values, the per-element triplet counts
+// accumulate in registers, the per-(anchor, positive) counts in a shared-memory table that takes the place of the
+// second E^T stage (the epilogue is several times longer than GEMM2 here, so GEMM2's operand ring can be one deep).
+template <int kMode, bool kLoss, bool kG1Bf16, bool kBig = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const __grid_constant__ CUtensorMap tm_et_hi, const __grid_constant__ CUtensorMap tm_et_lo,
@@ -151,6 +157,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.tiles * p.n_wide * p.n_jparts;
+  static_assert(!kBig || kMode == 0, "kBig is a batch-all variant");
+  constexpr int kEtStages = kBig ? 1 : ET_STAGES;
+  uint32_t* slot_cnt = reinterpret_cast<uint32_t*>(et + ET_STAGE_BYTES);  // kBig: [MAXP_BIG][BM] active negatives
+  static_assert(MAXP_BIG * BM * 4 <= ET_STAGE_BYTES, "the slot-count table replaces one E^T stage");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_hi);
@@ -213,7 +223,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const int rowc = (it.wide * NSUB + sub) * DN;
               ptx::tma_load_2d(&tm_et_hi, &bars->et_full[es], st, J * BN + kb2 * JB, rowc);
               ptx::tma_load_2d(&tm_et_lo, &bars->et_full[es], st + TILE_BYTES, J * BN + kb2 * JB, rowc);
-              if (++es == ET_STAGES) { es = 0; eph ^= 1; }
+              if (++es == kEtStages) { es = 0; eph ^= 1; }
             }
           }
         }
@@ -286,7 +296,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 ptx::mma_bf16_ts(acc, a_h, e_hi + koff, idesc16, 1);
               }
               ptx::mma_commit(&bars->et_empty[es]);
-              if (++es == ET_STAGES) { es = 0; eph ^= 1; }
+              if (++es == kEtStages) { es = 0; eph ^= 1; }
             }
           }
           ptx::mma_commit(&bars->c_empty);
@@ -313,17 +323,26 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       float pi[MAXP];
       float cnt_s[MAXP];  // counts as floats (exact far beyond the 4096 columns of an item): FSET + FADD per slot
       int npi = 0;
+      unsigned long long np_big = 0;  // kBig: this thread's share of the positive-triplet count
       if (kMode == 0) {
         npi = row_ok ? p.pos_n[row] : 0;
+        if (!kBig) {
 #pragma unroll
-        for (int s = 0; s < MAXP; ++s) {
-          pi[s] = (s < npi) ? p.pos_d[row * MAXP + s] + p.margin : -INFINITY;
-          cnt_s[s] = 0.f;
+          for (int s = 0; s < MAXP; ++s) {
+            pi[s] = (s < npi) ? p.pos_d[row * MAXP + s] + p.margin : -INFINITY;
+            cnt_s[s] = 0.f;
+          }
         }
       }
       // loss terms and per-slot counts are reported by the first column group only (the tiles are visited once per
       // 256 gradient columns): the other groups skip that arithmetic
       const bool full = it.wide == 0;
+      if (kBig) {
+        // the four warps that share a row (one per column chunk) clear its slot counts, a quarter each
+        if (full)
+          for (int s = cq; s < p.cap; s += EPI_Q) slot_cnt[s * BM + quarter * 32 + lane] = 0u;
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+      }
       double rowsum = 0.0, loss_sum = 0.0;
       for (int J = it.j0; J < it.j1; ++J, ++e_it) {
         ptx::mbar_wait(&bars->s_full, e_it & 1);
@@ -342,7 +361,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           const bool ok = cc < p.B;
           wf[lane] = ok ? __ldg(&p.norms[cc]) : 0.f;
           wi[lane] = ok ? __ldg(&p.labels[cc]) : -2;
-          if (kMode == 0) {
+          if (kMode == 0 && !kBig) {
             const int npk = ok ? p.pos_n[cc] : 0;
 #pragma unroll
             for (int s = 0; s < MAXP; ++s)
@@ -350,7 +369,135 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           }
         }
         __syncwarp();
-        {
+        if constexpr (kBig) {
+          // ---- lists longer than eight: cap / 8 passes over the 32 S values of this thread.  Pass g holds slots
+          // 8g .. 8g+7 of the row anchor's list in registers and of the 32 column anchors' lists in this warp's
+          // scratch; cntv[j] collects, over the passes, the number of active triplets the pair (row, column j) is the
+          // (anchor, negative) or (negative, anchor) of.  Elements are taken eight per trip of a rolled loop with the
+          // register arrays rotated (as below), so that the code stays small.
+          const int64_t col0 = static_cast<int64_t>(J) * BN + cq * 32;
+          const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
+          const int64_t ccol = col0 + lane;
+          const bool col_ok = ccol < p.B;
+          const int npk = col_ok ? __ldg(&p.pos_n[ccol]) : 0;
+          float cntv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cntv[j] = 0.f;
+          float chunk_loss = 0.f;
+          const int n_groups = p.cap >> 3;
+#pragma unroll 1
+          for (int g = 0; g < n_groups; ++g) {
+            float pi8[8], cs8[8];
+            {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+              if (row_ok && g * 8 < npi) {
+                a = __ldg(reinterpret_cast<const float4*>(p.pos_d + row * p.cap + g * 8));
+                b = __ldg(reinterpret_cast<const float4*>(p.pos_d + row * p.cap + g * 8 + 4));
+              }
+              const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int s = 0; s < 8; ++s) {
+                pi8[s] = (g * 8 + s < npi) ? v[s] + p.margin : -INFINITY;
+                cs8[s] = 0.f;
+              }
+            }
+            __syncwarp();  // the previous pass has read its column thresholds
+            {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+              if (g * 8 < npk) {
+                a = __ldg(reinterpret_cast<const float4*>(p.pos_d + ccol * p.cap + g * 8));
+                b = __ldg(reinterpret_cast<const float4*>(p.pos_d + ccol * p.cap + g * 8 + 4));
+              }
+              const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int s = 0; s < 8; ++s) wpos[lane * MAXP + s] = (g * 8 + s < npk) ? v[s] + p.margin : -INFINITY;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int jj = 0; jj < 32; jj += 8) {
+              float keep[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int j = jj + u;
+                const bool ok = interior || (row_ok && col0 + j < p.B && col0 + j != row);
+                const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
+                const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
+                const bool isneg = ok && wi[j] != la;
+                const float dn = isneg ? (p.squared ? d2 : d2 * rs) : INFINITY;
+                float cnt = 0.f;
+                if (full) {
+#pragma unroll
+                  for (int s = 0; s < 8; ++s) {
+                    const float t = pi8[s] - dn;
+                    const float act = t > 1e-16f ? 1.f : 0.f;
+                    cnt += act;
+                    cs8[s] += act;
+                    if (kLoss) chunk_loss += fmaxf(t, 0.f);
+                  }
+                } else {
+#pragma unroll
+                  for (int s = 0; s < 8; ++s) cnt += (pi8[s] - dn) > 1e-16f ? 1.f : 0.f;
+                }
+                const float4 q0 = *reinterpret_cast<const float4*>(wpos + j * MAXP);
+                const float4 q1 = *reinterpret_cast<const float4*>(wpos + j * MAXP + 4);
+                cnt += ((q0.x - dn > 1e-16f ? 1.f : 0.f) + (q0.y - dn > 1e-16f ? 1.f : 0.f)) +
+                       ((q0.z - dn > 1e-16f ? 1.f : 0.f) + (q0.w - dn > 1e-16f ? 1.f : 0.f)) +
+                       ((q1.x - dn > 1e-16f ? 1.f : 0.f) + (q1.y - dn > 1e-16f ? 1.f : 0.f)) +
+                       ((q1.z - dn > 1e-16f ? 1.f : 0.f) + (q1.w - dn > 1e-16f ? 1.f : 0.f));
+                keep[u] = cntv[u] + cnt;
+              }
+              // rotate both arrays by eight: after four trips they are back in place
+              float wk[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) wk[u] = w[u];
+#pragma unroll
+              for (int i = 0; i < 24; ++i) { w[i] = w[i + 8]; cntv[i] = cntv[i + 8]; }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) { w[24 + u] = wk[u]; cntv[24 + u] = keep[u]; }
+            }
+            if (full) {
+              unsigned tot = 0;
+#pragma unroll
+              for (int s = 0; s < 8; ++s) {
+                const unsigned c = static_cast<unsigned>(cs8[s]);  // exact small integers
+                tot += c;
+                if (c != 0u) atomicAdd(&slot_cnt[(g * 8 + s) * BM + quarter * 32 + lane], c);
+              }
+              np_big += tot;
+            }
+          }
+          // coefficients from the accumulated counts; packing as in the short-list path
+          float chunk_sum = 0.f;
+#pragma unroll 1
+          for (int jj = 0; jj < 32; jj += 8) {
+            float cv8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = jj + u;
+              const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
+              const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
+              cv8[u] = -cntv[u] * cs * (p.squared ? 2.f : rs);  // the count is 0 where the pair is not a negative pair
+            }
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              hw[u] = pack_bf16x2(cv8[2 * u + 1], cv8[2 * u]);
+              const float h0 = __uint_as_float(hw[u] << 16), h1 = __uint_as_float(hw[u] & 0xFFFF0000u);
+              lw[u] = pack_bf16x2(cv8[2 * u + 1] - h1, cv8[2 * u] - h0);
+              const float l0 = __uint_as_float(lw[u] << 16), l1 = __uint_as_float(lw[u] & 0xFFFF0000u);
+              chunk_sum += (h0 + l0) + (h1 + l1);
+            }
+#pragma unroll
+            for (int i = 0; i < 24; ++i) { w[i] = w[i + 8]; cntv[i] = cntv[i + 8]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              w[24 + u] = __uint_as_float(hw[u]);
+              w[28 + u] = __uint_as_float(lw[u]);
+            }
+          }
+          rowsum += static_cast<double>(chunk_sum);
+          if (kLoss) loss_sum += static_cast<double>(chunk_loss);
+        } else {
           const int c = cq;
           const int64_t col0 = static_cast<int64_t>(J) * BN + c * 32;
           const float* wfc = wf;
@@ -460,10 +607,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       // ---- loss partial of this (row, J range, column chunk); only the first column group reports it
       if (kLoss && it.wide == 0 && row_ok) {
         unsigned long long np = 0;
-        if (kMode == 0) {
+        if (kMode == 0 && !kBig) {
 #pragma unroll
           for (int s = 0; s < MAXP; ++s) np += static_cast<unsigned long long>(cnt_s[s]);  // exact integers
         }
+        if (kBig) np = np_big;
         p.partial[(row * p.n_jparts + it.part) * EPI_Q + cq] = PairPartial{loss_sum, np};
       }
       // ---- this item's share of the gradient.  grad_i = rowsum_i (e_i - mu) - (C.E)_i: the kernel leaves the two
@@ -473,6 +621,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       // made every load / atomic of a warp touch 32 different rows: ncu r2, 44 % of the kernel's stall samples.
       rowsum_x[cq * BM + quarter * 32 + lane] = static_cast<float>(rowsum);
       ptx::named_bar_sync(1, EPI_WARPS * 32);
+      if (kBig && it.wide == 0 && row_ok) {
+        // every warp's shared-memory adds of this item are done: the four warps of a row publish a quarter each
+        for (int s = cq; s < npi; s += EPI_Q) {
+          const unsigned c = slot_cnt[s * BM + quarter * 32 + lane];
+          if (c != 0u) atomicAdd(&p.pos_cnt[row * p.cap + s], static_cast<int>(c));
+        }
+      }
       if (it.wide == 0 && cq == 0 && row_ok) {
         float rs = 0.f;
 #pragma unroll
@@ -514,7 +669,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->g_empty);
       ptx::named_bar_sync(1, EPI_WARPS * 32);  // rowsum_x may be rewritten by the next item
-      if (kMode == 0 && it.wide == 0 && row_ok) {
+      if (kMode == 0 && !kBig && it.wide == 0 && row_ok) {
 #pragma unroll
         for (int s = 0; s < MAXP; ++s)
           if (s < npi && cnt_s[s] != 0.f) atomicAdd(&p.pos_cnt[row * MAXP + s], static_cast<int>(cnt_s[s]));
@@ -674,7 +829,8 @@ int pair_tc_partials_per_row(int64_t B, int d) {
   return ptc::geometry(B, d, sms > 0 ? sms : 148).n_jparts * ptc::EPI_Q;
 }
 
-// mode 0 = batch-all (pos_* describe lists with capacity 8), mode 1 = all-pairs contrastive.
+// mode 0 = batch-all (pos_* describe lists with capacity `cap`: 8, or a multiple of 8 up to 64 for large classes),
+// mode 1 = all-pairs contrastive.
 // partial != nullptr: also accumulate the forward loss (PairPartial[B][pair_tc_partials_per_row()]).
 // coef_scale multiplies every pair coefficient (contrastive: 4 / (B (B-1)), batch-all: 1); stats (optional, device):
 // batch-all coefficients are also divided by stats[1] = #positive triplets -- known when the forward already ran;
@@ -682,9 +838,12 @@ int pair_tc_partials_per_row(int64_t B, int d) {
 // gemb receives -(C.E) and `fin` the pointers pair_tc_finish() needs to turn it into the gradient (the caller may
 // reduce the loss partials in between: batch-all's scale 1 / #positive triplets comes out of that reduction).
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
-                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, const double* stats,
-                   PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, int cap,
+                   const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
   if (int rc = check_sm100()) return rc;
+  if (mode == 0 && !(cap == ptc::MAXP || (cap > ptc::MAXP && cap <= ptc::MAXP_BIG && cap % 8 == 0)))
+    return fail(EN_ERR_ARG, "pair kernel: list capacity %d (8, or a multiple of 8 up to %d)", cap, ptc::MAXP_BIG);
   if (!ws || ws_bytes < pair_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair kernel: workspace too small");
   Workspace w(ws, ws_bytes);
   const int sms = device_sm_count();
@@ -718,7 +877,7 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
       tc::make_plane_tmap_bf16(&teh, et_hi, g.rows_t, g.bpad) || tc::make_plane_tmap_bf16(&tel, et_lo, g.rows_t, g.bpad))
     return fail(EN_ERR_DRIVER, "pair kernel: cuTensorMapEncodeTiled failed");
   ptc::Params p;
-  p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt;
+  p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt; p.cap = cap;
   p.gemb = gemb; p.rowsum = rowsum; p.partial = partial; p.B = B; p.d = d;
   p.tiles = g.tiles; p.n_wide = g.n_wide; p.n_jparts = g.n_jparts; p.tiles_per_part = g.tiles_per_part;
   p.kblocks = dpad / (g1_bf16 ? tc::BK16 : tc::BK); p.squared = squared; p.margin = margin; p.coef_scale = coef_scale; p.stats = stats;
@@ -728,18 +887,21 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
   EN_CUDA(cudaMemsetAsync(rowsum, 0, static_cast<size_t>(B) * sizeof(float), st));
   fin->mu = mu;
   fin->rowsum = rowsum;
-#define EN_PAIR_LAUNCH(MODE, LOSS, G1B)                                                                              \
+#define EN_PAIR_LAUNCH(MODE, LOSS, G1B, BIG)                                                                         \
   do {                                                                                                              \
-    EN_CUDA(cudaFuncSetAttribute(ptc::pair_tc_kernel<MODE, LOSS, G1B>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 ptc::SMEM_BYTES));                                                                 \
+    EN_CUDA(cudaFuncSetAttribute(ptc::pair_tc_kernel<MODE, LOSS, G1B, BIG>,                                          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ptc::SMEM_BYTES));                    \
     prof_begin(st);                                                                                                 \
-    ptc::pair_tc_kernel<MODE, LOSS, G1B><<<grid, ptc::NUM_THREADS, ptc::SMEM_BYTES, st>>>(th, tl, teh, tel, p);       \
+    ptc::pair_tc_kernel<MODE, LOSS, G1B, BIG><<<grid, ptc::NUM_THREADS, ptc::SMEM_BYTES, st>>>(th, tl, teh, tel, p);  \
     prof_end(st);                                                                                                   \
   } while (0)
-  if (mode == 0 && partial) EN_PAIR_LAUNCH(0, true, false);
-  else if (mode == 0) EN_PAIR_LAUNCH(0, false, false);
-  else if (partial) EN_PAIR_LAUNCH(1, true, true);
-  else EN_PAIR_LAUNCH(1, false, true);
+  const bool big = mode == 0 && cap > ptc::MAXP;
+  if (big && partial) EN_PAIR_LAUNCH(0, true, false, true);
+  else if (big) EN_PAIR_LAUNCH(0, false, false, true);
+  else if (mode == 0 && partial) EN_PAIR_LAUNCH(0, true, false, false);
+  else if (mode == 0) EN_PAIR_LAUNCH(0, false, false, false);
+  else if (partial) EN_PAIR_LAUNCH(1, true, true, false);
+  else EN_PAIR_LAUNCH(1, false, true, false);
 #undef EN_PAIR_LAUNCH
   EN_LAUNCHED("pair_tc_kernel");
   return EN_OK;

@@ -37,6 +37,15 @@ if what == "pairbwd":
             e = x.clone().requires_grad_(True)
             fn(labels, e).backward()
     torch.cuda.synchronize()
+if what == "ba64":
+    # stress shape of SURVEY 8(d): 64 classes x 64 rows (63 positives per anchor), batch-all loss + gradient
+    raw, labels = synth.make_device(4096, 512, n_classes=64, rows_per_class=64, noise=0.5, relu=True, device=dev)
+    emb = lac.l2_normalize(raw).detach()
+    ba = lac.batch_all_triplet_loss(0.5, max_positives=63)
+    for _ in range(2):
+        e = emb.clone().requires_grad_(True)
+        ba(labels, e).backward()
+    torch.cuda.synchronize()
 if what == "mining":
     # C4-shaped bank mining at reduced size: hardest (label-excluded 1-NN) and semihard (count + select passes)
     n, A = 200_000, 16384
