@@ -1180,13 +1180,21 @@ __device__ __forceinline__ void exact_d2x4(const float* __restrict__ e, int d, i
 // its duration is ONE warp's latency; round 1/2 launch lists: 23 us, more than a third of the distance GEMM it
 // prepares): (1) the label scan, 512 labels per trip with all four 128-bit loads in flight; (2) the distances, four
 // positives per trip.
+// Rows B .. rows_padded-1 (the launch covers them when the lists are allocated for a whole number of 128-row tiles:
+// the tensor-core pair kernel reads the lists of every column of a tile) get empty lists.
 __global__ void collect_positives_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                          int64_t B, int d, int squared, int cap, float* __restrict__ pos_d,
                                          int32_t* __restrict__ pos_j, int32_t* __restrict__ pos_n,
-                                         int32_t* __restrict__ status) {
+                                         int32_t* __restrict__ status, int64_t rows_padded) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= B) return;
+  if (row >= B) {
+    if (row < rows_padded) {
+      for (int s = lane; s < cap; s += 32) pos_d[row * cap + s] = -INFINITY;
+      if (lane == 0) pos_n[row] = 0;
+    }
+    return;
+  }
   const int32_t la = labels[row];
   int count = 0;
   int32_t* mine_j = pos_j + row * cap;
@@ -1242,6 +1250,8 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
       pos_d[row * cap + s0 + lane] = static_cast<float>(squared ? v : sqrt(v));
     }
   }
+  // unused slots hold -inf ("never the harder positive"): readers that walk whole lists need no count check
+  for (int s = n + lane; s < cap; s += 32) pos_d[row * cap + s] = -INFINITY;
   if (lane == 0) {
     pos_n[row] = n;
     if (count > cap) atomicMax(status, count);  // caller's max_positives was too small
@@ -1896,7 +1906,7 @@ size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
   const size_t tiles = static_cast<size_t>((B + tc::BM - 1) / tc::BM);
   const size_t fwd = operand_bytes(B, d) + pos_bytes(B, max_positives) +
                      align_up(static_cast<size_t>(B) * tiles * tc::EPI_H * sizeof(PairPartial));
-  const size_t bwd = pos_bytes(B, tc_list_cap(max_positives)) +
+  const size_t bwd = pos_bytes((B + tc::BM - 1) / tc::BM * tc::BM, tc_list_cap(max_positives)) +
                      align_up(static_cast<size_t>(B) * pair_tc_partials_per_row(B, d) * sizeof(PairPartial)) +
                      pair_tc_ws_bytes(B, d);
   return fwd > bwd ? fwd : bwd;
@@ -1940,7 +1950,7 @@ int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
   collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, max_positives, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
+      emb, labels, B, d, squared, max_positives, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, B);
   EN_LAUNCHED("collect_positives_kernel");
   EpBatchAll::Params ep{labels, o.norms, pl.pos_d, pl.pos_n, partial, B, max_positives, sh.n_splits, squared, margin};
   prof_begin(st);
@@ -1969,11 +1979,12 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   Workspace w(ws, ws_bytes);
   const bool tensor = max_positives <= kTcBwdMaxPos || !cuda_core_bwd_requested();
   const int cap = tensor ? tc_list_cap(max_positives) : max_positives;
-  PosLists pl = take_pos(w, B, cap);
+  const int64_t Bp = (B + tc::BM - 1) / tc::BM * tc::BM;  // lists for whole tiles (empty past B)
+  PosLists pl = take_pos(w, Bp, cap);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
-  collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
+  collect_positives_kernel<<<static_cast<unsigned>((Bp * 32 + 255) / 256), 256, 0, st>>>(
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp);
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   if (tensor) {
@@ -2026,13 +2037,14 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   }
   Workspace w(ws, ws_bytes);
   const int cap = tc_list_cap(max_positives);
-  PosLists pl = take_pos(w, B, cap);
+  const int64_t Bp = (B + tc::BM - 1) / tc::BM * tc::BM;  // lists for whole tiles (empty past B)
+  PosLists pl = take_pos(w, Bp, cap);
   const int ppr = pair_tc_partials_per_row(B, d);
   PairPartial* partial = w.take<PairPartial>(static_cast<size_t>(B) * ppr);
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
-  collect_positives_kernel<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status);
+  collect_positives_kernel<<<static_cast<unsigned>((Bp * 32 + 255) / 256), 256, 0, st>>>(
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp);
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));

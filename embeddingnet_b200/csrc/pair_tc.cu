@@ -84,7 +84,7 @@ struct Bars {
 struct Params {
   const int32_t* labels;
   const float* norms;
-  const float* pos_d;     // [B][cap] (batch-all)
+  const float* pos_d;     // [B rounded up to whole tiles][cap] (batch-all), -inf past each list's end
   const int32_t* pos_n;   // [B]
   int32_t* pos_cnt;       // [B][cap] out: active negatives per (anchor, positive slot)
   int cap;                // list capacity: MAXP, or a multiple of 8 up to MAXP_BIG (kBig)
@@ -370,60 +370,53 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
         __syncwarp();
         if constexpr (kBig) {
-          // ---- lists longer than eight: cap / 8 passes over the 32 S values of this thread.  Pass g holds slots
-          // 8g .. 8g+7 of the row anchor's list in registers and of the 32 column anchors' lists in this warp's
-          // scratch; cntv[j] collects, over the passes, the number of active triplets the pair (row, column j) is the
-          // (anchor, negative) or (negative, anchor) of.  Elements are taken eight per trip of a rolled loop with the
-          // register arrays rotated (as below), so that the code stays small.
+          // ---- lists longer than eight.  Eight elements per trip of a rolled loop, as in the short-list path; inside
+          // a trip the lists are walked eight slots at a time (rolled): the row anchor's slots from its list in
+          // global memory (L1), the column anchors' slots likewise (one address per warp and element: a broadcast).
+          // The per-(anchor, positive) counts go to the shared-memory table, eight adds per trip and group.
           const int64_t col0 = static_cast<int64_t>(J) * BN + cq * 32;
           const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
-          const int64_t ccol = col0 + lane;
-          const bool col_ok = ccol < p.B;
-          const int npk = col_ok ? __ldg(&p.pos_n[ccol]) : 0;
-          float cntv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cntv[j] = 0.f;
-          float chunk_loss = 0.f;
           const int n_groups = p.cap >> 3;
+          // lists are padded with -inf up to cap (collect_positives_kernel), so no slot needs a count check
+          const float* row_list = p.pos_d + (row_ok ? row : 0) * p.cap;
+          float chunk_sum = 0.f, chunk_loss = 0.f;
+          unsigned np_tile = 0;
 #pragma unroll 1
-          for (int g = 0; g < n_groups; ++g) {
-            float pi8[8], cs8[8];
-            {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-              if (row_ok && g * 8 < npi) {
-                a = __ldg(reinterpret_cast<const float4*>(p.pos_d + row * p.cap + g * 8));
-                b = __ldg(reinterpret_cast<const float4*>(p.pos_d + row * p.cap + g * 8 + 4));
-              }
-              const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          for (int jj = 0; jj < 32; jj += 8) {
+            float dn8[8], sf8[8], cnt8[8];
+            // (the lists cover whole tiles: columns past B have empty ones, and their dn is +inf anyway)
+            const float* col_lists = p.pos_d + (col0 + jj) * p.cap;
+            const int col_step = p.cap;
 #pragma unroll
-              for (int s = 0; s < 8; ++s) {
-                pi8[s] = (g * 8 + s < npi) ? v[s] + p.margin : -INFINITY;
-                cs8[s] = 0.f;
-              }
+            for (int u = 0; u < 8; ++u) {
+              const int j = jj + u;
+              const bool ok = interior || (row_ok && col0 + j < p.B && col0 + j != row);
+              const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
+              const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
+              const bool isneg = ok && wi[j] != la;
+              dn8[u] = isneg ? (p.squared ? d2 : d2 * rs) : INFINITY;
+              sf8[u] = p.squared ? 2.f : rs;
+              cnt8[u] = 0.f;
             }
-            __syncwarp();  // the previous pass has read its column thresholds
-            {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-              if (g * 8 < npk) {
-                a = __ldg(reinterpret_cast<const float4*>(p.pos_d + ccol * p.cap + g * 8));
-                b = __ldg(reinterpret_cast<const float4*>(p.pos_d + ccol * p.cap + g * 8 + 4));
-              }
-              const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int s = 0; s < 8; ++s) wpos[lane * MAXP + s] = (g * 8 + s < npk) ? v[s] + p.margin : -INFINITY;
-            }
-            __syncwarp();
 #pragma unroll 1
-            for (int jj = 0; jj < 32; jj += 8) {
-              float keep[8];
+            for (int g = 0; g < n_groups; ++g) {
+              float pi8[8], cs8[8];
+              {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(row_list + g * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(row_list + g * 8 + 4));
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                  pi8[s] = v[s] + p.margin;
+                  cs8[s] = 0.f;
+                }
+              }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int j = jj + u;
-                const bool ok = interior || (row_ok && col0 + j < p.B && col0 + j != row);
-                const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
-                const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
-                const bool isneg = ok && wi[j] != la;
-                const float dn = isneg ? (p.squared ? d2 : d2 * rs) : INFINITY;
+                const float dn = dn8[u];
+                // the column anchor's slots 8g .. 8g+7: one address per warp (a broadcast load)
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(col_lists + u * col_step + g * 8));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(col_lists + u * col_step + g * 8 + 4));
                 float cnt = 0.f;
                 if (full) {
 #pragma unroll
@@ -438,46 +431,23 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 #pragma unroll
                   for (int s = 0; s < 8; ++s) cnt += (pi8[s] - dn) > 1e-16f ? 1.f : 0.f;
                 }
-                const float4 q0 = *reinterpret_cast<const float4*>(wpos + j * MAXP);
-                const float4 q1 = *reinterpret_cast<const float4*>(wpos + j * MAXP + 4);
-                cnt += ((q0.x - dn > 1e-16f ? 1.f : 0.f) + (q0.y - dn > 1e-16f ? 1.f : 0.f)) +
-                       ((q0.z - dn > 1e-16f ? 1.f : 0.f) + (q0.w - dn > 1e-16f ? 1.f : 0.f)) +
-                       ((q1.x - dn > 1e-16f ? 1.f : 0.f) + (q1.y - dn > 1e-16f ? 1.f : 0.f)) +
-                       ((q1.z - dn > 1e-16f ? 1.f : 0.f) + (q1.w - dn > 1e-16f ? 1.f : 0.f));
-                keep[u] = cntv[u] + cnt;
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int s = 0; s < 8; ++s) cnt += (qv[s] + p.margin) - dn > 1e-16f ? 1.f : 0.f;
+                cnt8[u] += cnt;
               }
-              // rotate both arrays by eight: after four trips they are back in place
-              float wk[8];
+              if (full) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) wk[u] = w[u];
-#pragma unroll
-              for (int i = 0; i < 24; ++i) { w[i] = w[i + 8]; cntv[i] = cntv[i + 8]; }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) { w[24 + u] = wk[u]; cntv[24 + u] = keep[u]; }
-            }
-            if (full) {
-              unsigned tot = 0;
-#pragma unroll
-              for (int s = 0; s < 8; ++s) {
-                const unsigned c = static_cast<unsigned>(cs8[s]);  // exact small integers
-                tot += c;
-                if (c != 0u) atomicAdd(&slot_cnt[(g * 8 + s) * BM + quarter * 32 + lane], c);
+                for (int s = 0; s < 8; ++s) {
+                  const unsigned c = static_cast<unsigned>(cs8[s]);  // exact small integers
+                  np_tile += c;
+                  if (c != 0u) atomicAdd(&slot_cnt[(g * 8 + s) * BM + quarter * 32 + lane], c);
+                }
               }
-              np_big += tot;
             }
-          }
-          // coefficients from the accumulated counts; packing as in the short-list path
-          float chunk_sum = 0.f;
-#pragma unroll 1
-          for (int jj = 0; jj < 32; jj += 8) {
             float cv8[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = jj + u;
-              const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
-              const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
-              cv8[u] = -cntv[u] * cs * (p.squared ? 2.f : rs);  // the count is 0 where the pair is not a negative pair
-            }
+            for (int u = 0; u < 8; ++u) cv8[u] = -cnt8[u] * cs * sf8[u];  // the count is 0 where the pair is no negative pair
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -488,13 +458,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               chunk_sum += (h0 + l0) + (h1 + l1);
             }
 #pragma unroll
-            for (int i = 0; i < 24; ++i) { w[i] = w[i + 8]; cntv[i] = cntv[i + 8]; }
+            for (int i = 0; i < 24; ++i) w[i] = w[i + 8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               w[24 + u] = __uint_as_float(hw[u]);
               w[28 + u] = __uint_as_float(lw[u]);
             }
           }
+          np_big += np_tile;
           rowsum += static_cast<double>(chunk_sum);
           if (kLoss) loss_sum += static_cast<double>(chunk_loss);
         } else {
