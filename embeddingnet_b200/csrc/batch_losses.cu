@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "tc_engine.cuh"
+#include "tc_engine_wide.cuh"
 
 namespace en {
 
@@ -1766,6 +1767,10 @@ int splits_for(int64_t B, int sms) {
 
 using namespace en;
 
+// developer aid (tools/trace_bh.py; not part of the C ABI): device buffer of 64 stamps per CTA for the batch-hard GEMM
+static unsigned long long* g_bh_trace = nullptr;
+extern "C" void en_debug_set_bh_trace(void* device_buffer) { g_bh_trace = static_cast<unsigned long long*>(device_buffer); }
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------ batch-hard
@@ -1807,13 +1812,30 @@ static int batch_hard_core(const float* emb, const int32_t* labels, int64_t B, i
   // |a||b| <= (|a|^2 + |b|^2) / 2, best and contender both off by it: band = 2 c (|a|^2 + |b|^2).
   // The epilogue also truncates 7 mantissa bits of each proxy (index packing): < 2^-16 |t|, |t| <= 2 (|a|^2 +
   // |b|^2), on both sides: + 2^-14.
-  const float band_c = 2.0f * (3.0f / 65536.0f + (o.dpad / 16 + 1) / 4194304.0f) + 1.0f / 16384.0f;
+  // From four column tiles on, a CTA takes one row tile and a PAIR of column tiles (csrc/tc_engine_wide.cuh: the A
+  // tiles are fetched once for both; the kernel is bound by the L2 -> SM operand stream).  Its three products share
+  // one accumulator, so the truncation term counts 3 d/16 links.  EN_BH_NARROW=1 keeps the 128 x 128 schedule (tests
+  // compare the two).
+  const char* narrow_env = getenv("EN_BH_NARROW");
+  const bool wide = tiles_n >= 4 && !(narrow_env && narrow_env[0] == '1');
+  const int links = wide ? 3 * (o.dpad / 16) + 1 : o.dpad / 16 + 1;
+  const float band_c = 2.0f * (3.0f / 65536.0f + links / 4194304.0f) + 1.0f / 16384.0f;
   tc::Shape sh = tc::make_shape_symmetric(B, d, 3, 1);  // upper-triangular tiles, one per work item; BF16 planes
+  sh.trace = g_bh_trace;
   EpBatchHard::Params ep{labels, o.norms, cand, B, tiles_n};
   const int sms = device_sm_count();
-  prof_begin(st);
-  EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
-  prof_end(st);
+  if (wide) {
+    CUtensorMap bh, bl;  // the same planes with 256-row boxes (both column tiles of a pair in one load)
+    if (tc::make_plane_tmap_bf16(&bh, o.hi, B, o.dpad, 2 * tc::BN) || tc::make_plane_tmap_bf16(&bl, o.lo, B, o.dpad, 2 * tc::BN))
+      return fail(EN_ERR_DRIVER, "%s: cuTensorMapEncodeTiled failed", who);
+    prof_begin(st);
+    EN_CUDA(tc::wide::launch<EpBatchHard>(o.th, o.tl, bh, bl, sh, ep, sms, st));
+    prof_end(st);
+  } else {
+    prof_begin(st);
+    EN_CUDA(tc::launch<EpBatchHard>(o.th, o.tl, o.th, o.tl, sh, ep, sms, st));
+    prof_end(st);
+  }
   prof_mark(st, 2);
   ++launch_counter();
   const bool fast = d % 128 == 0 && d <= 512 && tiles_n * BH_SLOTS <= 128 &&

@@ -63,7 +63,19 @@ struct Shape {
                     // rate; ~2^-16 relative instead of ~2^-22: for paths that only SELECT candidates which are then
                     // re-evaluated exactly (bank scan, batch-hard)
   int bk;           // elements per k-block (one 128-byte swizzle row): 32 fp32/TF32 or 64 BF16
+  unsigned long long* trace;  // developer aid (null in production): per CTA 64 globaltimer stamps, see trace_stamp()
 };
+
+// Developer aid: CTA `blockIdx.x` writes stamp `slot` (ns) when the launch carries a trace buffer.
+// Slots: 0 kernel entry, 1 set-up done; MMA thread: 8+4t tile t accumulator free, 9+4t first operands landed,
+// 10+4t all MMAs issued; epilogue warp 2 lane 0: 40+2t tile t accumulator full, 41+2t tile t drained.
+__device__ __forceinline__ void trace_stamp(const Shape& sh, int slot) {
+  if (sh.trace != nullptr && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    sh.trace[blockIdx.x * 64 + slot] = t;
+  }
+}
 
 // Work item -> (row tile, column-tile range).  Same arithmetic in all three warp roles.
 struct Item {
@@ -148,6 +160,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_items = shape.num_items;
+  if (threadIdx.x == 0) trace_stamp(shape, 0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -170,6 +183,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (threadIdx.x == 0) trace_stamp(shape, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -202,6 +216,8 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN);
       constexpr uint32_t idesc16 = ptx::make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_w = ptx::make_idesc_tf32(BM, 2 * BN);      // B = [B_hi ; B_lo], D = main | cross
+      constexpr uint32_t idesc16_w = ptx::make_idesc_bf16(BM, 2 * BN);
       const bool bf16 = shape.bf16 != 0;
       int stage = 0;
       uint32_t phase = 0;
@@ -213,11 +229,13 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
           ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
+          trace_stamp(shape, 8 + 4 * static_cast<int>(acc_it));
           const uint32_t tmem_d = tmem_base + acc * ACC_COLS;   // hi*hi
           const uint32_t tmem_x = tmem_d + BN;                   // hi*lo + lo*hi
           for (int kb = 0; kb < shape.kblocks; ++kb) {
             ptx::mbar_wait(&bars->full[stage], phase);
             ptx::tc_fence_after();
+            if (kb == 0) trace_stamp(shape, 9 + 4 * static_cast<int>(acc_it));
             const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
             const uint64_t a_lo = ptx::make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
@@ -228,16 +246,21 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
               // advance 32 bytes along K inside the 128B swizzle row: +2 in the (addr>>4) field
               // (8 TF32 or 16 BF16 elements per instruction: the same 32 bytes either way)
               const uint64_t koff = static_cast<uint64_t>(k * UMMA_K * 4 / 16);
+              // Three products from TWO instructions: the B_hi and B_lo tiles are adjacent in the stage, and so
+              // are the main and cross accumulators, so A_hi x [B_hi ; B_lo] (N = 256) leaves hi*hi in the main
+              // columns and hi*lo in the cross columns while reading A_hi once; A_lo x B_hi (N = 128) follows.
+              // Operand reads from shared memory drop from 24 to 20 KiB per k-step (the MMAs were paced by shared-
+              // memory bandwidth: 8 KiB per 64-cycle instruction is the SM's 128 B/clk, with TMA writing beside).
               if (bf16) {
                 if (shape.passes > 1) {
-                  ptx::mma_bf16_ss(tmem_x, a_lo + koff, b_hi + koff, idesc16, (kb | k) != 0);
-                  ptx::mma_bf16_ss(tmem_x, a_hi + koff, b_lo + koff, idesc16, 1);
+                  ptx::mma_bf16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc16_w, (kb | k) != 0);
+                  ptx::mma_bf16_ss(tmem_x, a_lo + koff, b_hi + koff, idesc16, 1);
+                } else {
+                  ptx::mma_bf16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc16, (kb | k) != 0);
                 }
-                ptx::mma_bf16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc16, (kb | k) != 0);
               } else if (shape.passes > 1) {
-                ptx::mma_tf32_ss(tmem_x, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-                ptx::mma_tf32_ss(tmem_x, a_hi + koff, b_lo + koff, idesc, 1);
-                ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+                ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc_w, (kb | k) != 0);
+                ptx::mma_tf32_ss(tmem_x, a_lo + koff, b_hi + koff, idesc, 1);
               } else {
                 ptx::mma_tf32_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
               }
@@ -246,6 +269,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          trace_stamp(shape, 10 + 4 * static_cast<int>(acc_it));
         }
       }
     }
@@ -269,6 +293,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const uint32_t acc_phase = (acc_it / NUM_ACC) & 1;
         ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
         ptx::tc_fence_after();
+        if (warp == 2 && lane == 0) trace_stamp(shape, 40 + 2 * static_cast<int>(acc_it));
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
         for (int c = half * (COLS_PER_EPI_WARP / 32); c < (half + 1) * (COLS_PER_EPI_WARP / 32); ++c) {
@@ -289,6 +314,7 @@ dist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
         Ep::tile_end(ep, rs, ctx, row, row_valid, shape.nt_base + nt);
+        if (warp == 2 && lane == 0) trace_stamp(shape, 41 + 2 * static_cast<int>(acc_it));
       }
       Ep::item_end(ep, rs, ctx, row, row_valid, tile_m, split);
     }
@@ -370,6 +396,7 @@ inline Shape make_shape(int64_t M, int64_t N, int d, int n_splits, int passes, i
   s.symmetric = 0;
   s.num_items = s.tiles_m * s.n_splits;
   s.nt_base = 0;
+  s.trace = nullptr;
   return s;
 }
 

@@ -284,6 +284,41 @@ def run_batch_hard(x, lab, margin=0.5, squared=False, soft=False):
             g.cpu().numpy())
 
 
+@pytest.mark.parametrize("ncls,per,d,shuf", [(75, 8, 96, True),     # 600 rows: 5 column tiles -> 3 pairs, one phantom sub-tile
+                                             (64, 9, 128, False),    # 576 rows, class-major
+                                             (130, 7, 192, True),    # 910 rows: 8 tiles (ragged last), fast finalize (DV = 1.5 -> generic)
+                                             (256, 8, 256, True)])   # 2048 rows, 16 tiles: two rounds of items per SM
+def test_batch_hard_wide_tile_schedule(ncls, per, d, shuf, monkeypatch):
+    """From four column tiles on the distance GEMM takes (row tile, PAIR of column tiles) work items with one merged
+    accumulator (csrc/tc_engine_wide.cuh).  Same selected indices, distances and loss as the 128 x 128 schedule
+    (EN_BH_NARROW=1) and as the float64 oracle; gradient 1e-4."""
+    x, lab = make_batch(ncls, per, d, True, shuf)
+    # near-duplicates of a few rows (same class and other classes): contenders inside the error band on both paths
+    rs = np.random.RandomState(3)
+    for i in rs.choice(len(lab), 12, replace=False):
+        j = int(rs.randint(len(lab)))
+        x[j] = x[i] * (1.0 + 1e-7 * rs.randn(x.shape[1])).astype(np.float32)
+    x = unit_rows(x)
+    ref = O.batch_hard(lab, x, 0.5, False, False)
+    _, gref = O.batch_hard_grad(lab, x, 0.5, False, False)
+    outs = []
+    for narrow in (False, True):
+        if narrow:
+            monkeypatch.setenv("EN_BH_NARROW", "1")
+        else:
+            monkeypatch.delenv("EN_BH_NARROW", raising=False)
+        outs.append(run_batch_hard(x, lab))
+    monkeypatch.delenv("EN_BH_NARROW", raising=False)
+    for loss, hp_idx, hn_idx, hp, hn, g in outs:
+        np.testing.assert_array_equal(hp_idx, ref["hp_idx"])
+        np.testing.assert_array_equal(hn_idx, ref["hn_idx"])
+        np.testing.assert_allclose(hp, ref["hp"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(hn, ref["hn"], rtol=1e-5, atol=1e-7)
+        assert abs(loss - float(ref["loss"])) <= 1e-5 * float(ref["loss"])
+        assert rel_err(g, gref) < 1e-4
+    assert outs[0][0] == outs[1][0]  # the exact re-evaluation makes the loss independent of the schedule
+
+
 SAT_CASES = [(ncls, per, d, n_dup, kind)
              for (ncls, per, d) in [(512, 8, 128),   # B = 4096: fast + slow finalize kernels (DV = 1), 32 row tiles
                                     (48, 8, 100)]    # 384 rows, 3 tiles, generic finalize kernel
