@@ -403,10 +403,13 @@ def main():
     # the batch-hard GEMM runs on split-BF16 operands (3 kind::f16 MMAs per k-step): its own tensor roofline is
     # dense bf16 / 3; north_star's "TF32-emulated roofline" (dense bf16 / 2 / 3) is reported beside it
     peak = peaks["bf16"] / 3.0
+    n_t = B // 128
+    tiles_exec = 2 * sum((n_t + 1) // 2 - (i >> 1) for i in range(n_t))   # csrc/tc_engine_wide.cuh: num_items() pairs
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": ncu_traffic("batch_hard_gemm_dram_bytes_per_launch"),
-        "kernel": "dist_gemm_kernel<EpBatchHard> (tcgen05 kind::f16 on split-BF16 planes, 3 MMAs per k-step)",
+        "kernel": "dist_gemm_wide_kernel<EpBatchHard> (tcgen05 kind::f16 on split-BF16 planes, 3 N=256 MMAs per "
+                  "k-step; work item = row tile x pair of column tiles)",
         "kernel_ms": gemm_ms_avg, "share_of_step": gemm_ms_avg / ms_per_step,
         "algorithmic_flops_per_launch": flops,
         "peak_note": "%s bf16 dense %.1f TFLOP/s (burst) / 3 (hi*hi + hi*lo + lo*hi passes)" % (
@@ -414,13 +417,14 @@ def main():
         "frac_of_bf16_peak": achieved / peaks["bf16"],
         "frac_of_tf32x3_roofline": achieved / (peaks["bf16"] / 6.0),
         # `achieved` credits the ALGORITHMIC 2 B^2 d flops.  The symmetric schedule executes only the
-        # upper-triangular tiles (528 of 1024 at B = 4096), three kind::f16 MMAs per k-step each: the rate the
-        # tensor pipe actually runs at is below, so `frac` (which can reach 1024/528 = 1.94 for this schedule) is
-        # not misread as pipe utilisation (ncu: sm__pipe_tensor_cycles_active ~46 %)
-        "tiles_executed": (B // 128) * (B // 128 + 1) // 2, "tiles_algorithmic": (B // 128) ** 2,
-        "hardware_mma_tflops": 3.0 * ((B // 128) * (B // 128 + 1) // 2) * 2.0 * 128 * 128 * D / (gemm_ms_avg * 1e-3) / 1e12,
-        "hardware_frac_of_bf16_peak": 3.0 * ((B // 128) * (B // 128 + 1) // 2) * 2.0 * 128 * 128 * D /
-                                      (gemm_ms_avg * 1e-3) / 1e12 / peaks["bf16"],
+        # tile pairs that touch the upper triangle (272 pairs = 544 tiles of 1024 at B = 4096), three kind::f16 MMAs
+        # per k-step each: the rate the tensor pipe actually runs at is below, so `frac` (which can reach
+        # 1024/544 = 1.88 for this schedule) is not misread as pipe utilisation.  What bounds the kernel is the
+        # L2 -> SM operand stream (tools/trace_bh.py), reported as l2_operand_stream_tbs.
+        "tiles_executed": tiles_exec, "tiles_algorithmic": (B // 128) ** 2,
+        "hardware_mma_tflops": 3.0 * tiles_exec * 2.0 * 128 * 128 * D / (gemm_ms_avg * 1e-3) / 1e12,
+        "hardware_frac_of_bf16_peak": 3.0 * tiles_exec * 2.0 * 128 * 128 * D / (gemm_ms_avg * 1e-3) / 1e12 / peaks["bf16"],
+        "l2_operand_stream_tbs": (tiles_exec // 2) * (D // 64) * 96 * 1024 / (gemm_ms_avg * 1e-3) / 1e12,
     }
 
     # end to end through the reference-shaped public API, host buffers in and out

@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libembeddingnet_b200.so")
+# EMBEDDINGNET_B200_LIB: developer override (A/B timing of a variant build, tools/ab_bh.py); unset in production
+LIB_PATH = os.environ.get("EMBEDDINGNET_B200_LIB") or os.path.join(HERE, "libembeddingnet_b200.so")
 
 EN_MODE_SEMIHARD, EN_MODE_HARDEST, EN_MODE_RANDOM_HARD = 0, 1, 2
 EN_KNN_SLACK, EN_KNN_MAX_K, EN_KNN_STREAM_MAX_Q, EN_KNN_EXACT_MAX_Q, EN_KNN_SMALLQ_MAX_Q = 3, 29, 8, 64, 64

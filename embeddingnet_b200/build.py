@@ -45,6 +45,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(out_path: str, extra_flags, only=("batch_losses.cu",)) -> str:
+    """Developer aid (tools/ab_bh.py): a second library with extra -D switches on some sources, linked with the
+    objects of the regular build.  Never loaded by the package itself."""
+    build()
+    nvcc = _nvcc()
+    vdir = os.path.join(OBJ_DIR, "variant_" + hashlib.sha256(" ".join(extra_flags).encode()).hexdigest()[:8])
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        if src in only:
+            obj = os.path.join(vdir, src.replace(".cu", ".o"))
+            subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        else:
+            obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+    subprocess.run([nvcc, "-shared", "-o", out_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"],
+                   check=True)
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     stamp = os.path.join(OBJ_DIR, "digest.txt")

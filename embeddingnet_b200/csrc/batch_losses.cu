@@ -32,6 +32,31 @@ int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, 
 namespace {
 
 constexpr float kBig = 3.0e38f;
+
+// Developer aid, compiled in only with -DEN_FIN_TRACE (tools/trace_bh.py builds such a variant; in the production
+// build these are empty -- the stamps cost ~1 us per step, measured A/B): globaltimer stamps of the two finalize
+// kernels.  fin_stamp: first entry (atomic min) / last exit (atomic max); fin_sample: plain per-phase stamps of every
+// 64th anchor's warp at [8 + 2048 + 4 * (row / 64) + phase].
+__device__ unsigned long long* g_fin_trace = nullptr;
+__device__ __forceinline__ void fin_stamp(int slot, bool is_min) {
+#ifdef EN_FIN_TRACE
+  unsigned long long* t = g_fin_trace;
+  if (t == nullptr) return;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (is_min) atomicMin(&t[slot], now);
+  else atomicMax(&t[slot], now);
+#endif
+}
+__device__ __forceinline__ void fin_sample(int64_t row, int lane, int phase) {
+#ifdef EN_FIN_TRACE
+  unsigned long long* t = g_fin_trace;
+  if (t == nullptr || lane != 0 || (row & 63) != 0 || row >= 64 * 64) return;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  t[8 + 2048 + 4 * (row >> 6) + phase] = now;
+#endif
+}
 constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps eight positives per anchor in registers / scratch per pass
 // list capacity of the tensor-core pair kernel for a class bound: 8, or the next multiple of 8 (at most 64) --
 // longer lists are walked eight slots per pass over a tile (pair_tc_kernel<..., kBig>)
@@ -630,6 +655,7 @@ __device__ __forceinline__ bool bh_fast_anchor(const float* __restrict__ emb, co
     // inside the record's tile rides in the low mantissa bits.  Each lane queues up to two contenders per kind.  A
     // record whose SECOND entry is a contender marks a saturated slot (it may hide more): general resolver.
     int pc = 0, nc = 0, pi0 = -1, pi1 = -1, ni0 = -1, ni1 = -1;
+    fin_sample(row, lane, 1);  // (trace builds) this warp has its records
     const BhThr thr = bh_thresholds(na, bp, bn, band_c);
     const float thr_p = thr.p, thr_n = thr.n;
     bool sat = false;
@@ -720,6 +746,7 @@ __device__ __forceinline__ bool bh_fast_anchor(const float* __restrict__ emb, co
     }
     // a single round leaves the winners' rows in registers for the gradient
     const bool rows_cached = rounds == 1;
+    fin_sample(row, lane, 2);  // (trace builds) this warp has its exact distances
     const double hp = pos.idx >= 0 ? (squared ? pos.d2 : sqrt(pos.d2)) : 0.0;
     const double hn = neg.idx >= 0 ? (squared ? neg.d2 : sqrt(neg.d2)) : 0.0;
     const double z = hp - hn;
@@ -792,10 +819,14 @@ batch_hard_finalize_fast_kernel(const float* __restrict__ emb, const int32_t* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * FF_WARPS + warp;
   if (row >= B) return;
+  if (lane == 0) fin_stamp(0, true);
+  fin_sample(row, lane, 0);
   if (bh_fast_anchor<kGrad, DV>(emb, labels, norms, cand, B, tiles_n, margin, squared, soft, band_c, hp_idx, hn_idx,
                                 hp_out, hn_out, coef, hinge_all, gloss, gemb, row, lane) &&
       lane == 0)
     work_list[atomicAdd(&counters[0], 1u)] = static_cast<int32_t>(row);
+  if (lane == 0) fin_stamp(1, false);
+  fin_sample(row, lane, 3);
 }
 
 // ---- slow finalize: the anchors the fast kernel put on the work list, one BLOCK per anchor -------------------
@@ -1038,10 +1069,25 @@ batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __
   __shared__ BhBlockShared<FS_WARPS> sm;
   __shared__ double s_red[FS_WARPS];
   __shared__ bool s_last;
+  if (threadIdx.x == 0) fin_stamp(2, true);
   const unsigned n_work = *reinterpret_cast<volatile unsigned*>(&counters[0]);
-  for (unsigned k = blockIdx.x; k < n_work; k += gridDim.x)
+  for (unsigned k = blockIdx.x; k < n_work; k += gridDim.x) {
+#ifdef EN_FIN_TRACE
+    unsigned long long t_in = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_in));
+#endif
     bh_block_resolve<kGrad, FS_WARPS>(sm, emb, labels, norms, cand, B, d, tiles_n, margin, squared, soft, band_c,
                                       work_list[k], hp_idx, hn_idx, hp_out, hn_out, coef, hinge_all, gloss, gemb);
+#ifdef EN_FIN_TRACE
+    if (g_fin_trace != nullptr && threadIdx.x == 0 && k < 1024) {  // per listed anchor: resolve ns, start stamp
+      unsigned long long t_out;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_out));
+      g_fin_trace[8 + 2 * k] = t_out - t_in;
+      g_fin_trace[9 + 2 * k] = t_in;
+    }
+#endif
+  }
+  if (threadIdx.x == 0 && blockIdx.x < n_work) fin_stamp(3, false);
   // ---- mean over all anchors, in a fixed order, by the last WORKING block (blocks without an anchor leave at
   // once) -- or by block 0 when the list is empty
   const unsigned n_working = n_work < gridDim.x ? n_work : gridDim.x;
@@ -1061,6 +1107,10 @@ batch_hard_finalize_slow_kernel(const float* __restrict__ emb, const int32_t* __
     if (threadIdx.x == 0) {
       counters[0] = 0;  // re-armed for the next call on this workspace
       counters[1] = 0;
+      fin_stamp(4, false);
+#ifdef EN_FIN_TRACE
+      if (g_fin_trace) g_fin_trace[5] = n_work;
+#endif
     }
   }
 }
@@ -1769,7 +1819,13 @@ using namespace en;
 
 // developer aid (tools/trace_bh.py; not part of the C ABI): device buffer of 64 stamps per CTA for the batch-hard GEMM
 static unsigned long long* g_bh_trace = nullptr;
-extern "C" void en_debug_set_bh_trace(void* device_buffer) { g_bh_trace = static_cast<unsigned long long*>(device_buffer); }
+// layout: 64 stamps per GEMM CTA (csrc/tc_engine.cuh trace_stamp), then the words of the finalize kernels (fin_stamp,
+// fin_sample, per listed anchor; written only by a -DEN_FIN_TRACE build)
+extern "C" void en_debug_set_bh_trace(void* device_buffer, int n_ctas) {
+  g_bh_trace = static_cast<unsigned long long*>(device_buffer);
+  unsigned long long* fin = g_bh_trace ? g_bh_trace + static_cast<size_t>(n_ctas) * 64 : nullptr;
+  cudaMemcpyToSymbol(g_fin_trace, &fin, sizeof(fin));
+}
 
 extern "C" {
 

@@ -13,15 +13,19 @@ $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_m
     python tools/profile_step.py mining > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_smallq.csv \
     python tools/profile_step.py smallq > /dev/null 2>&1
-$NCU --set full --import-source on -k regex:"dist_gemm_kernel|batch_hard_finalize|split_planes" -s 8 -c 4 -o $T/bh \
+$NCU --set full --import-source on -k regex:"dist_gemm|batch_hard_finalize|split_planes" -s 8 -c 4 -o $T/bh \
     python tools/profile_step.py triplet > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:"pair_tc_kernel|pair_finish|collect_positives" -c 8 -o $T/pair \
     python tools/profile_step.py pairbwd > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:"pair_tc_kernel" -c 1 -o $T/ba64 \
+    python tools/profile_step.py ba64 > /dev/null 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_ba64.csv \
+    python tools/profile_step.py ba64 > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:"knn_smallq|knn_stream" -c 6 -o $T/smallq \
     python tools/profile_step.py smallq > /dev/null 2>&1
 $NCU --set full -k regex:"l2norm|row_dist" -s 4 -c 4 -o $T/rowwise python tools/profile_step.py rowwise > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:"EpMine" -c 2 -o $T/mine python tools/profile_step.py mining > /dev/null 2>&1
-python tools/ncu_summary.py $T/bh.ncu-rep $T/pair.ncu-rep $T/smallq.ncu-rep $T/rowwise.ncu-rep $T/mine.ncu-rep \
+python tools/ncu_summary.py $T/bh.ncu-rep $T/pair.ncu-rep $T/ba64.ncu-rep $T/smallq.ncu-rep $T/rowwise.ncu-rep $T/mine.ncu-rep \
     > gpurun_out/r02_ncu_summary.md 2> gpurun_out/r02_ncu_summary.err
 hot() {  # <rep> <kernel id (1-based)> <name>
   ncu -i $T/$1.ncu-rep --page source --csv --kernel-id :::$2 > $T/src.csv 2>/dev/null
@@ -29,5 +33,9 @@ hot() {  # <rep> <kernel id (1-based)> <name>
 }
 hot bh 2 bh_gemm; hot bh 3 bh_finalize_fast; hot bh 4 bh_finalize_slow
 hot pair 2 pair_tc_batch_all; hot pair 6 pair_tc_contrastive
-hot smallq 3 knn_smallq_q8; hot mine 1 mine_count
+hot smallq 3 knn_smallq_q8; hot mine 1 mine_count; hot ba64 1 pair_tc_batch_all_big
+EMBEDDINGNET_B200_LIB=build/lib_trace.so python tools/trace_bh.py > gpurun_out/r02_trace_bh_step.txt 2>&1
+python tools/time_bh.py > gpurun_out/r02_time_bh.txt 2>&1
+python tools/time_ba64.py > gpurun_out/r02_time_batch_all.txt 2>&1
+./build/pipe_probe 3 > gpurun_out/r02_pipe_probe.txt 2>&1
 ls -la $T gpurun_out | tail -30
