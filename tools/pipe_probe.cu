@@ -52,13 +52,13 @@ int main(int argc, char** argv) {
     CK(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
   }
   const size_t n16 = bytes / 16;
-  for (int variant = (argc > 2 ? 8 : 0); variant < 11; ++variant) {
+  for (int variant = (argc > 2 ? 8 : 0); variant < 13; ++variant) {
     for (int kern_us : {0, 70}) {
       double t0 = 0;
       for (int i = -20; i < N; ++i) {
         if (i == 0) { CK(cudaDeviceSynchronize()); t0 = now(); }
         const int k = ((i % DEPTH) + DEPTH) % DEPTH;
-        if (i + 20 >= DEPTH) CK(cudaEventSynchronize(out_done[k]));
+        if (i + 20 >= DEPTH + 2) CK(cudaEventSynchronize(out_done[k]));
         switch (variant) {
           case 0:  // three streams, device-side event waits (the en_bh_host_pipe schedule)
             CK(cudaMemcpyAsync(d_in[k], h_in, bytes, cudaMemcpyHostToDevice, s_in));
@@ -145,6 +145,36 @@ int main(int argc, char** argv) {
             CK(cudaMemcpyAsync(h_out[k], d_out[k], bytes, cudaMemcpyDeviceToHost, s_out));
             CK(cudaEventRecord(out_done[k], s_out));
             break;
+          case 11:  // host-driven download: the host waits for kernel(i-1) and only then issues its download (no
+                    // copy-engine channel ever sits on a semaphore waiting for a kernel)
+            CK(cudaMemcpyAsync(d_in[k], h_in, bytes, cudaMemcpyHostToDevice, s_in));
+            CK(cudaEventRecord(in_done[k], s_in));
+            CK(cudaStreamWaitEvent(s_cmp, in_done[k], 0));
+            if (kern_us) sleep_kernel<<<1, 32, 0, s_cmp>>>(kern_us * 1000);
+            CK(cudaEventRecord(cmp_done[k], s_cmp));
+            if (i + 20 >= 1) {
+              const int kp = ((i - 1) % DEPTH + DEPTH) % DEPTH;
+              CK(cudaEventSynchronize(cmp_done[kp]));
+              CK(cudaMemcpyAsync(h_out[kp], d_out[kp], bytes, cudaMemcpyDeviceToHost, s_out));
+              CK(cudaEventRecord(out_done[kp], s_out));
+            }
+            break;
+          case 12:  // host-driven on both sides: kernel(i) is launched by the host once upload(i) has landed
+            CK(cudaMemcpyAsync(d_in[k], h_in, bytes, cudaMemcpyHostToDevice, s_in));
+            CK(cudaEventRecord(in_done[k], s_in));
+            if (i + 20 >= 1) {
+              const int kp = ((i - 1) % DEPTH + DEPTH) % DEPTH;
+              CK(cudaEventSynchronize(in_done[kp]));
+              if (kern_us) sleep_kernel<<<1, 32, 0, s_cmp>>>(kern_us * 1000);
+              CK(cudaEventRecord(cmp_done[kp], s_cmp));
+            }
+            if (i + 20 >= 2) {
+              const int kq = ((i - 2) % DEPTH + DEPTH) % DEPTH;
+              CK(cudaEventSynchronize(cmp_done[kq]));
+              CK(cudaMemcpyAsync(h_out[kq], d_out[kq], bytes, cudaMemcpyDeviceToHost, s_out));
+              CK(cudaEventRecord(out_done[kq], s_out));
+            }
+            break;
           case 7:  // zero-copy downloads only
             copy_kernel<<<64, 256, 0, s_out>>>((const float4*)d_out[k], (float4*)h_out[k], n16);
             CK(cudaEventRecord(out_done[k], s_out));
@@ -157,7 +187,8 @@ int main(int argc, char** argv) {
                                     "CE up, SM-kernel down (mapped host)", "SM-kernel up, SM-kernel down",
                                     "SM-kernel up, CE down", "CE uploads only", "SM-kernel uploads only",
                                     "SM-kernel downloads only", "lock step (up(i) starts with down(i-2))",
-                                    "3 streams, copies in 4 chunks", "kernel in the upload stream"};
+                                    "3 streams, copies in 4 chunks", "kernel in the upload stream",
+                                    "host-driven download", "host-driven kernel and download"};
       printf("depth %d  kernel %2d us  %-38s  %.4f ms/step\n", DEPTH, kern_us, names[variant], dt);
     }
   }
