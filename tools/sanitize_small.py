@@ -52,6 +52,28 @@ def main():
     loss.backward()
     ref = float(O.batch_hard(lab2.astype(np.int64), x2, 0.5)["loss"])
     assert abs(loss.item() - ref) <= 1e-5 * ref
+    # batch-all with large classes: lists of 24 slots walked eight at a time (pair_tc_kernel<..., kBig>), ragged tile
+    x3, lab3 = synth.make_numpy(7 * 20, 72, n_classes=7, rows_per_class=20, noise=0.5, relu=True)
+    x3 = unit(x3)
+    e = torch.tensor(x3, device=dev, requires_grad=True)
+    loss = lac.batch_all_triplet_loss(0.5, max_positives=19)(lab3.astype(np.int64), e)
+    loss.backward()
+    ref = float(O.batch_all(lab3.astype(np.int64), x3, 0.5)["loss"])
+    assert abs(loss.item() - ref) <= 1e-5 * ref + 1e-7
+    # host-buffer pipeline (en_bh_host_pipe_*): three steps through two slots
+    from embeddingnet_b200.fused import BatchHardHostPipeline
+    pipe = BatchHardHostPipeline(x2.shape[0], x2.shape[1], margin=0.5, depth=2)
+    pin = BatchHardHostPipeline.pinned
+    e_h, l_h = pin(x2.shape), pin((x2.shape[0],), torch.int32)
+    e_h.copy_(torch.from_numpy(x2))
+    l_h.copy_(torch.from_numpy(lab2.astype(np.int32)))
+    outs = [(pin((1,)), pin(x2.shape)) for _ in range(3)]
+    tickets = [pipe.submit(e_h, l_h, o[0], o[1]) for o in outs]
+    for t in tickets:
+        pipe.wait(t)
+    ref = float(O.batch_hard(lab2.astype(np.int64), x2, 0.5)["loss"])
+    assert all(abs(float(o[0][0]) - ref) <= 1e-5 * ref for o in outs)
+    pipe.close()
     # in-batch mining (reference semantics)
     np.random.seed(0)
     want, _ = O.mine_batch_triplets(xu[:160], 32, 5, 0.5, "semihard")
