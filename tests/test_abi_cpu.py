@@ -56,6 +56,15 @@ def test_argument_errors_are_reported_without_a_gpu(lib_built):
     rc2 = lib.en_knn_exact_topk(ctypes.c_void_p(256), 65, 64, ctypes.c_void_p(256), 1000, 0, 5, None, None,
                                 ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 1 << 20, None)
     assert rc2 == -1 and b"at most 64" in lib.en_last_error()
+    # host-buffer pipeline: sizes and argument checks happen before anything touches a device
+    assert lib.en_bh_host_pipe_device_bytes(4096, 512, 3) >= 3 * (2 * 4096 * 512 * 4 + lib.en_ws_bytes_batch_hard(4096, 512))
+    assert lib.en_bh_host_pipe_device_bytes(4096, 512, 9) == 0 and lib.en_bh_host_pipe_device_bytes(0, 512, 3) == 0
+    pipe = ctypes.c_void_p(0)
+    rc3 = lib.en_bh_host_pipe_create(4096, 512, ctypes.c_float(0.5), 0, 0, 0, ctypes.c_void_p(256), 1 << 30,
+                                     ctypes.byref(pipe))
+    assert rc3 == -1 and b"depth" in lib.en_last_error() and not pipe.value
+    assert lib.en_bh_host_pipe_submit(None, None, None, None, None, None, None, None) == -1
+    assert lib.en_bh_host_pipe_destroy(None) == 0
     with pytest.raises(ValueError):
         _lib.check(rc, "en_l2_normalize_fwd")
 
