@@ -24,7 +24,8 @@ $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_b
 $NCU --set full --import-source on -k regex:"knn_smallq|knn_stream" -c 6 -o $T/smallq \
     python tools/profile_step.py smallq > /dev/null 2>&1
 $NCU --set full -k regex:"l2norm|row_dist" -s 4 -c 4 -o $T/rowwise python tools/profile_step.py rowwise > /dev/null 2>&1
-$NCU --set full --import-source on -k regex:"EpMine" -c 2 -o $T/mine python tools/profile_step.py mining > /dev/null 2>&1
+# (-k matches the base name, which carries no template arguments: match the demangled name for the epilogue type)
+$NCU --set full --import-source on --kernel-name-base demangled -k regex:"EpMine" -c 2 -o $T/mine python tools/profile_step.py mining > /dev/null 2>&1
 python tools/ncu_summary.py $T/bh.ncu-rep $T/pair.ncu-rep $T/ba64.ncu-rep $T/smallq.ncu-rep $T/rowwise.ncu-rep $T/mine.ncu-rep \
     > gpurun_out/r02_ncu_summary.md 2> gpurun_out/r02_ncu_summary.err
 hot() {  # <rep> <kernel id (1-based)> <name>
