@@ -22,8 +22,8 @@ namespace en {
 size_t pair_tc_ws_bytes(int64_t B, int d);
 int pair_tc_partials_per_row(int64_t B, int d);
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
-                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, int cap,
-                   const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
+                   float coef_scale, const float* pos_d, const double* pos_pre, const int32_t* pos_n, int32_t* pos_cnt,
+                   int cap, const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
                    size_t ws_bytes, cudaStream_t st);
 int pair_tc_finish(const PairTcFinish& fin, const float* emb, int64_t B, int d, int cap, int squared, const float* pos_d,
                    const int32_t* pos_j, const int32_t* pos_n, const int32_t* pos_cnt, const double* stats,
@@ -59,7 +59,7 @@ __device__ __forceinline__ void fin_sample(int64_t row, int lane, int phase) {
 }
 constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps eight positives per anchor in registers / scratch per pass
 // list capacity of the tensor-core pair kernel for a class bound: 8, or the next multiple of 8 (at most 64) --
-// longer lists are walked eight slots per pass over a tile (pair_tc_kernel<..., kBig>)
+// longer lists are sorted and binary-searched per element (pair_tc_kernel<..., kBig>)
 static int tc_list_cap(int max_positives) { return max_positives <= kTcBwdMaxPos ? kTcBwdMaxPos : (max_positives + 7) / 8 * 8; }
 // EN_BATCH_ALL_CUDA_CORE=1 sends classes with more than 8 positives per anchor to the CUDA-core tile kernel of
 // round 1 (kept as an independent implementation for the tests to compare against)
@@ -1236,7 +1236,8 @@ __device__ __forceinline__ void exact_d2x4(const float* __restrict__ e, int d, i
 __global__ void collect_positives_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels,
                                          int64_t B, int d, int squared, int cap, float* __restrict__ pos_d,
                                          int32_t* __restrict__ pos_j, int32_t* __restrict__ pos_n,
-                                         int32_t* __restrict__ status, int64_t rows_padded) {
+                                         int32_t* __restrict__ status, int64_t rows_padded,
+                                         double* __restrict__ pos_pre = nullptr) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) {
@@ -1299,6 +1300,44 @@ __global__ void collect_positives_kernel(const float* __restrict__ emb, const in
     if (lane < 4 && s0 + lane < n) {
       const double v = lane == 0 ? d2[0] : lane == 1 ? d2[1] : lane == 2 ? d2[2] : d2[3];
       pos_d[row * cap + s0 + lane] = static_cast<float>(squared ? v : sqrt(v));
+    }
+  }
+  // Lists for the large-class pair kernel (pos_pre given): ordered by DECREASING distance (ties: ascending slot), so
+  // that the hinges D_ap + m - D_an > 0 of a given negative are active for a PREFIX of the list, whose length a
+  // binary search finds; pos_pre[s] = D_ap(0) + ... + D_ap(s) in float64 turns the hinge sum of that prefix into
+  // one lookup.  Slot order carries no other meaning (pos_j / pos_cnt follow; "i in j's list" lookups search).
+  if (pos_pre != nullptr) {
+    __syncwarp();
+    float dv[2];
+    int jv[2], rank[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = lane + 32 * h;
+      dv[h] = s < n ? pos_d[row * cap + s] : -INFINITY;
+      jv[h] = s < n ? mine_j[s] : -1;
+    }
+    for (int t = 0; t < n; ++t) {
+      const float dt = __shfl_sync(0xffffffffu, t < 32 ? dv[0] : dv[1], t & 31);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int s = lane + 32 * h;
+        rank[h] += (dt > dv[h] || (dt == dv[h] && t < s)) ? 1 : 0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (lane + 32 * h < n) {
+        pos_d[row * cap + rank[h]] = dv[h];
+        mine_j[rank[h]] = jv[h];
+      }
+    __syncwarp();
+    if (lane == 0) {  // n <= 64 sequential float64 additions: a fixed order
+      double run = 0.0;
+      for (int s = 0; s < n; ++s) {
+        run += static_cast<double>(pos_d[row * cap + s]);
+        pos_pre[row * cap + s] = run;
+      }
     }
   }
   // unused slots hold -inf ("never the harder positive"): readers that walk whole lists need no count check
@@ -1976,7 +2015,8 @@ int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int
 
 // ------------------------------------------------------------------------------------------ batch-all
 static size_t pos_bytes(int64_t B, int cap) {
-  return align_up(static_cast<size_t>(B) * cap * 4) * 3 + align_up(static_cast<size_t>(B) * 4) + align_up(4);
+  return align_up(static_cast<size_t>(B) * cap * 4) * 3 + align_up(static_cast<size_t>(B) * 4) + align_up(4) +
+         (cap > kTcBwdMaxPos ? align_up(static_cast<size_t>(B) * cap * 8) : 0);  // + float64 prefix sums (large classes)
 }
 
 size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives) {
@@ -1996,6 +2036,7 @@ struct PosLists {
   int32_t* pos_cnt;
   int32_t* pos_n;
   int32_t* status;
+  double* pos_pre;  // large classes only (cap > 8): prefix sums of the sorted distances
 };
 
 static PosLists take_pos(Workspace& w, int64_t B, int cap) {
@@ -2005,6 +2046,7 @@ static PosLists take_pos(Workspace& w, int64_t B, int cap) {
   p.pos_cnt = w.take<int32_t>(static_cast<size_t>(B) * cap);
   p.pos_n = w.take<int32_t>(B);
   p.status = w.take<int32_t>(1);
+  p.pos_pre = cap > kTcBwdMaxPos ? w.take<double>(static_cast<size_t>(B) * cap) : nullptr;
   return p;
 }
 
@@ -2062,7 +2104,7 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
   collect_positives_kernel<<<static_cast<unsigned>((Bp * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp);
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp, tensor ? pl.pos_pre : nullptr);
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   if (tensor) {
@@ -2070,7 +2112,7 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
     // row-sum term and the sparse positive pairs and applies gloss / #positive triplets
     void* rest = w.base + w.off;
     PairTcFinish fin;
-    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, cap,
+    if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_pre, pl.pos_n, pl.pos_cnt, cap,
                                 nullptr, nullptr, gemb, &fin, rest, ws_bytes - w.off, st))
       return rc;
     return pair_tc_finish(fin, emb, B, d, cap, squared, pl.pos_d, pl.pos_j, pl.pos_n, pl.pos_cnt, stats, gloss, gemb, st);
@@ -2122,13 +2164,13 @@ int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int
   if (!w.ok()) return fail(EN_ERR_WORKSPACE, "en_batch_all_fwd_bwd: workspace too small or misaligned");
   EN_CUDA(cudaMemsetAsync(pl.status, 0, 4, st));
   collect_positives_kernel<<<static_cast<unsigned>((Bp * 32 + 255) / 256), 256, 0, st>>>(
-      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp);
+      emb, labels, B, d, squared, cap, pl.pos_d, pl.pos_j, pl.pos_n, pl.status, Bp, pl.pos_pre);
   EN_LAUNCHED("collect_positives_kernel");
   EN_CUDA(cudaMemsetAsync(pl.pos_cnt, 0, static_cast<size_t>(B) * cap * 4, st));
   EN_CUDA(cudaMemsetAsync(partial, 0, static_cast<size_t>(B) * ppr * sizeof(PairPartial), st));
   void* rest = w.base + w.off;
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_n, pl.pos_cnt, cap, nullptr,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 0, squared, margin, 1.f, pl.pos_d, pl.pos_pre, pl.pos_n, pl.pos_cnt, cap, nullptr,
                               partial, gemb, &fin, rest, ws_bytes - w.off, st))
     return rc;
   if (int rc = launch_pair_reduce(partial, static_cast<int64_t>(B) * ppr, pl.pos_n, B, 0, out, stats, st, pl.status))
@@ -2183,7 +2225,7 @@ int en_contrastive_allpairs_bwd(const float* emb, const int32_t* labels, int64_t
     return fail(EN_ERR_WORKSPACE, "en_contrastive_allpairs_bwd: workspace too small");
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, 0, nullptr, nullptr, gemb,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, gemb,
                               &fin, ws, ws_bytes, as_stream(stream)))
     return rc;
   return pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb,
@@ -2206,7 +2248,7 @@ int en_contrastive_allpairs_fwd_bwd(const float* emb, const int32_t* labels, int
   const float scale = static_cast<float>(4.0 / (static_cast<double>(B) * static_cast<double>(B - 1)));
   void* rest = w.base + w.off;
   PairTcFinish fin;
-  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, 0, nullptr, partial, gemb,
+  if (int rc = pair_tc_launch(emb, labels, B, d, 1, 0, 0.f, scale, nullptr, nullptr, nullptr, nullptr, 0, nullptr, partial, gemb,
                               &fin, rest, ws_bytes - w.off, st))
     return rc;
   if (int rc = pair_tc_finish(fin, emb, B, d, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, gloss, gemb, st))

@@ -60,7 +60,7 @@ constexpr int EPI_WARPS = 4 * EPI_Q;
 constexpr int CTRL_WARPS = 3;            // warp 0: GEMM1 operand TMA, warp 1: MMA issuer, warp 2: E^T (GEMM2) TMA
 constexpr int NUM_THREADS = 32 * (CTRL_WARPS + EPI_WARPS);
 constexpr int MAXP = 8;                 // positives per anchor held in registers per pass over a tile
-constexpr int MAXP_BIG = 64;            // kBig: lists of up to 64 positives, taken eight at a time (cap / 8 passes)
+constexpr int MAXP_BIG = 64;            // kBig: sorted lists of up to 64 slots, binary-searched per element
 constexpr int WARP_SCR = 128 + 128 + 32 * MAXP * 4;  // per warp, for its 32 columns: norms | labels | positives lists
 constexpr int SMEM_BYTES = G1_STAGES * G1_STAGE_BYTES + ET_STAGES * ET_STAGE_BYTES + 256 + EPI_WARPS * WARP_SCR +
                            BM * EPI_Q * 4;
@@ -85,6 +85,7 @@ struct Params {
   const int32_t* labels;
   const float* norms;
   const float* pos_d;     // [B rounded up to whole tiles][cap] (batch-all), -inf past each list's end
+  const double* pos_pre;  // kBig: [..][cap] float64 prefix sums of the lists, which are sorted by decreasing distance
   const int32_t* pos_n;   // [B]
   int32_t* pos_cnt;       // [B][cap] out: active negatives per (anchor, positive slot)
   int cap;                // list capacity: MAXP, or a multiple of 8 up to MAXP_BIG (kBig)
@@ -138,10 +139,10 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 // kMode: 0 = batch-all, 1 = contrastive (template parameter so that each instantiation carries only its own
 // coefficient code: both together overflowed the instruction cache, ncu r1: stall_no_instruction 5.4 / issue).
 // kLoss: also accumulate the forward loss.  kG1Bf16: GEMM1 on BF16 planes (backward-only contrastive).
-// kBig (batch-all only): classes with more than MAXP positives per anchor.  The positives lists (row anchor's and
-// column anchors') are taken eight at a time: cap / 8 passes over the tile's S values, the per-element triplet counts
-// accumulate in registers, the per-(anchor, positive) counts in a shared-memory table that takes the place of the
-// second E^T stage (the epilogue is several times longer than GEMM2 here, so GEMM2's operand ring can be one deep).
+// kBig (batch-all only): classes with more than MAXP positives per anchor.  The positives lists (sorted by
+// decreasing distance) are binary-searched per element; the per-(anchor, positive) counts live in a shared-memory
+// histogram that takes the place of the second E^T stage (the epilogue is longer than GEMM2 here, so GEMM2's
+// operand ring can be one deep).
 template <int kMode, bool kLoss, bool kG1Bf16, bool kBig = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -159,8 +160,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int n_items = p.tiles * p.n_wide * p.n_jparts;
   static_assert(!kBig || kMode == 0, "kBig is a batch-all variant");
   constexpr int kEtStages = kBig ? 1 : ET_STAGES;
-  uint32_t* slot_cnt = reinterpret_cast<uint32_t*>(et + ET_STAGE_BYTES);  // kBig: [MAXP_BIG][BM] active negatives
-  static_assert(MAXP_BIG * BM * 4 <= ET_STAGE_BYTES, "the slot-count table replaces one E^T stage");
+  // kBig shared-memory plan: the second E^T stage holds the row anchors' sorted lists, transposed [slot][row in tile]
+  // (conflict-free for the per-lane binary search); the per-warp scratch shrinks to its norms / labels part (256 B
+  // per warp: the column lists are read from global memory) and its remainder holds the histogram of prefix lengths,
+  // [slot][row pair] with two 16-bit counters per word (a counter sees at most the item's columns: B <= 65535).
+  float* row_lists = reinterpret_cast<float*>(et + ET_STAGE_BYTES);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(warp_scr + EPI_WARPS * 256);
+  static_assert(MAXP_BIG * BM * 4 <= ET_STAGE_BYTES, "the row lists replace one E^T stage");
+  static_assert(EPI_WARPS * 256 + MAXP_BIG * (BM / 2) * 4 <= EPI_WARPS * WARP_SCR, "histogram fits the freed scratch");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_hi);
@@ -307,7 +314,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue warps: loss, C, then the gradient slice
     const int quarter = warp & 3, cq = (warp - CTRL_WARPS) >> 2;  // TMEM lane quarter = warp id % 4; column chunk
-    uint8_t* ws = warp_scr + (warp - CTRL_WARPS) * WARP_SCR;
+    uint8_t* ws = warp_scr + (warp - CTRL_WARPS) * (kBig ? 256 : WARP_SCR);
     float* wf = reinterpret_cast<float*>(ws);
     int32_t* wi = reinterpret_cast<int32_t*>(ws + 128);
     float* wpos = reinterpret_cast<float*>(ws + 256);  // [32 columns][MAXP], margin added, -inf padded
@@ -338,9 +345,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       // 256 gradient columns): the other groups skip that arithmetic
       const bool full = it.wide == 0;
       if (kBig) {
-        // the four warps that share a row (one per column chunk) clear its slot counts, a quarter each
-        if (full)
-          for (int s = cq; s < p.cap; s += EPI_Q) slot_cnt[s * BM + quarter * 32 + lane] = 0u;
+        // clear the histogram; the four warps that share a row (one per column chunk) stage its list, a quarter each
+        for (int i = (warp - CTRL_WARPS) * 32 + lane; i < MAXP_BIG * (BM / 2); i += EPI_WARPS * 32) hist[i] = 0u;
+        for (int s = cq; s < p.cap; s += EPI_Q)
+          row_lists[s * BM + quarter * 32 + lane] = row_ok ? __ldg(p.pos_d + row * p.cap + s) : -INFINITY;
         ptx::named_bar_sync(1, EPI_WARPS * 32);
       }
       double rowsum = 0.0, loss_sum = 0.0;
@@ -370,23 +378,28 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
         __syncwarp();
         if constexpr (kBig) {
-          // ---- lists longer than eight.  Eight elements per trip of a rolled loop, as in the short-list path; inside
-          // a trip the lists are walked eight slots at a time (rolled): the row anchor's slots from its list in
-          // global memory (L1), the column anchors' slots likewise (one address per warp and element: a broadcast).
-          // The per-(anchor, positive) counts go to the shared-memory table, eight adds per trip and group.
+          // ---- lists longer than eight (collect_positives_kernel sorted them by DECREASING distance and padded them
+          // with -inf): for a negative at distance dn the active hinges D_ap + m - dn > 0 are a PREFIX of the
+          // anchor's list, so a binary search (<= 6 steps over <= 64 slots) replaces one compare per slot -- once in
+          // the row anchor's list (shared memory, [slot][row]: conflict free) and once in the column anchor's (global
+          // memory: one list per warp and element).  (A two-level 4 x 16 search -- two dependent loads instead of
+          // six, but 2.5x the instructions -- measured slower: 1.12 vs 1.01 ms per 64 x 64 step.)  The prefix length L feeds everything: the pair coefficient (L_row + L_col), the loss
+          // (float64 prefix sum of the list: pre[L-1] + L (m - dn)), and the per-(anchor, positive) counts (slots
+          // 0 .. L-1 each gain one: a histogram over L in shared memory, suffix-summed when the item ends).
+          // Eight elements per trip of a rolled loop, as in the short-list path.
           const int64_t col0 = static_cast<int64_t>(J) * BN + cq * 32;
           const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
-          const int n_groups = p.cap >> 3;
-          // lists are padded with -inf up to cap (collect_positives_kernel), so no slot needs a count check
-          const float* row_list = p.pos_d + (row_ok ? row : 0) * p.cap;
-          float chunk_sum = 0.f, chunk_loss = 0.f;
+          const int cap = p.cap;
+          const float* row_list = row_lists + quarter * 32 + lane;  // [slot][row in tile]: stride BM between slots
+          const double* row_pre = p.pos_pre + (row_ok ? row : 0) * cap;
+          const int first = cap >= 32 ? 32 : 16;  // largest power of two <= cap (16, 24 .. 64): L < 2 * first covers every list
+          float chunk_sum = 0.f;
+          double chunk_loss = 0.0;
           unsigned np_tile = 0;
 #pragma unroll 1
           for (int jj = 0; jj < 32; jj += 8) {
-            float dn8[8], sf8[8], cnt8[8];
-            // (the lists cover whole tiles: columns past B have empty ones, and their dn is +inf anyway)
-            const float* col_lists = p.pos_d + (col0 + jj) * p.cap;
-            const int col_step = p.cap;
+            const float* col_lists = p.pos_d + (col0 + jj) * cap;  // lists cover whole tiles (empty past B)
+            float cv8[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int j = jj + u;
@@ -394,60 +407,28 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const float d2 = fmaxf(na + wf[j] - 2.f * w[u], 0.f);
               const float rs = d2 > 1e-30f ? rsqrt_ftz(d2) : 0.f;
               const bool isneg = ok && wi[j] != la;
-              dn8[u] = isneg ? (p.squared ? d2 : d2 * rs) : INFINITY;
-              sf8[u] = p.squared ? 2.f : rs;
-              cnt8[u] = 0.f;
+              const float dn = isneg ? (p.squared ? d2 : d2 * rs) : INFINITY;
+              const float* cl = col_lists + u * cap;
+              int lr = 0, lc = 0;  // prefix lengths: slots [0, lr) of the row anchor, [0, lc) of the column anchor
+#pragma unroll
+              for (int step = 32; step >= 1; step >>= 1) {
+                if (step <= first) {
+                  const int ir = lr + step - 1, ic = lc + step - 1;
+                  const float tr = ir < cap ? row_list[ir * BM] : -INFINITY;
+                  const float tcn = ic < cap ? __ldg(cl + ic) : -INFINITY;
+                  lr += ((tr + p.margin) - dn > 1e-16f) ? step : 0;
+                  lc += ((tcn + p.margin) - dn > 1e-16f) ? step : 0;
+                }
+              }
+              if (full && lr > 0) {
+                atomicAdd(&hist[(lr - 1) * (BM / 2) + ((quarter * 32 + lane) >> 1)], (lane & 1) ? 65536u : 1u);
+                np_tile += static_cast<unsigned>(lr);
+                if (kLoss)
+                  chunk_loss += __ldg(row_pre + lr - 1) +
+                                static_cast<double>(lr) * (static_cast<double>(p.margin) - static_cast<double>(dn));
+              }
+              cv8[u] = -static_cast<float>(lr + lc) * cs * (p.squared ? 2.f : rs);  // 0 where the pair is no negative pair
             }
-#pragma unroll 1
-            for (int g = 0; g < n_groups; ++g) {
-              float pi8[8], cs8[8];
-              {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(row_list + g * 8));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(row_list + g * 8 + 4));
-                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                  pi8[s] = v[s] + p.margin;
-                  cs8[s] = 0.f;
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float dn = dn8[u];
-                // the column anchor's slots 8g .. 8g+7: one address per warp (a broadcast load)
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(col_lists + u * col_step + g * 8));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(col_lists + u * col_step + g * 8 + 4));
-                float cnt = 0.f;
-                if (full) {
-#pragma unroll
-                  for (int s = 0; s < 8; ++s) {
-                    const float t = pi8[s] - dn;
-                    const float act = t > 1e-16f ? 1.f : 0.f;
-                    cnt += act;
-                    cs8[s] += act;
-                    if (kLoss) chunk_loss += fmaxf(t, 0.f);
-                  }
-                } else {
-#pragma unroll
-                  for (int s = 0; s < 8; ++s) cnt += (pi8[s] - dn) > 1e-16f ? 1.f : 0.f;
-                }
-                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                for (int s = 0; s < 8; ++s) cnt += (qv[s] + p.margin) - dn > 1e-16f ? 1.f : 0.f;
-                cnt8[u] += cnt;
-              }
-              if (full) {
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                  const unsigned c = static_cast<unsigned>(cs8[s]);  // exact small integers
-                  np_tile += c;
-                  if (c != 0u) atomicAdd(&slot_cnt[(g * 8 + s) * BM + quarter * 32 + lane], c);
-                }
-              }
-            }
-            float cv8[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cv8[u] = -cnt8[u] * cs * sf8[u];  // the count is 0 where the pair is no negative pair
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -467,7 +448,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           }
           np_big += np_tile;
           rowsum += static_cast<double>(chunk_sum);
-          if (kLoss) loss_sum += static_cast<double>(chunk_loss);
+          if (kLoss) loss_sum += chunk_loss;
         } else {
           const int c = cq;
           const int64_t col0 = static_cast<int64_t>(J) * BN + c * 32;
@@ -592,11 +573,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       // made every load / atomic of a warp touch 32 different rows: ncu r2, 44 % of the kernel's stall samples.
       rowsum_x[cq * BM + quarter * 32 + lane] = static_cast<float>(rowsum);
       ptx::named_bar_sync(1, EPI_WARPS * 32);
-      if (kBig && it.wide == 0 && row_ok) {
-        // every warp's shared-memory adds of this item are done: the four warps of a row publish a quarter each
-        for (int s = cq; s < npi; s += EPI_Q) {
-          const unsigned c = slot_cnt[s * BM + quarter * 32 + lane];
-          if (c != 0u) atomicAdd(&p.pos_cnt[row * p.cap + s], static_cast<int>(c));
+      if (kBig && it.wide == 0 && row_ok && cq == 0) {
+        // every warp's shared-memory adds of this item are done.  hist[L-1] counted the negatives whose active
+        // prefix has length L: positive s is active for every L > s, i.e. its count is the suffix sum from s on.
+        unsigned run = 0;
+        for (int s = npi - 1; s >= 0; --s) {
+          const uint32_t two = hist[s * (BM / 2) + ((quarter * 32 + lane) >> 1)];
+          run += (lane & 1) ? (two >> 16) : (two & 0xFFFFu);
+          if (run != 0u) atomicAdd(&p.pos_cnt[row * p.cap + s], static_cast<int>(run));
         }
       }
       if (it.wide == 0 && cq == 0 && row_ok) {
@@ -809,10 +793,15 @@ int pair_tc_partials_per_row(int64_t B, int d) {
 // gemb receives -(C.E) and `fin` the pointers pair_tc_finish() needs to turn it into the gradient (the caller may
 // reduce the loss partials in between: batch-all's scale 1 / #positive triplets comes out of that reduction).
 int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, int mode, int squared, float margin,
-                   float coef_scale, const float* pos_d, const int32_t* pos_n, int32_t* pos_cnt, int cap,
-                   const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
+                   float coef_scale, const float* pos_d, const double* pos_pre, const int32_t* pos_n, int32_t* pos_cnt,
+                   int cap, const double* stats, PairPartial* partial, float* gemb, PairTcFinish* fin, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
   if (int rc = check_sm100()) return rc;
+  if (mode == 0 && cap > ptc::MAXP && pos_pre == nullptr)
+    return fail(EN_ERR_ARG, "pair kernel: lists of more than %d slots need their prefix sums", ptc::MAXP);
+  if (mode == 0 && cap > ptc::MAXP && B > 65535)
+    return fail(EN_ERR_ARG, "pair kernel: classes of more than %d rows are supported up to 65535 rows per batch",
+                ptc::MAXP + 1);
   if (mode == 0 && !(cap == ptc::MAXP || (cap > ptc::MAXP && cap <= ptc::MAXP_BIG && cap % 8 == 0)))
     return fail(EN_ERR_ARG, "pair kernel: list capacity %d (8, or a multiple of 8 up to %d)", cap, ptc::MAXP_BIG);
   if (!ws || ws_bytes < pair_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair kernel: workspace too small");
@@ -848,7 +837,7 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
       tc::make_plane_tmap_bf16(&teh, et_hi, g.rows_t, g.bpad) || tc::make_plane_tmap_bf16(&tel, et_lo, g.rows_t, g.bpad))
     return fail(EN_ERR_DRIVER, "pair kernel: cuTensorMapEncodeTiled failed");
   ptc::Params p;
-  p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_n = pos_n; p.pos_cnt = pos_cnt; p.cap = cap;
+  p.labels = labels; p.norms = norms; p.pos_d = pos_d; p.pos_pre = pos_pre; p.pos_n = pos_n; p.pos_cnt = pos_cnt; p.cap = cap;
   p.gemb = gemb; p.rowsum = rowsum; p.partial = partial; p.B = B; p.d = d;
   p.tiles = g.tiles; p.n_wide = g.n_wide; p.n_jparts = g.n_jparts; p.tiles_per_part = g.tiles_per_part;
   p.kblocks = dpad / (g1_bf16 ? tc::BK16 : tc::BK); p.squared = squared; p.margin = margin; p.coef_scale = coef_scale; p.stats = stats;
