@@ -58,9 +58,9 @@ __device__ __forceinline__ void fin_sample(int64_t row, int lane, int phase) {
 #endif
 }
 constexpr int kTcBwdMaxPos = 8;  // pair_tc_kernel keeps eight positives per anchor in registers / scratch per pass
-// list capacity of the tensor-core pair kernel for a class bound: 8, or the next multiple of 8 (at most 64) --
-// longer lists are sorted and binary-searched per element (pair_tc_kernel<..., kBig>)
-static int tc_list_cap(int max_positives) { return max_positives <= kTcBwdMaxPos ? kTcBwdMaxPos : (max_positives + 7) / 8 * 8; }
+// list capacity of the tensor-core pair kernel for a class bound: 8, or 64 -- longer lists are sorted, padded to 64
+// slots and binary-searched per element with constant strides (pair_tc_kernel<..., kBig>)
+static int tc_list_cap(int max_positives) { return max_positives <= kTcBwdMaxPos ? kTcBwdMaxPos : 64; }
 // EN_BATCH_ALL_CUDA_CORE=1 sends classes with more than 8 positives per anchor to the CUDA-core tile kernel of
 // round 1 (kept as an independent implementation for the tests to compare against)
 static bool cuda_core_bwd_requested() {

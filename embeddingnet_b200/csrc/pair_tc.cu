@@ -347,8 +347,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       if (kBig) {
         // clear the histogram; the four warps that share a row (one per column chunk) stage its list, a quarter each
         for (int i = (warp - CTRL_WARPS) * 32 + lane; i < MAXP_BIG * (BM / 2); i += EPI_WARPS * 32) hist[i] = 0u;
-        for (int s = cq; s < p.cap; s += EPI_Q)
-          row_lists[s * BM + quarter * 32 + lane] = row_ok ? __ldg(p.pos_d + row * p.cap + s) : -INFINITY;
+        for (int s = cq; s < MAXP_BIG; s += EPI_Q)  // (+ margin: one add less per search step; -inf stays -inf)
+          row_lists[s * BM + quarter * 32 + lane] = row_ok ? __ldg(p.pos_d + row * MAXP_BIG + s) + p.margin : -INFINITY;
         ptx::named_bar_sync(1, EPI_WARPS * 32);
       }
       double rowsum = 0.0, loss_sum = 0.0;
@@ -389,10 +389,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           // Eight elements per trip of a rolled loop, as in the short-list path.
           const int64_t col0 = static_cast<int64_t>(J) * BN + cq * 32;
           const bool interior = row_ok && (col0 + 32 <= p.B) && (col0 != row - lane);
-          const int cap = p.cap;
+          constexpr int cap = MAXP_BIG;  // long lists always have 64 slots (-inf padded): constant strides, no bound checks
           const float* row_list = row_lists + quarter * 32 + lane;  // [slot][row in tile]: stride BM between slots
           const double* row_pre = p.pos_pre + (row_ok ? row : 0) * cap;
-          const int first = cap >= 32 ? 32 : 16;  // largest power of two <= cap (16, 24 .. 64): L < 2 * first covers every list
           float chunk_sum = 0.f;
           double chunk_loss = 0.0;
           unsigned np_tile = 0;
@@ -411,14 +410,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const float* cl = col_lists + u * cap;
               int lr = 0, lc = 0;  // prefix lengths: slots [0, lr) of the row anchor, [0, lc) of the column anchor
 #pragma unroll
-              for (int step = 32; step >= 1; step >>= 1) {
-                if (step <= first) {
-                  const int ir = lr + step - 1, ic = lc + step - 1;
-                  const float tr = ir < cap ? row_list[ir * BM] : -INFINITY;
-                  const float tcn = ic < cap ? __ldg(cl + ic) : -INFINITY;
-                  lr += ((tr + p.margin) - dn > 1e-16f) ? step : 0;
-                  lc += ((tcn + p.margin) - dn > 1e-16f) ? step : 0;
-                }
+              for (int step = 32; step >= 1; step >>= 1) {  // at most 63 positives: slot 63 is always padding
+                const float tr = row_list[(lr + step - 1) * BM];           // margin already added
+                const float tcn = __ldg(cl + lc + step - 1) + p.margin;
+                lr += (tr - dn > 1e-16f) ? step : 0;
+                lc += (tcn - dn > 1e-16f) ? step : 0;
               }
               if (full && lr > 0) {
                 atomicAdd(&hist[(lr - 1) * (BM / 2) + ((quarter * 32 + lane) >> 1)], (lane & 1) ? 65536u : 1u);
@@ -784,7 +780,7 @@ int pair_tc_partials_per_row(int64_t B, int d) {
   return ptc::geometry(B, d, sms > 0 ? sms : 148).n_jparts * ptc::EPI_Q;
 }
 
-// mode 0 = batch-all (pos_* describe lists with capacity `cap`: 8, or a multiple of 8 up to 64 for large classes),
+// mode 0 = batch-all (pos_* describe lists with capacity `cap`: 8, or 64 for large classes -- sorted, -inf padded),
 // mode 1 = all-pairs contrastive.
 // partial != nullptr: also accumulate the forward loss (PairPartial[B][pair_tc_partials_per_row()]).
 // coef_scale multiplies every pair coefficient (contrastive: 4 / (B (B-1)), batch-all: 1); stats (optional, device):
@@ -802,8 +798,8 @@ int pair_tc_launch(const float* emb, const int32_t* labels, int64_t B, int d, in
   if (mode == 0 && cap > ptc::MAXP && B > 65535)
     return fail(EN_ERR_ARG, "pair kernel: classes of more than %d rows are supported up to 65535 rows per batch",
                 ptc::MAXP + 1);
-  if (mode == 0 && !(cap == ptc::MAXP || (cap > ptc::MAXP && cap <= ptc::MAXP_BIG && cap % 8 == 0)))
-    return fail(EN_ERR_ARG, "pair kernel: list capacity %d (8, or a multiple of 8 up to %d)", cap, ptc::MAXP_BIG);
+  if (mode == 0 && cap != ptc::MAXP && cap != ptc::MAXP_BIG)
+    return fail(EN_ERR_ARG, "pair kernel: list capacity %d (must be %d or %d)", cap, ptc::MAXP, ptc::MAXP_BIG);
   if (!ws || ws_bytes < pair_tc_ws_bytes(B, d)) return fail(EN_ERR_WORKSPACE, "pair kernel: workspace too small");
   Workspace w(ws, ws_bytes);
   const int sms = device_sm_count();
