@@ -521,23 +521,24 @@ def main():
     e2e_auto_dt = timed_pipeline(compute_autograd)
     e2e_py_dt = timed_pipeline(compute_cabi)
 
-    # The same schedule inside the library: en_bh_host_pipe_submit / _wait take HOST pointers (the reference-facing
-    # call for a loop that owns host buffers); per step the host issues ~11 driver calls instead of ~0.2 ms of Python.
+    # The same work inside the library: en_bh_host_pipe_submit / _wait take HOST pointers (the reference-facing call
+    # for a loop that owns host buffers) and make the stage hand-offs on the calling thread (csrc/host_pipe.cu).
     from embeddingnet_b200.fused import BatchHardHostPipeline
-    pipe = BatchHardHostPipeline(B, D, margin=MARGIN, depth=DEPTH)
-    p_grad = [BatchHardHostPipeline.pinned((B, D)) for _ in range(DEPTH)]
-    p_loss = [BatchHardHostPipeline.pinned((1,)) for _ in range(DEPTH)]
+    PD = 5  # slots; results are read four steps behind the newest submit
+    pipe = BatchHardHostPipeline(B, D, margin=MARGIN, depth=PD)
+    p_grad = [BatchHardHostPipeline.pinned((B, D)) for _ in range(PD)]
+    p_loss = [BatchHardHostPipeline.pinned((1,)) for _ in range(PD)]
 
     def host_pipe(n_steps):
         losses = []
-        for i in range(n_steps + DEPTH - 1):
+        for i in range(n_steps + PD - 1):
             if i < n_steps:
-                k = i % DEPTH
+                k = i % PD
                 pipe.submit(emb_h, lab_h, p_loss[k], p_grad[k])   # ticket == submit index (checked below)
-            j = i - (DEPTH - 1)
+            j = i - (PD - 1)
             if j >= 0:          # every step's loss is read on the host, in order, inside the timed region
                 pipe.wait(host_pipe.base + j)
-                losses.append(float(p_loss[j % DEPTH][0]))
+                losses.append(float(p_loss[j % PD][0]))
         host_pipe.base += n_steps
         return losses
 
@@ -553,16 +554,17 @@ def main():
     e2e_launches = launch_count() // K
     assert len(pl) == K and all(abs(x - loss_value) <= 1e-6 * max(1.0, abs(loss_value)) for x in pl), pl[:4]
     g_ref = stepper.step(emb, labels)[1]
-    assert torch.equal(p_grad[(K - 1) % DEPTH].to(dev), g_ref) or \
-        (p_grad[(K - 1) % DEPTH].to(dev) - g_ref).norm() <= 1e-6 * g_ref.norm()  # atomics: summation order only
+    assert torch.equal(p_grad[(K - 1) % PD].to(dev), g_ref) or \
+        (p_grad[(K - 1) % PD].to(dev) - g_ref).norm() <= 1e-6 * g_ref.norm()  # atomics: summation order only
     pipe.close()
     e2e = {"value": world * B * K / e2e_dt, "unit": "embeddings/s", "h2d_bytes_per_step": B * D * 4 + B * 4,
            "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": e2e_dt / K * 1e3,
            "api": "en_bh_host_pipe_submit / en_bh_host_pipe_wait (C ABI, HOST pointers: pinned embeddings + labels "
                   "in, loss + gradient out) through fused.BatchHardHostPipeline",
-           "schedule": "3 slots in flight inside the library over three CUDA streams (H2D | one CUDA graph of the 4 "
-                       "step kernels | D2H); every step copies its own inputs in and its gradient + loss out, every "
-                       "loss is read on the host in order",
+           "schedule": "5 slots inside the library over three CUDA streams (H2D | one CUDA graph of the 4 step kernels | "
+                       "D2H), stage hand-offs made by the calling thread inside submit / wait (no stream waits on "
+                       "another stream's event); every step copies its own inputs in and its gradient + loss out, "
+                       "every loss is read on the host in order, four steps behind the newest submit",
            "python_pipeline": {"value": world * B * K / e2e_py_dt, "ms_per_step": e2e_py_dt / K * 1e3,
                                "api": "fused.BatchHardStep.step (en_batch_hard_fwd_bwd on device buffers) with the "
                                       "same 3-stream schedule written in Python (host-bound: ~0.19 ms of "

@@ -4,11 +4,17 @@
 //
 // A pipe owns `depth` slots of device buffers (carved from the caller's device block), three streams (host->device |
 // compute | device->host) and, per slot, a CUDA graph of the en_batch_hard_fwd_bwd kernels captured once at creation
-// (device addresses of a slot never change, so neither do its tensor maps).  submit() enqueues one step and returns;
-// steps in different slots overlap: step i+1's upload and step i-1's download run under step i's kernels, which is
-// what keeps the PCIe link -- the bound of this call at 8.4 MB each way per 70 us of compute -- busy in both
-// directions.  Per submit the host issues ~11 driver calls and no tensor-map encodes (measured from Python with a
-// hand-rolled three-stream schedule: 0.19 ms of host time per step, more than the 0.176 ms the copies take).
+// (device addresses of a slot never change, so neither do its tensor maps).  Steps in different slots overlap: step
+// i+1's upload and step i-1's download run under step i's kernels, which is what keeps the PCIe link -- the bound of
+// this call at 8.4 MB each way per 65 us of compute -- busy in both directions.
+//
+// The hand-offs upload -> kernels -> download are made by the CALLING thread inside submit() / wait() (it waits for
+// the slot's event and then launches the next stage); no stream ever waits on another stream's event.  Measured on
+// the B200 box: with cudaStreamWaitEvent between the three streams a step takes 0.242 ms however the schedule is
+// expressed (tools/pipe_probe.cu: three streams, a stream per slot, lock step, chunked copies, a flag-polling
+// kernel: 0.217 - 0.233 ms with a 70 us sleep kernel in place of the step), with the hand-offs on the host 0.205 -
+// 0.213 ms (probe: 0.198; the copies alone, both directions at once: 0.176).  A helper thread polling the events
+// instead of the calling thread was slower than either (0.262 - 0.267 ms, tools/time_pipe.py A/B on one box).
 #include <new>
 #include "common.cuh"
 
@@ -28,6 +34,10 @@ struct Slot {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaEvent_t in_done = nullptr, cmp_done = nullptr, out_done = nullptr;
+  // host destinations of the step currently in this slot
+  float* h_loss = nullptr;
+  float* h_grad = nullptr;
+  int32_t *h_hp = nullptr, *h_hn = nullptr;
 };
 
 struct Pipe {
@@ -35,6 +45,8 @@ struct Pipe {
   int d = 0, depth = 0, device = 0;
   size_t ws_bytes = 0;
   int64_t next_ticket = 0;
+  int64_t launched = 0;      // tickets whose kernels have been launched
+  int64_t downloading = 0;   // tickets whose download has been issued
   int64_t kernels_per_step = 0;
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
   Slot slot[kMaxDepth];
@@ -150,6 +162,34 @@ int en_bh_host_pipe_create(int64_t B, int d, float margin, int squared, int soft
   return EN_OK;
 }
 
+// The stage hand-offs are made by the CALLING thread (no stream ever waits on another stream's event: see the file
+// header): launch the kernels of every ticket below `launch_upto` (each once its upload has landed) and issue the
+// download of every ticket below `download_upto` (each once its kernels have finished).
+static int drive(Pipe* p, int64_t launch_upto, int64_t download_upto) {
+  const size_t row_bytes = static_cast<size_t>(p->B) * p->d * sizeof(float), b4 = static_cast<size_t>(p->B) * 4;
+  if (launch_upto < download_upto) launch_upto = download_upto;
+  while (p->launched < launch_upto || p->downloading < download_upto) {
+    if (p->launched < launch_upto) {
+      Slot& s = p->slot[p->launched % p->depth];
+      EN_CUDA(cudaEventSynchronize(s.in_done));
+      EN_CUDA(cudaGraphLaunch(s.exec, p->s_cmp));
+      EN_CUDA(cudaEventRecord(s.cmp_done, p->s_cmp));
+      ++p->launched;
+    }
+    if (p->downloading < download_upto && p->downloading < p->launched) {
+      Slot& s = p->slot[p->downloading % p->depth];
+      EN_CUDA(cudaEventSynchronize(s.cmp_done));
+      EN_CUDA(cudaMemcpyAsync(s.h_grad, s.grad, row_bytes, cudaMemcpyDeviceToHost, p->s_out));
+      if (s.h_hp) EN_CUDA(cudaMemcpyAsync(s.h_hp, s.hp_idx, b4, cudaMemcpyDeviceToHost, p->s_out));
+      if (s.h_hn) EN_CUDA(cudaMemcpyAsync(s.h_hn, s.hn_idx, b4, cudaMemcpyDeviceToHost, p->s_out));
+      EN_CUDA(cudaMemcpyAsync(s.h_loss, s.loss, sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
+      EN_CUDA(cudaEventRecord(s.out_done, p->s_out));
+      ++p->downloading;
+    }
+  }
+  return EN_OK;
+}
+
 int en_bh_host_pipe_submit(void* pipe, const float* emb_host, const int32_t* labels_host, float* loss_host,
                            float* grad_host, int32_t* hp_idx_host, int32_t* hn_idx_host, int64_t* ticket_out) {
   Pipe* p = static_cast<Pipe*>(pipe);
@@ -158,23 +198,23 @@ int en_bh_host_pipe_submit(void* pipe, const float* emb_host, const int32_t* lab
   Slot& s = p->slot[t % p->depth];
   const size_t row_bytes = static_cast<size_t>(p->B) * p->d * sizeof(float), b4 = static_cast<size_t>(p->B) * 4;
   // the step that used this slot `depth` submits ago must have delivered its results before the slot is reused
-  if (t >= p->depth) EN_CUDA(cudaEventSynchronize(s.out_done));
+  if (t >= p->depth) {
+    if (int rc = drive(p, t - p->depth + 1, t - p->depth + 1)) return rc;
+    EN_CUDA(cudaEventSynchronize(s.out_done));
+  }
+  s.h_loss = loss_host;
+  s.h_grad = grad_host;
+  s.h_hp = hp_idx_host;
+  s.h_hn = hn_idx_host;
   EN_CUDA(cudaMemcpyAsync(s.emb, emb_host, row_bytes, cudaMemcpyHostToDevice, p->s_in));
   EN_CUDA(cudaMemcpyAsync(s.labels, labels_host, b4, cudaMemcpyHostToDevice, p->s_in));
   EN_CUDA(cudaEventRecord(s.in_done, p->s_in));
-  EN_CUDA(cudaStreamWaitEvent(p->s_cmp, s.in_done, 0));
-  EN_CUDA(cudaGraphLaunch(s.exec, p->s_cmp));
   launch_counter() += p->kernels_per_step;
-  EN_CUDA(cudaEventRecord(s.cmp_done, p->s_cmp));
-  EN_CUDA(cudaStreamWaitEvent(p->s_out, s.cmp_done, 0));
-  EN_CUDA(cudaMemcpyAsync(grad_host, s.grad, row_bytes, cudaMemcpyDeviceToHost, p->s_out));
-  if (hp_idx_host) EN_CUDA(cudaMemcpyAsync(hp_idx_host, s.hp_idx, b4, cudaMemcpyDeviceToHost, p->s_out));
-  if (hn_idx_host) EN_CUDA(cudaMemcpyAsync(hn_idx_host, s.hn_idx, b4, cudaMemcpyDeviceToHost, p->s_out));
-  EN_CUDA(cudaMemcpyAsync(loss_host, s.loss, sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
-  EN_CUDA(cudaEventRecord(s.out_done, p->s_out));
   p->next_ticket = t + 1;
   if (ticket_out) *ticket_out = t;
-  return EN_OK;
+  // with this step's upload queued: start the previous step's kernels (its upload has had a whole upload time) and
+  // the download of the step before that
+  return drive(p, t, t - 1);
 }
 
 int en_bh_host_pipe_wait(void* pipe, int64_t ticket) {
@@ -182,9 +222,10 @@ int en_bh_host_pipe_wait(void* pipe, int64_t ticket) {
   EN_REQUIRE(p != nullptr, "en_bh_host_pipe_wait: null pipe");
   EN_REQUIRE(ticket >= 0 && ticket < p->next_ticket, "en_bh_host_pipe_wait: ticket %lld was never issued",
              (long long)ticket);
-  // slot already reused: the submit that reused it synchronised on this step's out_done first (and the event now
+  // slot already reused: the submit that reused it waited for this step's download first (and the event now
   // belongs to the later step)
   if (ticket + p->depth <= p->next_ticket) return EN_OK;
+  if (int rc = drive(p, ticket + 1, ticket + 1)) return rc;
   EN_CUDA(cudaEventSynchronize(p->slot[ticket % p->depth].out_done));
   return EN_OK;
 }
@@ -192,9 +233,11 @@ int en_bh_host_pipe_wait(void* pipe, int64_t ticket) {
 int en_bh_host_pipe_destroy(void* pipe) {
   Pipe* p = static_cast<Pipe*>(pipe);
   if (!p) return EN_OK;
+  int rc = drive(p, p->next_ticket, p->next_ticket);  // everything submitted is carried through
   cudaError_t e = cudaSuccess;
   if (p->s_out) e = cudaStreamSynchronize(p->s_out);  // results of every submitted step are in host memory
   destroy(p);
+  if (rc) return rc;
   if (e != cudaSuccess) return cuda_fail(e, "en_bh_host_pipe_destroy");
   return EN_OK;
 }

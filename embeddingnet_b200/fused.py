@@ -49,10 +49,12 @@ class BatchHardHostPipeline:
     The reference computes its loss on whatever ``y_pred`` Keras hands it
     (embedding_net/losses_and_accuracies.py:26-42); this is the same call for a loop that owns host buffers::
 
-        pipe = BatchHardHostPipeline(B, d, margin=0.5)
-        t = pipe.submit(emb_h, labels_h, loss_h, grad_h)     # returns at once
+        pipe = BatchHardHostPipeline(B, d, margin=0.5, depth=5)
+        t = pipe.submit(emb_h, labels_h, loss_h, grad_h)     # queues the upload, advances the steps in flight
         ...                                                  # submit more steps (up to `depth` in flight)
         pipe.wait(t)                                         # loss_h / grad_h are now filled
+
+    Read results two or more steps behind the newest submit and the loop never stalls (``bench.py``: four behind).
 
     ``emb_h`` (B, d) float32, ``labels_h`` (B,) int32, ``loss_h`` 1 float32, ``grad_h`` (B, d) float32; buffers must
     stay untouched until ``wait`` returns.  Use ``pinned(...)`` for page-locked buffers (pageable memory works but

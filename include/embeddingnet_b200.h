@@ -154,11 +154,16 @@ int en_batch_hard_bwd(const float* emb, int64_t B, int d, int squared, const int
  * from the caller's device block (en_bh_host_pipe_device_bytes, 256-byte aligned), three internal streams
  * (upload | compute | download) and one CUDA graph of the en_batch_hard_fwd_bwd kernels per slot, so consecutive
  * steps overlap: the PCIe link, which bounds this call, stays busy in both directions.
- *   submit: enqueues one step and returns its ticket; blocks only when all `depth` slots are still in flight
- *           (then it waits for the oldest).  hp_idx_host / hn_idx_host (B,) int32 are optional (NULL = not wanted).
+ *   submit: enqueues one step's upload and returns its ticket.  The calling thread also makes the stage hand-offs
+ *           of the steps in flight (no stream waits on another stream's event: measured 15 % faster): before it
+ *           returns it launches the PREVIOUS step's kernels (waiting for that step's upload) and issues the download
+ *           of the step before that (waiting for its kernels), so in a steady loop it blocks for about one upload
+ *           time; it also waits for the oldest step when all `depth` slots are in flight.
+ *           hp_idx_host / hn_idx_host (B,) int32 are optional (NULL = not wanted).
  *           Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister); pageable memory is accepted
  *           but serialises the copies.  They must stay valid and untouched until wait(ticket) returns.
- *   wait:   returns once that step's outputs are in host memory.
+ *   wait:   carries that step through its remaining stages and returns once its outputs are in host memory
+ *           (waiting for the NEWEST ticket drains the pipe; a loop that reads results 2+ steps behind never stalls).
  * One pipe is driven by one thread at a time, with the device that was current at creation current. */
 size_t en_bh_host_pipe_device_bytes(int64_t B, int d, int depth);
 int en_bh_host_pipe_create(int64_t B, int d, float margin, int squared, int soft, int depth, void* device_mem,

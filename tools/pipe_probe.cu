@@ -18,6 +18,20 @@ __global__ void sleep_kernel(unsigned ns_total) {
   }
 }
 
+// waits until the copy engine has delivered generation `want` of the flag word (written by a 4-byte H2D copy queued
+// behind the data copy), then sleeps: the upload -> kernel dependency without any stream event
+__global__ void wait_flag_then_sleep(const volatile int* flag, int want, unsigned ns_total) {
+  while (*flag < want) __nanosleep(200);
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 >= ns_total) break;
+    __nanosleep(1000);
+  }
+}
+
 // grid-stride 16-byte copy (zero-copy upload / download when one side is mapped host memory)
 __global__ void copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -52,7 +66,13 @@ int main(int argc, char** argv) {
     CK(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
   }
   const size_t n16 = bytes / 16;
-  for (int variant = (argc > 2 ? 8 : 0); variant < 13; ++variant) {
+  int* h_gen;   // pinned generation words, one per step (each is copied once)
+  int* d_flag;
+  CK(cudaHostAlloc(&h_gen, 4096 * sizeof(int), cudaHostAllocDefault));
+  for (int i = 0; i < 4096; ++i) h_gen[i] = i + 1;
+  CK(cudaMalloc(&d_flag, 8 * sizeof(int)));
+  int gen = 0;
+  for (int variant = (argc > 2 ? 8 : 0); variant < 15; ++variant) {
     for (int kern_us : {0, 70}) {
       double t0 = 0;
       for (int i = -20; i < N; ++i) {
@@ -175,6 +195,25 @@ int main(int argc, char** argv) {
               CK(cudaEventRecord(out_done[kq], s_out));
             }
             break;
+          case 13:  // upload -> kernel through a flag the kernel polls (no event between them); download waits on an event
+          case 14:  // ... and the download is issued by the host once the kernel has finished (no device-side wait at all)
+            if (i == -20) { CK(cudaDeviceSynchronize()); CK(cudaMemset(d_flag, 0, 8 * sizeof(int))); gen = 0; }
+            CK(cudaMemcpyAsync(d_in[k], h_in, bytes, cudaMemcpyHostToDevice, s_in));
+            CK(cudaMemcpyAsync(d_flag + k, h_gen + gen, sizeof(int), cudaMemcpyHostToDevice, s_in));
+            wait_flag_then_sleep<<<1, 32, 0, s_cmp>>>(d_flag + k, gen + 1, kern_us * 1000);
+            ++gen;
+            CK(cudaEventRecord(cmp_done[k], s_cmp));
+            if (variant == 13) {
+              CK(cudaStreamWaitEvent(s_out, cmp_done[k], 0));
+              CK(cudaMemcpyAsync(h_out[k], d_out[k], bytes, cudaMemcpyDeviceToHost, s_out));
+              CK(cudaEventRecord(out_done[k], s_out));
+            } else if (i + 20 >= 1) {
+              const int kp = ((i - 1) % DEPTH + DEPTH) % DEPTH;
+              CK(cudaEventSynchronize(cmp_done[kp]));
+              CK(cudaMemcpyAsync(h_out[kp], d_out[kp], bytes, cudaMemcpyDeviceToHost, s_out));
+              CK(cudaEventRecord(out_done[kp], s_out));
+            }
+            break;
           case 7:  // zero-copy downloads only
             copy_kernel<<<64, 256, 0, s_out>>>((const float4*)d_out[k], (float4*)h_out[k], n16);
             CK(cudaEventRecord(out_done[k], s_out));
@@ -188,7 +227,8 @@ int main(int argc, char** argv) {
                                     "SM-kernel up, CE down", "CE uploads only", "SM-kernel uploads only",
                                     "SM-kernel downloads only", "lock step (up(i) starts with down(i-2))",
                                     "3 streams, copies in 4 chunks", "kernel in the upload stream",
-                                    "host-driven download", "host-driven kernel and download"};
+                                    "host-driven download", "host-driven kernel and download",
+                                    "flag-polling kernel, event download", "flag-polling kernel, host download"};
       printf("depth %d  kernel %2d us  %-38s  %.4f ms/step\n", DEPTH, kern_us, names[variant], dt);
     }
   }
