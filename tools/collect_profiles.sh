@@ -5,7 +5,10 @@
 #   r02_ncu_summary.md                                  tools/ncu_summary.py over every capture
 #   r02_sass_hot_<kernel>.txt                           tools/ncu_sass_hot.py: opcode mix, stall reasons, hottest lines
 set -u
-T=/tmp/en_prof; mkdir -p $T gpurun_out
+T=/tmp/en_prof; mkdir -p $T gpurun_out build
+# developer binaries (build/ is git-ignored): the PCIe / kernel overlap probe and the library variant with trace stamps
+[ -x build/pipe_probe ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/pipe_probe.cu -o build/pipe_probe
+[ -f build/lib_trace.so ] || python -c "from embeddingnet_b200 import build as b; b.build_variant('build/lib_trace.so', ['-DEN_FIN_TRACE'])"
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 700 --csv --log-file gpurun_out/r02_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --skip-knn --skip-cpu > /dev/null 2>&1
