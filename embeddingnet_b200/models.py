@@ -315,12 +315,19 @@ class BankKNNClassifier:
         bl = self._labels[self._offset:self._offset + n].contiguous()
         world, rank = self._world()
         if mode == "hardest":
-            # nearest row of another class; a candidate only if its loss is positive (dg:189-190)
-            d2, ids = self._search(a, 1, exclude_labels=al)
-            dist = torch.sqrt(d2[:, 0].to(torch.float32))
-            loss = (pos_d - dist[:, None]) + float(margin)
-            out = torch.where((loss > 0) & (pos_d >= 0) & (ids[:, :1] >= 0), ids[:, :1].expand(A, MS),
-                              torch.full_like(ids[:, :1].expand(A, MS), -1))
+            # The reference takes np.argmax of the FLOAT32 loss (d_ap - d_an) + margin over all negatives and keeps it
+            # if positive (dg:188-190, 235): float32 rounding can merge several nearest rows into one maximum, which
+            # argmax resolves to the lowest index.  The four nearest other-class rows (exact float64 d2, ascending
+            # (d2, id)) cover that: same float32 arithmetic per slot, lowest id among the equal maxima.
+            kk = 4
+            d2, ids = self._search(a, kk, exclude_labels=al)
+            dist = torch.sqrt(d2.to(torch.float32))                                  # (A, kk) float32; inf = no such row
+            loss = (pos_d[:, :, None] - dist[:, None, :]) + float(margin)            # (A, MS, kk), float32 left to right
+            idx = ids[:, None, :].expand(A, MS, kk)
+            tie = (loss == loss[:, :, :1]) & (idx >= 0)
+            pick = torch.where(tie, idx, torch.full_like(idx, torch.iinfo(torch.int64).max)).min(dim=2).values
+            ok = (loss[:, :, 0] > 0) & (pos_d >= 0) & (ids[:, :1] >= 0)
+            out = torch.where(ok, pick, torch.full_like(pick, -1))
             return out[:, :S].cpu().numpy()
         ws = workspace(lib.en_ws_bytes_mine_bank(A, d), dev, "mine_bank")
         counts = torch.zeros((A, MS, 2), dtype=torch.int32, device=dev)

@@ -372,6 +372,42 @@ def test_bank_mining_strategies_match_the_oracle(mode, precision):
     assert (want >= 0).mean() > 0.3  # the case is not vacuous
 
 
+def test_bank_mining_hardest_float32_ties_resolve_like_argmax():
+    """dg:188-190: np.argmax over the float32 loss.  Two other-class rows whose distances to the anchor differ in
+    float64 but round to the same float32 loss: the reference picks the LOWER index, not the float64-nearer row."""
+    from embeddingnet_b200.models import BankKNNClassifier
+
+    rs = np.random.RandomState(5)
+    d = 64
+    bank = rs.rand(400, d).astype(np.float32)
+    labels = (np.arange(400) % 20).astype(np.int32)
+    anchors = bank[[3, 50, 111]].copy()
+    a_lab = labels[[3, 50, 111]].copy()
+    for a_i, (near, lower) in enumerate(((300, 7), (390, 12), (201, 30))):
+        # `near` (higher id) sits very close to the anchor; `lower` (lower id) a hair farther: equal in float32
+        step = rs.randn(d).astype(np.float32)
+        step *= 0.05 / np.linalg.norm(step)
+        bank[near] = anchors[a_i] + step
+        bank[lower] = anchors[a_i] + step * np.float32(1.0 + 2e-8)
+        bank[lower, 0] = np.nextafter(bank[lower, 0], np.float32(10.0)) if bank[lower, 0] == bank[near, 0] else bank[lower, 0]
+        for r in (near, lower):
+            if labels[r] == a_lab[a_i]:
+                labels[r] = (labels[r] + 1) % 20
+    pos = (anchors + 0.3 * rs.randn(3, d).astype(np.float32))[:, None, :]
+    pos_d = np.sqrt(((anchors[:, None, :].astype(np.float64) - pos.astype(np.float64)) ** 2).sum(-1).astype(np.float32))
+    want, _ = O.mine_bank_modes(bank, labels, anchors, a_lab, pos_d, 0.5, "hardest")
+    clf = BankKNNClassifier(n_neighbors=1).fit_shard(bank, labels, 0, len(bank))
+    got = clf.mine_negatives(anchors, a_lab, positives=pos, margin=0.5, mode="hardest")
+    np.testing.assert_array_equal(got, want)
+    # the case really contains a float32 tie that the float64 order would resolve the other way
+    d64 = ((bank[None, :, :].astype(np.float64) - anchors[:, None, :].astype(np.float64)) ** 2).sum(-1)
+    flips = 0
+    for i in range(3):
+        neg = np.where(labels != a_lab[i])[0]
+        flips += int(neg[np.argmin(d64[i, neg])] != want[i, 0])
+    assert flips >= 1
+
+
 def test_bank_mining_counts_and_sharding_invariance():
     """Counts through the C ABI vs the oracle (ragged sizes, unused slots, un-normalised rows), and the two-shard
     protocol of SURVEY 8(e) emulated on one GPU: per-shard counts -> owner shard resolves the rank."""
