@@ -174,7 +174,7 @@ int en_bh_host_pipe_wait(void* pipe, int64_t ticket);
 int en_bh_host_pipe_destroy(void* pipe);
 
 /* Batch-all triplet loss: sum over valid (i,j,k) of max(D_ij - D_ik + margin, 0) / #{terms > 1e-16}.
- * out[0] = loss, out[1] = fraction of positive triplets.  max_positives >= largest class size - 1 (<= 64).
+ * out[0] = loss, out[1] = fraction of positive triplets.  max_positives >= largest class size - 1 (<= 63).
  * stats (3 doubles, device): hinge sum, #positive terms, #valid triplets -- kept for the backward. */
 size_t en_ws_bytes_batch_all(int64_t B, int d, int max_positives);
 int en_batch_all_fwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
@@ -186,8 +186,9 @@ int en_batch_all_bwd(const float* emb, const int32_t* labels, int64_t B, int d, 
  * callable inside the same train step, train.py:160-162): out / stats as en_batch_all_fwd, gemb (B, d) =
  * gloss[0] * d loss / d emb (gloss == NULL means 1).  Asynchronous (no host read-back): if a class turns out to have
  * more positives per anchor than max_positives, out / stats / gemb are filled with NaN and `overflow` (device int32,
- * optional) receives that count (0 when fine).  Classes with more than 8 positives per anchor take the two separate
- * passes internally (synchronous check, non-NULL gloss required). */
+ * optional) receives that count (0 when fine).  Classes with more than 8 positives per anchor (max_positives > 8)
+ * stay on the same fused tensor-core kernel: their positives lists are sorted, padded to 64 slots and searched per
+ * element; the lists then hold up to 64 entries, so overflow is only reported past that (B <= 65535 rows). */
 int en_batch_all_fwd_bwd(const float* emb, const int32_t* labels, int64_t B, int d, float margin, int squared,
                          int max_positives, float* out, double* stats, const float* gloss, float* gemb,
                          int32_t* overflow, void* ws, size_t ws_bytes, void* stream);
